@@ -1,0 +1,477 @@
+// C ABI implementation (include/sfmb200.h).  Host orchestration only: every
+// stage is a handful of kernel launches on the handle's stream into a
+// pre-allocated arena (the reference does ~21 cudaMalloc + ~19 cudaFree + >=4
+// device syncs per estimateE call, SfM/sfm.cu:94-236).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/sfmb200.h"
+#include "internal.cuh"
+
+using namespace sfmb200;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CK(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) return fail(SFMB200_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+#define CKL()                                                                        \
+    do {                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                         \
+        if (e_ != cudaSuccess) return fail(SFMB200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+struct sfmb200_handle {
+    DeviceState s;
+    cudaStream_t stream;
+    bool own_stream;
+    int device;
+    int compat;
+    int score_variant;
+    int tri_inliers_only;
+    // state of the last estimate
+    int H;            // hypotheses in the local slice
+    int h_begin;
+    float thr;
+    bool have_points, have_E, have_candidates, have_pose;
+    ScorePlan plan;
+    int64_t launches;
+    void* arena;
+};
+
+extern "C" {
+
+const char* sfmb200_last_error(void) { return g_err; }
+int sfmb200_version(void) { return 100; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_points, int max_hyp, sfmb200_t** out) {
+    if (!K || !Kinv || !out) return fail(SFMB200_ERR_ARG, "null argument%s");
+    if (pairs < 1 || max_points < 8 || max_hyp < 1) return fail(SFMB200_ERR_ARG, "pairs >= 1, max_points >= 8, max_hypotheses >= 1 required%s");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SFMB200_ERR_NODEVICE, "no CUDA device: sfmb200 has no CPU fallback%s");
+    }
+    sfmb200_handle* h = new (std::nothrow) sfmb200_handle();
+    if (!h) return fail(SFMB200_ERR_ARG, "out of host memory%s");
+    memset(h, 0, sizeof(*h));
+    CK(cudaGetDevice(&h->device));
+    DeviceState& s = h->s;
+    s.B = pairs;
+    s.n_max = max_points;
+    s.h_max = max_hyp;
+    s.n = 0;
+    s.n_stride = (int)align_up(max_points, SCORE_CHUNK);
+    s.h_stride = (int)align_up(max_hyp, 1024);
+    s.tiles_max = s.h_stride / 512;
+    memcpy(s.K, K, sizeof(float) * 9);
+    memcpy(s.Kinv, Kinv, sizeof(float) * 9);
+    // one arena, carved with 256-byte alignment
+    size_t B = pairs, off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_corr = carve(B * s.n_stride * sizeof(float4));
+    size_t o_dup = carve(B * s.n_stride * 2 * sizeof(float4));
+    size_t o_px = carve(B * s.n_stride * 4 * sizeof(float));
+    size_t o_ec = carve(B * 9 * (size_t)s.h_stride * sizeof(float));
+    size_t o_cnt = carve(B * (size_t)s.h_stride * sizeof(int));
+    size_t o_td = carve(B * (size_t)s.tiles_max * sizeof(int));
+    size_t o_best = carve(B * sizeof(unsigned long long));
+    size_t o_E = carve(B * 9 * sizeof(float));
+    size_t o_bi = carve(B * sizeof(int));
+    size_t o_bc = carve(B * sizeof(int));
+    size_t o_P = carve(B * 64 * sizeof(float));
+    size_t o_pi = carve(B * sizeof(int));
+    size_t o_pts = carve(B * 4 * (size_t)s.n_stride * sizeof(float));
+    size_t o_tc = carve(B * sizeof(int));
+    cudaError_t e = cudaMalloc(&h->arena, off);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(SFMB200_ERR_CUDA, "cudaMalloc(arena): %s", cudaGetErrorString(e));
+    }
+    char* base = (char*)h->arena;
+    s.corr = (float4*)(base + o_corr);
+    s.corr_dup = (float4*)(base + o_dup);
+    s.px = (float*)(base + o_px);
+    s.Ecand = (float*)(base + o_ec);
+    s.counts = (int*)(base + o_cnt);
+    s.tile_done = (int*)(base + o_td);
+    s.best = (unsigned long long*)(base + o_best);
+    s.E = (float*)(base + o_E);
+    s.best_idx = (int*)(base + o_bi);
+    s.best_count = (int*)(base + o_bc);
+    s.P = (float*)(base + o_P);
+    s.P_ind = (int*)(base + o_pi);
+    s.points = (float*)(base + o_pts);
+    s.tri_count = (int*)(base + o_tc);
+    e = cudaMemset(h->arena, 0, off);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        cudaFree(h->arena);
+        delete h;
+        return fail(SFMB200_ERR_CUDA, "create: %s", cudaGetErrorString(e));
+    }
+    h->own_stream = true;
+    h->compat = 1;
+    h->score_variant = -1;
+    h->tri_inliers_only = 0;
+    *out = h;
+    return SFMB200_OK;
+}
+
+int sfmb200_destroy(sfmb200_t* h) {
+    if (!h) return SFMB200_OK;
+    cudaStreamSynchronize(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    cudaFree(h->arena);
+    delete h;
+    return SFMB200_OK;
+}
+
+int sfmb200_set_option(sfmb200_t* h, int option, int value) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    switch (option) {
+        case SFMB200_OPT_COMPAT: h->compat = value ? 1 : 0; break;
+        case SFMB200_OPT_SCORE_VARIANT:
+            if (value < -1 || value > 1) return fail(SFMB200_ERR_ARG, "score variant must be -1, 0 or 1%s");
+            h->score_variant = value;
+            break;
+        case SFMB200_OPT_TRI_INLIERS_ONLY: h->tri_inliers_only = value ? 1 : 0; break;
+        default: return fail(SFMB200_ERR_ARG, "unknown option%s");
+    }
+    return SFMB200_OK;
+}
+
+int sfmb200_set_stream(sfmb200_t* h, void* stream) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (h->own_stream) {
+        cudaStreamSynchronize(h->stream);
+        cudaStreamDestroy(h->stream);
+        h->own_stream = false;
+    }
+    h->stream = (cudaStream_t)stream;
+    return SFMB200_OK;
+}
+
+int sfmb200_synchronize(sfmb200_t* h) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+
+static int check_n(sfmb200_t* h, const void* p, int n) {
+    if (!h || !p) return fail(SFMB200_ERR_ARG, "null argument%s");
+    if (n < 8 || n > h->s.n_max) return fail(SFMB200_ERR_ARG, "n must be in [8, max_points]%s");
+    return SFMB200_OK;
+}
+
+int sfmb200_set_points_sift(sfmb200_t* h, const void* d_sift, int n) {
+    int rc = check_n(h, d_sift, n);
+    if (rc) return rc;
+    if (h->s.B != 1) return fail(SFMB200_ERR_ARG, "SiftPoint ingest needs pairs == 1%s");
+    h->s.n = n;
+    launch_ingest_sift(h->s, d_sift, n, h->stream);
+    CKL();
+    h->launches++;
+    h->have_points = true;
+    return SFMB200_OK;
+}
+int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n) {
+    int rc = check_n(h, d_px, n);
+    if (rc) return rc;
+    h->s.n = n;
+    launch_ingest_xy(h->s, d_px, n, h->stream);
+    CKL();
+    h->launches++;
+    h->have_points = true;
+    return SFMB200_OK;
+}
+int sfmb200_set_points_xy_host(sfmb200_t* h, const float* h_px, int n) {
+    int rc = check_n(h, h_px, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->s.px, h_px, (size_t)h->s.B * n * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    return sfmb200_set_points_xy(h, h->s.px, n);
+}
+int sfmb200_set_points_normalised(sfmb200_t* h, const float* d_x, int n) {
+    int rc = check_n(h, d_x, n);
+    if (rc) return rc;
+    h->s.n = n;
+    launch_ingest_normalised(h->s, d_x, n, h->stream);
+    CKL();
+    h->launches++;
+    h->have_points = true;
+    return SFMB200_OK;
+}
+
+int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, int h_begin, int H, uint64_t seed,
+                             float thr) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->have_points) return fail(SFMB200_ERR_STATE, "estimate_e before set_points%s");
+    if (H < 1 || H > h->s.h_max || h_begin < 0 || (long long)h_begin + H > (long long)H_total)
+        return fail(SFMB200_ERR_ARG, "hypothesis slice out of range / above max_hypotheses%s");
+    if (!(thr > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
+    h->H = H;
+    h->h_begin = h_begin;
+    h->thr = thr;
+    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
+    launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->stream);
+    CKL();
+    launch_score(h->s, h->plan, H, h_begin, thr, h->stream);
+    CKL();
+    launch_select(h->s, h_begin, h->stream);
+    CKL();
+    h->launches += 3;
+    h->have_candidates = true;
+    h->have_E = true;
+    h->have_pose = false;
+    return SFMB200_OK;
+}
+int sfmb200_estimate_e(sfmb200_t* h, const int32_t* d_idx, int H, uint64_t seed, float thr) {
+    return sfmb200_estimate_e_slice(h, d_idx, H, 0, H, seed, thr);
+}
+
+int sfmb200_best_buffer(sfmb200_t* h, uint64_t** d_best) {
+    if (!h || !d_best) return fail(SFMB200_ERR_ARG, "null argument%s");
+    *d_best = (uint64_t*)h->s.best;
+    return SFMB200_OK;
+}
+int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->have_points) return fail(SFMB200_ERR_STATE, "adopt_best before set_points%s");
+    launch_regen_best(h->s, d_idx, (long long)H_total * 8, seed, h->stream);
+    CKL();
+    h->launches++;
+    h->have_E = true;
+    h->have_pose = false;
+    return SFMB200_OK;
+}
+
+int sfmb200_pose_candidates(sfmb200_t* h) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->have_E) return fail(SFMB200_ERR_STATE, "pose_candidates before an essential matrix exists%s");
+    launch_pose_candidates(h->s, h->compat, h->stream);
+    CKL();
+    h->launches++;
+    h->have_pose = true;
+    return SFMB200_OK;
+}
+int sfmb200_choose_pose(sfmb200_t* h) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->have_pose || !h->have_points) return fail(SFMB200_ERR_STATE, "choose_pose before pose_candidates%s");
+    launch_choose_pose(h->s, h->compat, h->thr > 0 ? h->thr : 1e-6f, h->stream);
+    CKL();
+    h->launches++;
+    return SFMB200_OK;
+}
+int sfmb200_triangulate(sfmb200_t* h) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->have_pose || !h->have_points) return fail(SFMB200_ERR_STATE, "triangulate before pose_candidates%s");
+    launch_triangulate(h->s, h->tri_inliers_only, h->thr > 0 ? h->thr : 1e-6f, h->stream);
+    CKL();
+    h->launches++;
+    return SFMB200_OK;
+}
+
+static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
+    int rc = sfmb200_estimate_e(h, nullptr, H, seed, thr);
+    if (rc) return rc;
+    if ((rc = sfmb200_pose_candidates(h))) return rc;
+    if ((rc = sfmb200_choose_pose(h))) return rc;
+    return sfmb200_triangulate(h);
+}
+
+int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t seed, float thr) {
+    int rc = sfmb200_set_points_xy(h, d_px, n);
+    if (rc) return rc;
+    return run_stages(h, H, seed, thr);
+}
+
+__global__ void gather_selected_pose_kernel(DeviceState s, float* out) {
+    int b = blockIdx.x;
+    int t = threadIdx.x;
+    if (t < 16) out[(size_t)b * 16 + t] = s.P[(size_t)b * 64 + 16 * s.P_ind[b] + t];
+}
+
+int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t seed, float thr, float* h_E, float* h_P,
+                     int32_t* h_pose_index, int32_t* h_inliers, float* h_points) {
+    int rc = sfmb200_set_points_xy_host(h, h_px, n);
+    if (rc) return rc;
+    if ((rc = run_stages(h, H, seed, thr))) return rc;
+    DeviceState& s = h->s;
+    size_t B = s.B;
+    if (h_E) CK(cudaMemcpyAsync(h_E, s.E, B * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_P) {
+        // selected pose per pair, staged through the (now free) pixel buffer
+        gather_selected_pose_kernel<<<(unsigned)B, 16, 0, h->stream>>>(s, s.px);
+        CKL();
+        h->launches++;
+        CK(cudaMemcpyAsync(h_P, s.px, B * 16 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (h_pose_index) CK(cudaMemcpyAsync(h_pose_index, s.P_ind, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h_inliers) CK(cudaMemcpyAsync(h_inliers, s.best_count, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h_points) {
+        if (s.n == s.n_stride) {
+            CK(cudaMemcpyAsync(h_points, s.points, B * 4 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            CK(cudaMemcpy2DAsync(h_points, (size_t)s.n * sizeof(float), s.points, (size_t)s.n_stride * sizeof(float),
+                                 (size_t)s.n * sizeof(float), B * 4, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+
+int sfmb200_copy_to_vbo(sfmb200_t* h, int pair, float* d_pos, float* d_col) {
+    if (!h || pair < 0 || pair >= h->s.B) return fail(SFMB200_ERR_ARG, "bad handle / pair%s");
+    launch_vbo(h->s, pair, d_pos, d_col, 1.0f, h->stream);
+    CKL();
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));   // the reference ends with cudaDeviceSynchronize (sfm.cu:382)
+    return SFMB200_OK;
+}
+
+int sfmb200_get_E(sfmb200_t* h, float* h_E) {
+    if (!h || !h_E) return fail(SFMB200_ERR_ARG, "null argument%s");
+    CK(cudaMemcpyAsync(h_E, h->s.E, (size_t)h->s.B * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+int sfmb200_set_E(sfmb200_t* h, const float* h_E) {
+    if (!h || !h_E) return fail(SFMB200_ERR_ARG, "null argument%s");
+    CK(cudaMemcpyAsync(h->s.E, h_E, (size_t)h->s.B * 9 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_E = true;
+    h->have_pose = false;
+    if (!(h->thr > 0)) h->thr = 1e-6f;
+    return SFMB200_OK;
+}
+int sfmb200_get_best(sfmb200_t* h, int32_t* h_index, int32_t* h_count) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null argument%s");
+    if (h_index) CK(cudaMemcpyAsync(h_index, h->s.best_idx, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h_count) CK(cudaMemcpyAsync(h_count, h->s.best_count, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+int sfmb200_get_poses(sfmb200_t* h, float* h_P) {
+    if (!h || !h_P) return fail(SFMB200_ERR_ARG, "null argument%s");
+    CK(cudaMemcpyAsync(h_P, h->s.P, (size_t)h->s.B * 64 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+int sfmb200_get_pose_index(sfmb200_t* h, int32_t* h_ind) {
+    if (!h || !h_ind) return fail(SFMB200_ERR_ARG, "null argument%s");
+    CK(cudaMemcpyAsync(h_ind, h->s.P_ind, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+static int check_pair(sfmb200_t* h, int pair, const void* p) {
+    if (!h || !p) return fail(SFMB200_ERR_ARG, "null argument%s");
+    if (pair < 0 || pair >= h->s.B) return fail(SFMB200_ERR_ARG, "pair out of range%s");
+    return SFMB200_OK;
+}
+int sfmb200_get_points(sfmb200_t* h, int pair, float* d_points) {
+    int rc = check_pair(h, pair, d_points);
+    if (rc) return rc;
+    const DeviceState& s = h->s;
+    CK(cudaMemcpy2DAsync(d_points, (size_t)s.n * sizeof(float), s.points + (size_t)pair * 4 * s.n_stride,
+                         (size_t)s.n_stride * sizeof(float), (size_t)s.n * sizeof(float), 4, cudaMemcpyDeviceToDevice,
+                         h->stream));
+    return SFMB200_OK;
+}
+int sfmb200_get_points_host(sfmb200_t* h, int pair, float* h_points) {
+    int rc = check_pair(h, pair, h_points);
+    if (rc) return rc;
+    const DeviceState& s = h->s;
+    CK(cudaMemcpy2DAsync(h_points, (size_t)s.n * sizeof(float), s.points + (size_t)pair * 4 * s.n_stride,
+                         (size_t)s.n_stride * sizeof(float), (size_t)s.n * sizeof(float), 4, cudaMemcpyDeviceToHost,
+                         h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+int sfmb200_get_inlier_counts(sfmb200_t* h, int pair, int32_t* d_counts) {
+    int rc = check_pair(h, pair, d_counts);
+    if (rc) return rc;
+    if (!h->have_candidates) return fail(SFMB200_ERR_STATE, "no estimate yet%s");
+    CK(cudaMemcpyAsync(d_counts, h->s.counts + (size_t)pair * h->s.h_stride, (size_t)h->H * sizeof(int),
+                       cudaMemcpyDeviceToDevice, h->stream));
+    return SFMB200_OK;
+}
+int sfmb200_get_E_candidates(sfmb200_t* h, int pair, float* d_E) {
+    int rc = check_pair(h, pair, d_E);
+    if (rc) return rc;
+    if (!h->have_candidates) return fail(SFMB200_ERR_STATE, "no estimate yet%s");
+    launch_export_ecand(h->s, pair, h->H, d_E, h->stream);
+    CKL();
+    h->launches++;
+    return SFMB200_OK;
+}
+int sfmb200_get_X(sfmb200_t* h, int pair, int image, float* d_X) {
+    int rc = check_pair(h, pair, d_X);
+    if (rc) return rc;
+    if (image < 0 || image > 1) return fail(SFMB200_ERR_ARG, "image must be 0 or 1%s");
+    if (!h->have_points) return fail(SFMB200_ERR_STATE, "no points yet%s");
+    launch_export_X(h->s, pair, image, d_X, h->stream);
+    CKL();
+    h->launches++;
+    return SFMB200_OK;
+}
+int sfmb200_get_inlier_mask(sfmb200_t* h, int pair, uint8_t* d_mask) {
+    int rc = check_pair(h, pair, d_mask);
+    if (rc) return rc;
+    if (!h->have_E || !h->have_points) return fail(SFMB200_ERR_STATE, "no essential matrix yet%s");
+    launch_inlier_mask(h->s, pair, h->thr > 0 ? h->thr : 1e-6f, d_mask, h->stream);
+    CKL();
+    h->launches++;
+    return SFMB200_OK;
+}
+int sfmb200_device_views(sfmb200_t* h, float** d_E, float** d_P, int32_t** d_pose_index, float** d_points,
+                         int* point_stride) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (d_E) *d_E = h->s.E;
+    if (d_P) *d_P = h->s.P;
+    if (d_pose_index) *d_pose_index = h->s.P_ind;
+    if (d_points) *d_points = h->s.points;
+    if (point_stride) *point_stride = h->s.n_stride;
+    return SFMB200_OK;
+}
+int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]) {
+    if (!h || !out) return fail(SFMB200_ERR_ARG, "null argument%s");
+    out[0] = h->plan.variant;
+    out[1] = h->plan.tiles;
+    out[2] = h->plan.splits;
+    out[3] = h->plan.pts_per_split;
+    return SFMB200_OK;
+}
+int64_t sfmb200_launch_count(sfmb200_t* h) { return h ? h->launches : 0; }
+
+int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms) {
+    if (!fmas || !ms || iters < 1 || mode < 0 || mode > 1) return fail(SFMB200_ERR_ARG, "bad argument%s");
+    float* sink = nullptr;
+    cudaEvent_t e0, e1;
+    CK(cudaMalloc(&sink, 256));
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    launch_fma_probe(mode, 4, 0, sink);   // warm-up
+    CK(cudaEventRecord(e0, 0));
+    *fmas = launch_fma_probe(mode, iters, 0, sink);
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    CKL();
+    CK(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return SFMB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// Ingest (fillXU), pose candidates, cheirality pose selection, linear
+// triangulation and egress.  Reference: SfM/sfm.cu:80-92, 238-344, 374-383 and
+// SfM/kernels.h:261-279, 357-450, 471-495.
+#include "internal.cuh"
+#include "smallmat.cuh"
+
+namespace sfmb200 {
+
+struct Mat9 { float v[9]; };
+
+// ---------------------------------------------------------------------------
+// Ingest.  X = K^-1 [u v 1]^T for both images (copy_point + 2 cublasSgemm in the
+// reference).  Writes the float4 correspondence array every later stage reads
+// and the duplicated layout the packed scoring path stages through TMA.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void normalise_store(const DeviceState& s, int b, int i, float u1, float v1, float u2, float v2,
+                                                const Mat9& k) {
+    float x1 = fmaf(k.v[1], v1, fmaf(k.v[0], u1, k.v[2]));
+    float y1 = fmaf(k.v[4], v1, fmaf(k.v[3], u1, k.v[5]));
+    float z1 = fmaf(k.v[7], v1, fmaf(k.v[6], u1, k.v[8]));
+    float x2 = fmaf(k.v[1], v2, fmaf(k.v[0], u2, k.v[2]));
+    float y2 = fmaf(k.v[4], v2, fmaf(k.v[3], u2, k.v[5]));
+    float z2 = fmaf(k.v[7], v2, fmaf(k.v[6], u2, k.v[8]));
+    // The reference keeps a z row (== 1 for any K with last row 0 0 1); the
+    // float4 layout fixes z = 1, which is the same projective point.
+    if (z1 != 1.0f) { x1 /= z1; y1 /= z1; }
+    if (z2 != 1.0f) { x2 /= z2; y2 /= z2; }
+    size_t o = (size_t)b * s.n_stride + i;
+    s.corr[o] = make_float4(x1, y1, x2, y2);
+    s.corr_dup[2 * o] = make_float4(x1, x1, y1, y1);
+    s.corr_dup[2 * o + 1] = make_float4(x2, x2, y2, y2);
+}
+
+// SiftPoint is 576 bytes (CudaSift/cudaSift.h:6-22); only xpos@0, ypos@4,
+// match_xpos@36, match_ypos@40 are read (kernels.h:268-273).
+constexpr int SIFT_STRIDE_F = 144;
+__global__ void ingest_sift_kernel(DeviceState s, const float* __restrict__ sift, int n, Mat9 k) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = sift + (size_t)i * SIFT_STRIDE_F;
+    float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    float u2 = __ldg(p + 9), v2 = __ldg(p + 10);
+    normalise_store(s, 0, i, a.x, a.y, u2, v2, k);
+}
+__global__ void ingest_xy_kernel(DeviceState s, const float4* __restrict__ px, int n, Mat9 k) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.y;
+    if (i >= n) return;
+    float4 p = __ldg(px + (size_t)b * n + i);
+    normalise_store(s, b, i, p.x, p.y, p.z, p.w, k);
+}
+void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStream_t st) {
+    Mat9 k;
+    for (int i = 0; i < 9; i++) k.v[i] = s.Kinv[i];
+    ingest_sift_kernel<<<(n + 255) / 256, 256, 0, st>>>(s, (const float*)d_sift, n, k);
+}
+void launch_ingest_xy(const DeviceState& s, const float* d_px, int n, cudaStream_t st) {
+    Mat9 k;
+    for (int i = 0; i < 9; i++) k.v[i] = s.Kinv[i];
+    dim3 grid((n + 255) / 256, s.B);
+    ingest_xy_kernel<<<grid, 256, 0, st>>>(s, (const float4*)d_px, n, k);
+}
+void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cudaStream_t st) {
+    Mat9 k = {{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+    dim3 grid((n + 255) / 256, s.B);
+    ingest_xy_kernel<<<grid, 256, 0, st>>>(s, (const float4*)d_x, n, k);
+}
+
+// ---------------------------------------------------------------------------
+// Pose candidates (computePosecandidates sfm.cu:238-252 + candidate_kernels
+// kernels.h:357-385).  One thread per pair; the reference does the SVD on the
+// host between two synchronous copies.
+// compat = 1: P_i = [ (U W(^T) V^T)^T | +-u3 ], det-typo sign fix (Q15, Q16).
+// compat = 0: textbook pose for x1^T E x2 = 0: X2 = R X1 + t, R = V W(^T) U^T, t = +-v3.
+// ---------------------------------------------------------------------------
+__global__ void pose_candidates_kernel(DeviceState s, int compat) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    float E[9], u[9], sg[9], v[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) E[i] = s.E[(size_t)b * 9 + i];
+    svd3<5>(E, u, sg, v);
+    const float W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+    const float Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    if (compat) {
+        float tmp[9];
+        mul33_ABt(u, v, tmp);
+        if (det33_reference_typo(tmp) < 0.0f) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) v[i] = -v[i];
+        }
+    }
+    float* Pb = s.P + (size_t)b * 64;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float t1[9], R[9];
+        const float* Wc = (c < 2) ? W : Wt;
+        float sign = (c == 0 || c == 2) ? -1.0f : 1.0f;
+        float tx, ty, tz;
+        if (compat) {
+            mul33_ABt(Wc, v, t1);     // W V^T
+            mul33(u, t1, R);          // U W V^T ; stored transposed
+            float Rt[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
+#pragma unroll
+            for (int i = 0; i < 9; i++) R[i] = Rt[i];
+            tx = sign * u[2]; ty = sign * u[5]; tz = sign * u[8];
+        } else {
+            mul33_ABt(Wc, u, t1);     // W U^T
+            mul33(v, t1, R);          // V W U^T
+            if (det33(R) < 0.0f) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) R[i] = -R[i];
+            }
+            tx = sign * v[2]; ty = sign * v[5]; tz = sign * v[8];
+        }
+        float* P = Pb + 16 * c;
+        P[0] = R[0]; P[1] = R[1]; P[2] = R[2];  P[3] = tx;
+        P[4] = R[3]; P[5] = R[4]; P[6] = R[5];  P[7] = ty;
+        P[8] = R[6]; P[9] = R[7]; P[10] = R[8]; P[11] = tz;
+        P[12] = 0.0f; P[13] = 0.0f; P[14] = 0.0f; P[15] = 1.0f;
+    }
+}
+void launch_pose_candidates(const DeviceState& s, int compat, cudaStream_t st) {
+    pose_candidates_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s, compat);
+}
+
+// DLT rows for one correspondence, camera 1 = I4, camera 2 = M
+// (compute_linear_triangulation_A, kernels.h:387-431).
+__device__ __forceinline__ void dlt_matrix(float x1, float y1, float x2, float y2, const float* M, float* A) {
+    A[0] = -1.0f; A[1] = 0.0f;  A[2] = x1; A[3] = 0.0f;
+    A[4] = 0.0f;  A[5] = -1.0f; A[6] = y1; A[7] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        A[8 + i] = fmaf(x2, M[8 + i], -M[i]);
+        A[12 + i] = fmaf(y2, M[8 + i], -M[4 + i]);
+    }
+}
+// De-homogenise like normalize_pt_kernal (kernels.h:433-450): w == 0 -> origin.
+__device__ __forceinline__ void dehomogenise(const float* v, float& X, float& Y, float& Z) {
+    if (v[3] == 0.0f) { X = 0.0f; Y = 0.0f; Z = 0.0f; return; }
+    float iw = 1.0f / v[3];
+    X = v[0] * iw; Y = v[1] * iw; Z = v[2] * iw;
+}
+
+__device__ __forceinline__ float sampson_d_geom(const float* e, float x1, float y1, float x2, float y2, float nthr) {
+    float l0 = fmaf(e[0], x2, fmaf(e[1], y2, e[2]));
+    float l1 = fmaf(e[3], x2, fmaf(e[4], y2, e[5]));
+    float l2 = fmaf(e[6], x2, fmaf(e[7], y2, e[8]));
+    float num = fmaf(x1, l0, fmaf(y1, l1, l2));
+    float m0 = fmaf(e[0], x1, fmaf(e[3], y1, e[6]));
+    float m1 = fmaf(e[1], x1, fmaf(e[4], y1, e[7]));
+    float den = fmaf(l0, l0, fmaf(l1, l1, fmaf(m0, m0, m1 * m1)));
+    return fmaf(den, nthr, num * num);
+}
+
+// ---------------------------------------------------------------------------
+// choosePose (sfm.cu:254-307).
+// compat = 1: cheirality of correspondence 0 only; every candidate is inverted
+//   in place; depth tested in both frames; the LAST passing index wins (default
+//   0); afterwards P holds the inverses (Q17-Q19).  One thread per pair.
+// compat = 0: every inlier of the selected E votes (z > 0 in both cameras,
+//   X2 = P_i X); arg-max of votes, first on ties; P is left untouched.
+//   One 256-thread CTA per pair.
+// ---------------------------------------------------------------------------
+__global__ void choose_pose_compat_kernel(DeviceState s) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    float4 c0 = s.corr[(size_t)b * s.n_stride];
+    float* Pb = s.P + (size_t)b * 64;
+    int ind = 0;
+    for (int c = 0; c < 4; c++) {
+        float M[16], A[16], v[4], Minv[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) M[i] = Pb[16 * c + i];
+        dlt_matrix(c0.x, c0.y, c0.z, c0.w, M, A);
+        null4<5>(A, v);
+        float X, Y, Z;
+        dehomogenise(v, X, Y, Z);
+        inv4(M, Minv);
+        float z2 = fmaf(Minv[8], X, fmaf(Minv[9], Y, fmaf(Minv[10], Z, Minv[11])));
+        if (Z > 0.0f && z2 > 0.0f) ind = c;
+#pragma unroll
+        for (int i = 0; i < 16; i++) Pb[16 * c + i] = Minv[i];
+    }
+    s.P_ind[b] = ind;
+}
+
+__global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, float thr) {
+    const int b = blockIdx.x;
+    __shared__ float sP[64];
+    __shared__ float sE[9];
+    __shared__ int votes[4];
+    if (threadIdx.x < 64) sP[threadIdx.x] = s.P[(size_t)b * 64 + threadIdx.x];
+    if (threadIdx.x < 9) sE[threadIdx.x] = s.E[(size_t)b * 9 + threadIdx.x];
+    if (threadIdx.x < 4) votes[threadIdx.x] = 0;
+    __syncthreads();
+    int local[4] = {0, 0, 0, 0};
+    const float4* corr = s.corr + (size_t)b * s.n_stride;
+    for (int i = threadIdx.x; i < s.n; i += blockDim.x) {
+        float4 p = corr[i];
+        if (sampson_d_geom(sE, p.x, p.y, p.z, p.w, -thr) >= 0.0f) continue;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float A[16], v[4];
+            dlt_matrix(p.x, p.y, p.z, p.w, sP + 16 * c, A);
+            null4<5>(A, v);
+            float X, Y, Z;
+            dehomogenise(v, X, Y, Z);
+            const float* M = sP + 16 * c;
+            float z2 = fmaf(M[8], X, fmaf(M[9], Y, fmaf(M[10], Z, M[11])));
+            local[c] += (Z > 0.0f && z2 > 0.0f) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int v = local[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&votes[c], v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int c = 1; c < 4; c++)
+            if (votes[c] > votes[best]) best = c;
+        s.P_ind[b] = best;
+    }
+}
+void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_t st) {
+    if (compat)
+        choose_pose_compat_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s);
+    else
+        choose_pose_vote_kernel<<<s.B, 256, 0, st>>>(s, thr);
+}
+
+// ---------------------------------------------------------------------------
+// Linear triangulation (sfm.cu:309-344): one thread per correspondence, 4x4 DLT
+// null vector in registers (replaces the batched 4x4 cusolver gesvdj that writes
+// U, S and V for every point), de-homogenised into the reference's 4xN SoA.
+// HBM roofline: 16 B read + 16 B written per point.
+// inliers_only: points failing the Sampson test of the selected E get (0,0,0,1).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inliers_only, float thr) {
+    const int b = blockIdx.y;
+    __shared__ float sM[16];
+    __shared__ float sE[9];
+    if (threadIdx.x < 16) sM[threadIdx.x] = s.P[(size_t)b * 64 + 16 * s.P_ind[b] + threadIdx.x];
+    if (threadIdx.x < 9) sE[threadIdx.x] = s.E[(size_t)b * 9 + threadIdx.x];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    float4 p = __ldg(s.corr + (size_t)b * s.n_stride + i);
+    float X = 0.0f, Y = 0.0f, Z = 0.0f;
+    bool keep = !inliers_only || sampson_d_geom(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f;
+    if (keep) {
+        float A[16], v[4];
+        dlt_matrix(p.x, p.y, p.z, p.w, sM, A);
+        null4<5>(A, v);
+        dehomogenise(v, X, Y, Z);
+    }
+    float* out = s.points + (size_t)b * 4 * s.n_stride;
+    out[i] = X;
+    out[(size_t)s.n_stride + i] = Y;
+    out[(size_t)2 * s.n_stride + i] = Z;
+    out[(size_t)3 * s.n_stride + i] = 1.0f;
+}
+void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st) {
+    dim3 grid((s.n + 255) / 256, s.B);
+    triangulate_kernel<<<grid, 256, 0, st>>>(s, inliers_only, thr);
+}
+
+// ---------------------------------------------------------------------------
+// Egress and getters.
+// ---------------------------------------------------------------------------
+// copyBoidsToVBO (sfm.cu:374-383, kernels.h:471-495): 4xN SoA -> Nx4 AoS, colour = 1.
+__global__ void vbo_kernel(DeviceState s, int pair, float4* pos, float4* col, float scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    const float* in = s.points + (size_t)pair * 4 * s.n_stride;
+    if (pos) pos[i] = make_float4(in[i] * scale, in[(size_t)s.n_stride + i] * scale, in[(size_t)2 * s.n_stride + i] * scale, 1.0f);
+    if (col) col[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+}
+void launch_vbo(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, cudaStream_t st) {
+    vbo_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, (float4*)d_pos, (float4*)d_col, scale);
+}
+
+// E candidates as the reference stores them: [H][3][3] row-major (d_E_candidate).
+__global__ void export_ecand_kernel(DeviceState s, int pair, int H, float* out) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const float* Eb = s.Ecand + (size_t)pair * 9 * s.h_stride;
+#pragma unroll
+    for (int k = 0; k < 9; k++) out[(size_t)h * 9 + k] = Eb[(size_t)k * s.h_stride + h];
+}
+void launch_export_ecand(const DeviceState& s, int pair, int H, float* d_out, cudaStream_t st) {
+    export_ecand_kernel<<<(H + 255) / 256, 256, 0, st>>>(s, pair, H, d_out);
+}
+
+// X[image] as the reference stores it: 3xN row-major, rows x, y, 1 (sfm.cu:88-89).
+__global__ void export_X_kernel(DeviceState s, int pair, int image, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    float4 p = s.corr[(size_t)pair * s.n_stride + i];
+    out[i] = image == 0 ? p.x : p.z;
+    out[(size_t)s.n + i] = image == 0 ? p.y : p.w;
+    out[(size_t)2 * s.n + i] = 1.0f;
+}
+void launch_export_X(const DeviceState& s, int pair, int image, float* d_out, cudaStream_t st) {
+    export_X_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, image, d_out);
+}
+
+__global__ void inlier_mask_kernel(DeviceState s, int pair, float thr, unsigned char* mask) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    float e[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) e[k] = s.E[(size_t)pair * 9 + k];
+    float4 p = s.corr[(size_t)pair * s.n_stride + i];
+    mask[i] = sampson_d_geom(e, p.x, p.y, p.z, p.w, -thr) < 0.0f ? 1 : 0;
+}
+void launch_inlier_mask(const DeviceState& s, int pair, float thr, unsigned char* d_mask, cudaStream_t st) {
+    inlier_mask_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, thr, d_mask);
+}
+
+}  // namespace sfmb200

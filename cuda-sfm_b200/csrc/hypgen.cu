@@ -1,0 +1,99 @@
+// Hypothesis generation: one thread = one minimal sample = one E candidate.
+// See hyp_solver.cuh for the per-hypothesis math and the reference kernels it
+// replaces (SfM/kernels.h:196-295, SfM/sfm.cu:107-129).
+//
+// Roofline: FP32 pipe.  ~5 sweeps x 36 rotations x ~80 FP32 instructions plus
+// Gram build / refinement / 3x3 SVD ~= 17 k FP32 instructions per hypothesis;
+// memory traffic is 8 gathered 16-byte correspondences (L2 hits) in and 36 B out.
+#include "hyp_solver.cuh"
+#include "internal.cuh"
+
+namespace sfmb200 {
+
+constexpr int HYP_THREADS = 128;
+
+// Loads the 8 sampled correspondences of hypothesis (pair b, global index hg).
+// A sample with an out-of-range or repeated index is degenerate: returns false.
+__device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int n, const int32_t* __restrict__ idx_rows,
+                                            unsigned long long seed, long long hg, Corr* pts) {
+    int id[8];
+    if (idx_rows != nullptr) {
+        const int4* row = reinterpret_cast<const int4*>(idx_rows + 8 * hg);
+        int4 a = __ldg(row), b = __ldg(row + 1);
+        id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w;
+        id[4] = b.x; id[5] = b.y; id[6] = b.z; id[7] = b.w;
+    } else {
+        sample_indices(seed, (unsigned long long)hg, n, id);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        ok = ok && (id[i] >= 0) && (id[i] < n);
+#pragma unroll
+        for (int j = 0; j < i; j++) ok = ok && (id[i] != id[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int k = ok ? id[i] : 0;
+        float4 c = __ldg(corr + k);
+        pts[i] = Corr{c.x, c.y, c.z, c.w};
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(HYP_THREADS)
+hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride, int H, int h_offset,
+              unsigned long long seed) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * HYP_THREADS + threadIdx.x;   // local hypothesis slot
+    // Reset the per-launch accumulators of this pair (scoring adds into them).
+    if (j < s.tiles_max) s.tile_done[(size_t)b * s.tiles_max + j] = 0;
+    if (j == 0) s.best[b] = 0ull;
+    if (j >= H) return;
+    const float4* corr = s.corr + (size_t)b * s.n_stride;
+    const int32_t* rows = d_idx ? d_idx + (size_t)b * idx_pair_stride : nullptr;
+    Corr pts[8];
+    float E[9];
+    bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b, (long long)h_offset + j, pts);
+    solve_hypothesis(pts, E);
+    float* out = s.Ecand + (size_t)b * 9 * s.h_stride + j;
+#pragma unroll
+    for (int k = 0; k < 9; k++) out[(size_t)k * s.h_stride] = ok ? E[k] : 0.0f;
+    s.counts[(size_t)b * s.h_stride + j] = 0;
+}
+
+void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
+                   unsigned long long seed, cudaStream_t st) {
+    int need = H > s.tiles_max ? H : s.tiles_max;
+    dim3 grid((need + HYP_THREADS - 1) / HYP_THREADS, s.B);
+    hypgen_kernel<<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+}
+
+// Multi-GPU single-pair case: after the (count, index) all-reduce every rank
+// regenerates the winning hypothesis from its global index instead of
+// broadcasting 36 bytes.  best[] already holds the reduced value.
+__global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride,
+                                  unsigned long long seed) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    unsigned long long packed = s.best[b];
+    unsigned int hg = 0xFFFFFFFFu - (unsigned int)(packed & 0xFFFFFFFFull);
+    int cnt = (int)(packed >> 32);
+    const float4* corr = s.corr + (size_t)b * s.n_stride;
+    const int32_t* rows = d_idx ? d_idx + (size_t)b * idx_pair_stride : nullptr;
+    Corr pts[8];
+    float E[9];
+    bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b, (long long)hg, pts);
+    solve_hypothesis(pts, E);
+#pragma unroll
+    for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = ok ? E[k] : 0.0f;
+    s.best_idx[b] = (int)hg;
+    s.best_count[b] = cnt;
+}
+
+void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, unsigned long long seed,
+                       cudaStream_t st) {
+    regen_best_kernel<<<(s.B + 31) / 32, 32, 0, st>>>(s, d_idx, idx_pair_stride, seed);
+}
+
+}  // namespace sfmb200

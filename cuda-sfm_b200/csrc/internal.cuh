@@ -1,0 +1,70 @@
+// Internal declarations shared by the kernels and the C ABI (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sfmb200 {
+
+// Launch parameters of the scoring kernel; chosen by the host per problem shape.
+struct ScorePlan {
+    int variant;        // 0: scalar FFMA, 2 hyp/thread; 1: packed FFMA2, 4 hyp/thread
+    int hyp_per_cta;    // hypotheses per CTA (256 threads * hyp/thread)
+    int tiles;          // ceil(H / hyp_per_cta)
+    int splits;         // point-range splits per tile (grid.y)
+    int pts_per_split;  // multiple of SCORE_CHUNK
+};
+
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_CHUNK = 512;     // points per TMA stage
+
+// Everything one handle owns on the device.  All per-pair arrays are laid out
+// [pair][...] with fixed strides so a batch is one launch (blockIdx.y / z = pair).
+struct DeviceState {
+    int B;              // pairs in the batch
+    int n_max;          // capacity: correspondences per pair
+    int h_max;          // capacity: hypotheses per pair (local slice)
+    int n;              // current correspondences per pair
+    int n_stride;       // points stride (n_max rounded up to SCORE_CHUNK)
+    int h_stride;       // hypothesis stride (h_max rounded up to 1024)
+    int tiles_max;
+    float Kinv[9];
+    float K[9];
+
+    float4* corr;       // [B][n_stride]   (x1,y1,x2,y2) normalised camera coords
+    float4* corr_dup;   // [B][n_stride][2] (x1,x1,y1,y1),(x2,x2,y2,y2) for FFMA2 scoring
+    float* px;          // [B][n_stride][4] staging for host pixel input (device)
+    float* Ecand;       // [B][9][h_stride] SoA essential-matrix candidates
+    int* counts;        // [B][h_stride] inlier count per hypothesis
+    int* tile_done;     // [B][tiles_max] split tickets per hypothesis tile
+    unsigned long long* best;   // [B] packed (count << 32) | (0xFFFFFFFF - global index)
+    float* E;           // [B][9] selected essential matrix
+    int* best_idx;      // [B]
+    int* best_count;    // [B]
+    float* P;           // [B][4][16] pose candidates (row-major 4x4 each)
+    int* P_ind;         // [B]
+    float* points;      // [B][4][n_stride] SoA (x,y,z,1), the reference's d_final_points layout
+    int* tri_count;     // [B] points triangulated in front of both cameras (diagnostic)
+};
+
+void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStream_t st);
+void launch_ingest_xy(const DeviceState& s, const float* d_px, int n, cudaStream_t st);
+void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cudaStream_t st);
+void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
+                   unsigned long long seed, cudaStream_t st);
+ScorePlan make_score_plan(int B, int n, int H, int variant_override);
+void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
+void launch_select(const DeviceState& s, int h_offset, cudaStream_t st);
+void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride,
+                       unsigned long long seed, cudaStream_t st);
+void launch_pose_candidates(const DeviceState& s, int compat, cudaStream_t st);
+void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_t st);
+void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st);
+void launch_vbo(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, cudaStream_t st);
+void launch_export_ecand(const DeviceState& s, int pair, int H, float* d_out_Hx9, cudaStream_t st);
+void launch_export_X(const DeviceState& s, int pair, int image, float* d_out_3xN, cudaStream_t st);
+void launch_inlier_mask(const DeviceState& s, int pair, float thr, unsigned char* d_mask, cudaStream_t st);
+
+// FP32 pipe micro-benchmark (bench/roofline denominator): returns lane-FMAs issued.
+double launch_fma_probe(int mode, int iters, cudaStream_t st, float* d_sink);
+
+}  // namespace sfmb200

@@ -1,0 +1,315 @@
+// Small fixed-size matrix kernels shared by every stage of the hot path.
+//
+// Everything here is __host__ __device__ so the same code backs the device
+// kernels (hypgen / pose / triangulate) and the host-callable svd.h facade
+// (reference surface: SfM/svd.h:33-501).  The algorithms are our own:
+// exact-angle cyclic Jacobi on the Gram matrix followed by a Givens QR,
+// with the reference's output contract for svd() (SfM/svd.h:311-335):
+//   a = u * s * v^T, v NOT transposed, s (nearly) diagonal with
+//   |s00| >= |s11| >= |s22|, u and v proper rotations (s22 may be negative).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#ifndef SFM_HD
+#define SFM_HD __host__ __device__ __forceinline__
+#endif
+
+namespace sfmb200 {
+
+// Symmetric Jacobi rotation that annihilates a_pq.  Returns (c, s, t) of the
+// rotation J = [c s; -s c] applied as A <- J^T A J, i.e. the classic
+//   t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (a_qq - a_pp) / (2 a_pq).
+// Tiny off-diagonals give the identity (no NaN from 0/0).
+SFM_HD void jacobi_angle(float app, float aqq, float apq, float& c, float& s, float& t) {
+    const float tiny = 1e-37f;
+    bool skip = fabsf(apq) < tiny;
+    float theta = 0.5f * (aqq - app) / (skip ? 1.0f : apq);
+    float at = fabsf(theta);
+    // for |theta| large, sqrt(theta^2+1) overflows to inf and t -> 0: fine.
+    float tt = 1.0f / (at + sqrtf(fmaf(theta, theta, 1.0f)));
+    tt = theta < 0.0f ? -tt : tt;
+    tt = skip ? 0.0f : tt;
+    float cc = 1.0f / sqrtf(fmaf(tt, tt, 1.0f));
+    c = cc;
+    s = tt * cc;
+    t = tt;
+}
+
+// Givens pair (c, s) with c*a + s*b = r >= 0 and -s*a + c*b = 0.
+SFM_HD void givens(float a, float b, float& c, float& s) {
+    float r2 = fmaf(a, a, b * b);
+    if (r2 < 1e-37f) { c = 1.0f; s = 0.0f; return; }
+    float ir = 1.0f / sqrtf(r2);
+    c = a * ir;
+    s = b * ir;
+}
+
+SFM_HD void mul33(const float* a, const float* b, float* m) {      // m = a b
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            m[3 * i + j] = fmaf(a[3 * i + 2], b[6 + j], fmaf(a[3 * i + 1], b[3 + j], a[3 * i] * b[j]));
+}
+SFM_HD void mul33_AtB(const float* a, const float* b, float* m) {  // m = a^T b
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            m[3 * i + j] = fmaf(a[6 + i], b[6 + j], fmaf(a[3 + i], b[3 + j], a[i] * b[j]));
+}
+SFM_HD void mul33_ABt(const float* a, const float* b, float* m) {  // m = a b^T
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            m[3 * i + j] = fmaf(a[3 * i + 2], b[3 * j + 2], fmaf(a[3 * i + 1], b[3 * j + 1], a[3 * i] * b[3 * j]));
+}
+
+SFM_HD float det33(const float* a) {
+    return a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+           a[2] * (a[3] * a[7] - a[4] * a[6]);
+}
+// The reference's det() as written (SfM/svd.h:337-341): third term uses a0
+// where the cofactor expansion needs a1.  Needed for compat pose candidates
+// (SURVEY Q15); never use it for anything else.
+SFM_HD float det33_reference_typo(const float* a) {
+    return a[0] * a[4] * a[8] - a[0] * a[5] * a[7] - a[0] * a[3] * a[8] + a[1] * a[5] * a[6] +
+           a[2] * a[3] * a[7] - a[2] * a[4] * a[6];
+}
+
+// 3x3 SVD, contract in the file header.  One-sided (Hestenes) Jacobi: the
+// columns of B = a V are rotated pairwise until orthogonal, which keeps high
+// relative accuracy for small singular values (a Gram-matrix eigensolve would
+// lose sigma_2 of a nearly rank-1 matrix to fp32 rounding, and the rank-2
+// projection of E needs it).
+template <int SWEEPS = 5>
+SFM_HD void svd3(const float* a, float* u, float* s, float* v) {
+    float B[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int i = 0; i < 9; i++) B[i] = a[i];
+    float c, sn, t;
+#pragma unroll 1
+    for (int sw = 0; sw < SWEEPS; sw++) {
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int q = p + 1; q < 3; q++) {
+                float app = fmaf(B[6 + p], B[6 + p], fmaf(B[3 + p], B[3 + p], B[p] * B[p]));
+                float aqq = fmaf(B[6 + q], B[6 + q], fmaf(B[3 + q], B[3 + q], B[q] * B[q]));
+                float apq = fmaf(B[6 + p], B[6 + q], fmaf(B[3 + p], B[3 + q], B[p] * B[q]));
+                // skip when already orthogonal to working precision
+                bool small = fabsf(apq) <= 1e-9f * sqrtf(app * aqq);
+                jacobi_angle(app, aqq, small ? 0.0f : apq, c, sn, t);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    float bp = B[3 * k + p], bq = B[3 * k + q];
+                    B[3 * k + p] = fmaf(c, bp, -sn * bq); B[3 * k + q] = fmaf(sn, bp, c * bq);
+                    float vp = V[3 * k + p], vq = V[3 * k + q];
+                    V[3 * k + p] = fmaf(c, vp, -sn * vq); V[3 * k + q] = fmaf(sn, vp, c * vq);
+                }
+            }
+    }
+    // B = a V ; columns are (numerically) orthogonal with norms = singular values
+    float n0 = fmaf(B[6], B[6], fmaf(B[3], B[3], B[0] * B[0]));
+    float n1 = fmaf(B[7], B[7], fmaf(B[4], B[4], B[1] * B[1]));
+    float n2 = fmaf(B[8], B[8], fmaf(B[5], B[5], B[2] * B[2]));
+    // sort columns by norm, descending.  (col_i, col_j) <- (col_j, -col_i)
+    // is a rotation, so det V stays +1.
+#define SFM_SWAPNEG(i, j, ni, nj)                                   \
+    if (ni < nj) {                                                  \
+        float tn = ni; ni = nj; nj = tn;                            \
+        _Pragma("unroll") for (int k = 0; k < 3; k++) {             \
+            float bi = B[3 * k + i], vi = V[3 * k + i];             \
+            B[3 * k + i] = B[3 * k + j]; B[3 * k + j] = -bi;        \
+            V[3 * k + i] = V[3 * k + j]; V[3 * k + j] = -vi;        \
+        }                                                           \
+    }
+    SFM_SWAPNEG(0, 1, n0, n1)
+    SFM_SWAPNEG(0, 2, n0, n2)
+    SFM_SWAPNEG(1, 2, n1, n2)
+#undef SFM_SWAPNEG
+    // Givens QR of B: Qt accumulates the row rotations, u = Qt^T.
+    float Qt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#define SFM_ROWROT(p, q, col)                                                           \
+    {                                                                                   \
+        givens(B[3 * p + col], B[3 * q + col], c, sn);                                  \
+        _Pragma("unroll") for (int k = 0; k < 3; k++) {                                 \
+            float bp = B[3 * p + k], bq = B[3 * q + k];                                 \
+            B[3 * p + k] = fmaf(c, bp, sn * bq); B[3 * q + k] = fmaf(-sn, bp, c * bq);  \
+            float qp = Qt[3 * p + k], qq = Qt[3 * q + k];                               \
+            Qt[3 * p + k] = fmaf(c, qp, sn * qq); Qt[3 * q + k] = fmaf(-sn, qp, c * qq);\
+        }                                                                               \
+    }
+    SFM_ROWROT(0, 1, 0)
+    SFM_ROWROT(0, 2, 0)
+    SFM_ROWROT(1, 2, 1)
+#undef SFM_ROWROT
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            u[3 * i + j] = Qt[3 * j + i];
+            s[3 * i + j] = B[3 * i + j];
+            v[3 * i + j] = V[3 * i + j];
+        }
+}
+
+// Closest essential matrix in the reference's sense (SfM/kernels.h:281-295):
+// E <- U diag(1,1,0) V^T.  The reference leaves the QR residue of S
+// off-diagonals in (<= 1e-6 typical); we use the exact diag.
+SFM_HD void project_essential(float* E) {
+    float n = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; i++) n = fmaf(E[i], E[i], n);
+    float inv = n > 0.0f ? 1.0f / sqrtf(n) : 0.0f;
+    float En[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) En[i] = E[i] * inv;
+    float u[9], s[9], v[9];
+    svd3<5>(En, u, s, v);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            E[3 * i + j] = fmaf(u[3 * i + 1], v[3 * j + 1], u[3 * i] * v[3 * j]);
+}
+
+// Null vector (right singular vector of the smallest singular value) of a
+// row-major 4x4 A: cyclic Jacobi on A^T A with accumulated V, then one
+// refinement step that uses A itself (restores eps*cond instead of
+// eps*cond^2).  Replaces cusolverDnSgesvdjBatched 4x4 at
+// SfM/kernels.h:175-194 as used by sfm.cu:278,329.
+template <int SWEEPS = 5>
+SFM_HD void null4(const float* A, float* x) {
+    float g[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = i; j < 4; j++) {
+            float acc = A[i] * A[j];
+#pragma unroll
+            for (int r = 1; r < 4; r++) acc = fmaf(A[4 * r + i], A[4 * r + j], acc);
+            g[i][j] = acc;
+        }
+    float V[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) V[i][j] = (i == j) ? 1.0f : 0.0f;
+#pragma unroll 1
+    for (int sw = 0; sw < SWEEPS; sw++) {
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int q = p + 1; q < 4; q++) {
+                float c, s, t;
+                jacobi_angle(g[p][p], g[q][q], g[p][q], c, s, t);
+                g[p][p] = fmaf(-t, g[p][q], g[p][p]);
+                g[q][q] = fmaf(t, g[p][q], g[q][q]);
+                g[p][q] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k == p || k == q) continue;
+                    // upper-triangular storage: element (min,max)
+                    float& akp = (k < p) ? g[k][p] : g[p][k];
+                    float& akq = (k < q) ? g[k][q] : g[q][k];
+                    float a = akp, b = akq;
+                    akp = fmaf(c, a, -s * b);
+                    akq = fmaf(s, a, c * b);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float a = V[k][p], b = V[k][q];
+                    V[k][p] = fmaf(c, a, -s * b);
+                    V[k][q] = fmaf(s, a, c * b);
+                }
+            }
+    }
+    // smallest eigenvalue (first minimum)
+    float lam[4] = {g[0][0], g[1][1], g[2][2], g[3][3]};
+    int m = 0;
+    float lm = lam[0];
+#pragma unroll
+    for (int i = 1; i < 4; i++)
+        if (lam[i] < lm) { lm = lam[i]; m = i; }
+    float v0[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float val = V[k][0];
+#pragma unroll
+        for (int i = 1; i < 4; i++) val = (m == i) ? V[k][i] : val;
+        v0[k] = val;
+    }
+    // refinement: v <- v - sum_{i != m} V_i (V_i . A^T A v) / lam_i
+    float r[4], gg[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        r[i] = fmaf(A[4 * i + 3], v0[3], fmaf(A[4 * i + 2], v0[2], fmaf(A[4 * i + 1], v0[1], A[4 * i] * v0[0])));
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        gg[j] = fmaf(A[12 + j], r[3], fmaf(A[8 + j], r[2], fmaf(A[4 + j], r[1], A[j] * r[0])));
+    float lmax = fmaxf(fmaxf(lam[0], lam[1]), fmaxf(lam[2], lam[3]));
+    float v1[4] = {v0[0], v0[1], v0[2], v0[3]};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float d = fmaf(V[3][i], gg[3], fmaf(V[2][i], gg[2], fmaf(V[1][i], gg[1], V[0][i] * gg[0])));
+        bool use = (i != m) && (lam[i] > 1e-12f * lmax);
+        float coef = use ? d / lam[i] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v1[k] = fmaf(-coef, V[k][i], v1[k]);
+    }
+    float n2 = fmaf(v1[3], v1[3], fmaf(v1[2], v1[2], fmaf(v1[1], v1[1], v1[0] * v1[0])));
+    float inv = 1.0f / sqrtf(n2);
+#pragma unroll
+    for (int k = 0; k < 4; k++) x[k] = v1[k] * inv;
+}
+
+// Inverse of a rigid transform-shaped 4x4 done generally (Gauss-Jordan with
+// partial pivoting), like the LU the reference calls
+// (cublasSgetrfBatched/SgetriBatched, SfM/kernels.h:132-173).  Returns false
+// when singular.
+SFM_HD bool inv4(const float* m, float* out) {
+    float a[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            a[i][j] = m[4 * i + j];
+            a[i][4 + j] = (i == j) ? 1.0f : 0.0f;
+        }
+    bool ok = true;
+#pragma unroll
+    for (int col = 0; col < 4; col++) {
+        int piv = col;
+        float best = fabsf(a[col][col]);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (r > col && fabsf(a[r][col]) > best) { best = fabsf(a[r][col]); piv = r; }
+        if (best == 0.0f) ok = false;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (r == piv && piv != col) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) { float tmp = a[col][j]; a[col][j] = a[r][j]; a[r][j] = tmp; }
+            }
+        float ip = 1.0f / a[col][col];
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[col][j] *= ip;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (r == col) continue;
+            float f = a[r][col];
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[r][j] = fmaf(-f, a[col][j], a[r][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[4 * i + j] = a[i][4 + j];
+    return ok;
+}
+
+}  // namespace sfmb200

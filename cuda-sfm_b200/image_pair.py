@@ -1,0 +1,271 @@
+"""Python mirror of the reference's operator surface, SfM::Image_pair
+(SfM/sfm.h:20-60), over the C ABI.  Same method names and argument meaning as
+the C++ class (and as the C++ facade in cuda-sfm_b200/SfM/sfm.h); torch is used
+only for device memory and streams.  No algorithmic code lives here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .binding import Lib, load_library
+
+OPT_COMPAT, OPT_SCORE_VARIANT, OPT_TRI_INLIERS_ONLY = 1, 2, 3
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _dptr(t) -> C.c_void_p:
+    """Device pointer of a torch CUDA tensor (or a raw int address)."""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _hptr(a: np.ndarray) -> C.c_void_p:
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+class BatchedPairs:
+    """A handle over `pairs` image pairs with n correspondences each."""
+
+    def __init__(self, K, Kinv, pairs: int, max_points: int, max_hypotheses: int, lib: Lib | None = None):
+        self.lib = lib or load_library()
+        self.K = np.ascontiguousarray(K, dtype=np.float32).reshape(9)
+        self.Kinv = np.ascontiguousarray(Kinv, dtype=np.float32).reshape(9)
+        self.pairs, self.max_points, self.max_hypotheses = pairs, max_points, max_hypotheses
+        self.n = 0
+        self.H = 0
+        h = C.c_void_p()
+        fp = C.POINTER(C.c_float)
+        self.lib.call("sfmb200_create", self.K.ctypes.data_as(fp), self.Kinv.ctypes.data_as(fp), pairs, max_points,
+                      max_hypotheses, C.byref(h))
+        self._h = h
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.call("sfmb200_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, option: int, value: int):
+        self.lib.call("sfmb200_set_option", self._h, option, value)
+
+    def use_torch_stream(self, stream=None):
+        torch = _torch()
+        stream = stream or torch.cuda.current_stream()
+        self.lib.call("sfmb200_set_stream", self._h, C.c_void_p(stream.cuda_stream))
+
+    def synchronize(self):
+        self.lib.call("sfmb200_synchronize", self._h)
+
+    # ---- ingest ----
+    def set_points_sift(self, d_sift, n: int):
+        self.lib.call("sfmb200_set_points_sift", self._h, _dptr(d_sift), n)
+        self.n = n
+
+    def set_points_xy(self, d_px, n: int | None = None):
+        n = n if n is not None else d_px.shape[-2]
+        self.lib.call("sfmb200_set_points_xy", self._h, _dptr(d_px), n)
+        self.n = n
+
+    def set_points_xy_host(self, h_px: np.ndarray):
+        h_px = np.ascontiguousarray(h_px, dtype=np.float32)
+        n = h_px.shape[-2]
+        self.lib.call("sfmb200_set_points_xy_host", self._h, _hptr(h_px), n)
+        self.synchronize()   # h_px may be pageable and die with the caller
+        self.n = n
+
+    def set_points_normalised(self, d_x, n: int | None = None):
+        n = n if n is not None else d_x.shape[-2]
+        self.lib.call("sfmb200_set_points_normalised", self._h, _dptr(d_x), n)
+        self.n = n
+
+    # ---- stages ----
+    def estimate_e(self, H: int, seed: int = 0, thr: float = 1e-6, d_idx=None, H_total: int | None = None, h_begin: int = 0):
+        if H_total is None:
+            self.lib.call("sfmb200_estimate_e", self._h, _dptr(d_idx), H, C.c_uint64(seed), C.c_float(thr))
+        else:
+            self.lib.call("sfmb200_estimate_e_slice", self._h, _dptr(d_idx), H_total, h_begin, H, C.c_uint64(seed), C.c_float(thr))
+        self.H = H
+
+    def best_buffer(self):
+        """torch int64 view [pairs] of the packed winners (for dist.all_reduce MAX)."""
+        torch = _torch()
+        p = C.c_void_p()
+        self.lib.call("sfmb200_best_buffer", self._h, C.byref(p))
+        return _tensor_from_ptr(p.value, (self.pairs,), torch.int64)
+
+    def adopt_best(self, H_total: int, seed: int = 0, d_idx=None):
+        self.lib.call("sfmb200_adopt_best", self._h, _dptr(d_idx), H_total, C.c_uint64(seed))
+
+    def pose_candidates(self):
+        self.lib.call("sfmb200_pose_candidates", self._h)
+
+    def choose_pose(self):
+        self.lib.call("sfmb200_choose_pose", self._h)
+
+    def triangulate(self):
+        self.lib.call("sfmb200_triangulate", self._h)
+
+    def run_device(self, d_px, H: int, seed: int = 0, thr: float = 1e-6, n: int | None = None):
+        n = n if n is not None else d_px.shape[-2]
+        self.lib.call("sfmb200_run_device", self._h, _dptr(d_px), n, H, C.c_uint64(seed), C.c_float(thr))
+        self.n, self.H = n, H
+
+    def run_host(self, h_px: np.ndarray, H: int, seed: int = 0, thr: float = 1e-6, want_points: bool = True, out: dict | None = None):
+        """Whole path from host pixel correspondences to host results (the e2e call)."""
+        n = h_px.shape[-2]
+        B = self.pairs
+        if out is None:
+            out = {
+                "E": np.empty((B, 9), np.float32), "P": np.empty((B, 16), np.float32),
+                "pose_index": np.empty(B, np.int32), "inliers": np.empty(B, np.int32),
+                "points": np.empty((B, 4, n), np.float32) if want_points else None,
+            }
+        pts = out.get("points")
+        self.lib.call("sfmb200_run_host", self._h, _hptr(h_px), n, H, C.c_uint64(seed), C.c_float(thr), _hptr(out["E"]),
+                      _hptr(out["P"]), _hptr(out["pose_index"]), _hptr(out["inliers"]),
+                      _hptr(pts) if pts is not None else C.c_void_p(0))
+        self.n, self.H = n, H
+        return out
+
+    # ---- getters ----
+    def get_E(self) -> np.ndarray:
+        out = np.empty((self.pairs, 3, 3), np.float32)
+        self.lib.call("sfmb200_get_E", self._h, _hptr(out))
+        return out
+
+    def set_E(self, E: np.ndarray):
+        E = np.ascontiguousarray(E, dtype=np.float32).reshape(self.pairs, 9)
+        self.lib.call("sfmb200_set_E", self._h, _hptr(E))
+
+    def get_best(self):
+        idx = np.empty(self.pairs, np.int32)
+        cnt = np.empty(self.pairs, np.int32)
+        self.lib.call("sfmb200_get_best", self._h, _hptr(idx), _hptr(cnt))
+        return idx, cnt
+
+    def get_poses(self) -> np.ndarray:
+        out = np.empty((self.pairs, 4, 4, 4), np.float32)
+        self.lib.call("sfmb200_get_poses", self._h, _hptr(out))
+        return out
+
+    def get_pose_index(self) -> np.ndarray:
+        out = np.empty(self.pairs, np.int32)
+        self.lib.call("sfmb200_get_pose_index", self._h, _hptr(out))
+        return out
+
+    def get_points_host(self, pair: int = 0) -> np.ndarray:
+        out = np.empty((4, self.n), np.float32)
+        self.lib.call("sfmb200_get_points_host", self._h, pair, _hptr(out))
+        return out
+
+    def get_points(self, pair: int = 0):
+        torch = _torch()
+        out = torch.empty((4, self.n), dtype=torch.float32, device="cuda")
+        self.lib.call("sfmb200_get_points", self._h, pair, _dptr(out))
+        self.synchronize()
+        return out
+
+    def get_inlier_counts(self, pair: int = 0):
+        torch = _torch()
+        out = torch.empty(self.H, dtype=torch.int32, device="cuda")
+        self.lib.call("sfmb200_get_inlier_counts", self._h, pair, _dptr(out))
+        self.synchronize()
+        return out
+
+    def get_E_candidates(self, pair: int = 0):
+        torch = _torch()
+        out = torch.empty((self.H, 9), dtype=torch.float32, device="cuda")
+        self.lib.call("sfmb200_get_E_candidates", self._h, pair, _dptr(out))
+        self.synchronize()
+        return out
+
+    def get_X(self, image: int, pair: int = 0):
+        torch = _torch()
+        out = torch.empty((3, self.n), dtype=torch.float32, device="cuda")
+        self.lib.call("sfmb200_get_X", self._h, pair, image, _dptr(out))
+        self.synchronize()
+        return out
+
+    def get_inlier_mask(self, pair: int = 0):
+        torch = _torch()
+        out = torch.empty(self.n, dtype=torch.uint8, device="cuda")
+        self.lib.call("sfmb200_get_inlier_mask", self._h, pair, _dptr(out))
+        self.synchronize()
+        return out
+
+    def copy_to_vbo(self, d_pos, d_col, pair: int = 0):
+        self.lib.call("sfmb200_copy_to_vbo", self._h, pair, _dptr(d_pos), _dptr(d_col))
+
+    def score_plan(self) -> dict:
+        out = (C.c_int32 * 4)()
+        self.lib.call("sfmb200_score_plan", self._h, out)
+        return {"variant": out[0], "tiles": out[1], "splits": out[2], "pts_per_split": out[3]}
+
+    def launch_count(self) -> int:
+        return int(self.lib.raw("sfmb200_launch_count")(self._h))
+
+
+def _tensor_from_ptr(ptr: int, shape, dtype):
+    """Zero-copy torch view of device memory owned by the handle."""
+    torch = _torch()
+    n = int(np.prod(shape))
+    itemsize = torch.empty((), dtype=dtype).element_size()
+
+    class _Holder:
+        __cuda_array_interface__ = {
+            "shape": (n * itemsize,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+    raw = torch.as_tensor(_Holder(), device="cuda")
+    return raw.view(dtype).view(*shape)
+
+
+class ImagePair(BatchedPairs):
+    """SfM::Image_pair (SfM/sfm.h:20-60): same constructor arguments and method
+    names; `image_count` is accepted and must be 2 like the reference's only use
+    (src/main.cpp:298).  The reference's estimateE() draws H = N/8 disjoint
+    samples from a host shuffle (sfm.cu:95-104); here H, the seed and the
+    threshold are explicit (defaults reproduce H = N/8 and 1e-6)."""
+
+    def __init__(self, k, k_inv, image_count: int, num_points: int, max_hypotheses: int | None = None, lib: Lib | None = None):
+        if image_count != 2:
+            raise ValueError("Image_pair handles exactly two images (like the reference)")
+        self.image_count, self.num_points = image_count, num_points
+        super().__init__(k, k_inv, 1, num_points, max_hypotheses or max(num_points // 8, 1), lib)
+
+    def fillXU(self, data, n: int | None = None):
+        """data: device SiftPoint array (raw address or uint8 CUDA tensor)."""
+        self.set_points_sift(data, n or self.num_points)
+
+    def estimateE(self, H: int | None = None, seed: int = 0, thr: float = 1e-6, d_idx=None):
+        self.estimate_e(H or max(self.n // 8, 1), seed, thr, d_idx)
+
+    def computePosecandidates(self):
+        self.pose_candidates()
+
+    def choosePose(self):
+        self.choose_pose()
+
+    def linear_triangulation(self):
+        self.triangulate()
+
+    def copyBoidsToVBO(self, vbodptr_positions, vbodptr_velocities):
+        self.copy_to_vbo(vbodptr_positions, vbodptr_velocities)

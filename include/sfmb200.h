@@ -1,0 +1,146 @@
+/* sfmb200 - C ABI of the B200-native two-view SfM hot path.
+ *
+ * Drop-in boundary for the hot path of Black-Phoenix/CUDA-SfM: RANSAC
+ * essential-matrix estimation -> 4 pose candidates -> cheirality selection ->
+ * linear triangulation.  The reference has no FFI layer: its boundary is the
+ * C++ class SfM::Image_pair (SfM/sfm.h:20-60) called from src/main.cpp:298-307.
+ * Each entry point below names the reference interface it replaces; the
+ * source-compatible C++ facade (cuda-sfm_b200/SfM/sfm.h, kernels.h, svd.h) and
+ * the Python mirror (cuda-sfm_b200/image_pair.py) are thin layers over this
+ * file.  See INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative sfmb200_status;
+ *    sfmb200_last_error() gives the message.  Nothing here prints or exits
+ *    (the reference's checkCUDAError prints and exit()s, SfM/common.cu:3-15).
+ *  - pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *  - matrices are row-major float (access2/access3, SfM/common.h:19-20);
+ *    point sets are SoA (3xN / 4xN) exactly as the reference stores them.
+ *  - a handle owns one device (the current one at create time), one stream and
+ *    a pre-sized arena; no allocation happens in any other call.  Handles are
+ *    not thread-safe; different handles are independent.
+ *  - a handle processes a BATCH of `pairs` image pairs with the same number of
+ *    correspondences; SfM::Image_pair is the pairs == 1 case.
+ *  - there is no CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef SFMB200_H
+#define SFMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfmb200_handle sfmb200_t;
+
+typedef enum {
+    SFMB200_OK = 0,
+    SFMB200_ERR_ARG = -1,      /* bad argument (null, out of capacity, n < 8, ...) */
+    SFMB200_ERR_CUDA = -2,     /* a CUDA runtime call failed */
+    SFMB200_ERR_STATE = -3,    /* stage called before its prerequisite */
+    SFMB200_ERR_NODEVICE = -4  /* no CUDA device */
+} sfmb200_status;
+
+/* Options (sfmb200_set_option).  Defaults reproduce the reference's literals. */
+typedef enum {
+    SFMB200_OPT_COMPAT = 1,        /* 1 (default): reference semantics for poses / cheirality / triangulation
+                                      (SURVEY.md Appendix A); 0: textbook geometry with an inlier vote */
+    SFMB200_OPT_SCORE_VARIANT = 2, /* -1 auto (default), 0 scalar FFMA kernel, 1 packed FFMA2 kernel */
+    SFMB200_OPT_TRI_INLIERS_ONLY = 3 /* 0 (default, reference: all N points, sfm.cu:309-336); 1: inliers of E only */
+} sfmb200_option;
+
+const char* sfmb200_last_error(void);
+int sfmb200_version(void);
+
+/* ---- lifetime: SfM::Image_pair::Image_pair / ~Image_pair (SfM/sfm.cu:28-78, 346-359) ---- */
+/* K, Kinv: host 3x3 row-major, as src/main.cpp:292-297 builds them. */
+int sfmb200_create(const float h_K[9], const float h_Kinv[9], int pairs, int max_points, int max_hypotheses,
+                   sfmb200_t** out);
+int sfmb200_destroy(sfmb200_t* h);
+int sfmb200_set_option(sfmb200_t* h, int option, int value);
+/* cudaStream_t to enqueue on (default: a private non-blocking stream). */
+int sfmb200_set_stream(sfmb200_t* h, void* cuda_stream);
+int sfmb200_synchronize(sfmb200_t* h);
+
+/* ---- ingest: Image_pair::fillXU (SfM/sfm.cu:80-92; kernels::copy_point kernels.h:261-279) ---- */
+/* d_sift: device array of n CudaSift SiftPoint structs (576 B each, CudaSift/cudaSift.h:6-22). pairs must be 1. */
+int sfmb200_set_points_sift(sfmb200_t* h, const void* d_sift, int n);
+/* d_px: device [pairs][n][4] pixel coordinates (u1, v1, u2, v2). */
+int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n);
+/* same from host memory (pinned or pageable); copied on the handle's stream. */
+int sfmb200_set_points_xy_host(sfmb200_t* h, const float* h_px, int n);
+/* already normalised camera coordinates (x1, y1, x2, y2), device [pairs][n][4]. */
+int sfmb200_set_points_normalised(sfmb200_t* h, const float* d_x, int n);
+
+/* ---- RANSAC: Image_pair::estimateE (SfM/sfm.cu:94-153) + calculateInliers (155-236) ----
+ * H hypotheses per pair.  d_idx: device int32 [pairs][H_total][8] sample rows
+ * (the reference's shuffled `indices`, sfm.cu:97-106, generalised), or NULL to
+ * draw them on the device from `seed` (counter-based, reproducible on any GPU).
+ * thr: Sampson threshold in normalised coordinates (reference literal 1e-6,
+ * sfm.cu:220).  Hypotheses [h_begin, h_begin + H) of H_total are generated and
+ * scored by this handle: h_begin > 0 is the multi-GPU hypothesis-slice case. */
+int sfmb200_estimate_e(sfmb200_t* h, const int32_t* d_idx, int H, uint64_t seed, float thr);
+int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, int h_begin, int H, uint64_t seed,
+                             float thr);
+/* Device pointer to the per-pair packed winners, uint64 [pairs]:
+ * (count << 32) | (0xFFFFFFFF - global hypothesis index).  Multi-GPU: all-reduce
+ * this buffer with MAX over ranks (8 bytes per pair), then call
+ * sfmb200_adopt_best, which regenerates the winning E from its index. */
+int sfmb200_best_buffer(sfmb200_t* h, uint64_t** d_best);
+int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed);
+
+/* ---- poses: computePosecandidates (sfm.cu:238-252), choosePose (254-307) ---- */
+int sfmb200_pose_candidates(sfmb200_t* h);
+int sfmb200_choose_pose(sfmb200_t* h);
+/* ---- linear_triangulation (sfm.cu:309-344) ---- */
+int sfmb200_triangulate(sfmb200_t* h);
+/* Whole path for host callers: H2D of pixel correspondences, every stage, D2H
+ * of E [pairs][9], P (selected pose) [pairs][16], pose index [pairs], inlier
+ * count [pairs] and, if h_points != NULL, points [pairs][4][n].  One stream
+ * synchronisation at the end. */
+int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t seed, float thr, float* h_E, float* h_P,
+                     int32_t* h_pose_index, int32_t* h_inliers, float* h_points);
+/* Same with device-resident input, no output copies (results stay on the device). */
+int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t seed, float thr);
+
+/* ---- egress: copyBoidsToVBO (sfm.cu:374-383) ---- */
+/* pos / col: device [n][4]; either may be NULL.  Synchronises like the reference. */
+int sfmb200_copy_to_vbo(sfmb200_t* h, int pair, float* d_pos, float* d_col);
+
+/* ---- getters (the reference keeps these members private, sfm.h:21-41) ---- */
+int sfmb200_get_E(sfmb200_t* h, float* h_E /* [pairs][9] */);
+int sfmb200_set_E(sfmb200_t* h, const float* h_E /* [pairs][9] */);   /* inject E (parity harness) */
+int sfmb200_get_best(sfmb200_t* h, int32_t* h_index, int32_t* h_count /* [pairs] each */);
+int sfmb200_get_poses(sfmb200_t* h, float* h_P /* [pairs][4][16] */);
+int sfmb200_get_pose_index(sfmb200_t* h, int32_t* h_ind /* [pairs] */);
+int sfmb200_get_points(sfmb200_t* h, int pair, float* d_points /* device [4][n] */);
+int sfmb200_get_points_host(sfmb200_t* h, int pair, float* h_points /* [4][n] */);
+int sfmb200_get_inlier_counts(sfmb200_t* h, int pair, int32_t* d_counts /* device [H] */);
+int sfmb200_get_E_candidates(sfmb200_t* h, int pair, float* d_E /* device [H][9] */);
+int sfmb200_get_X(sfmb200_t* h, int pair, int image, float* d_X /* device [3][n] */);
+int sfmb200_get_inlier_mask(sfmb200_t* h, int pair, uint8_t* d_mask /* device [n] */);
+/* Raw device views for zero-copy consumers (valid until destroy). */
+int sfmb200_device_views(sfmb200_t* h, float** d_E, float** d_P, int32_t** d_pose_index, float** d_points,
+                         int* point_stride);
+/* how the last estimate was launched: variant, tiles, splits, points per split */
+int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]);
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t sfmb200_launch_count(sfmb200_t* h);
+
+/* ---- measurement helpers ---- */
+/* FP32-pipe probe: runs `iters` iterations of an FFMA (mode 0) or FFMA2 (mode 1)
+ * stream on all SMs; returns lane-FMAs executed in *fmas and device time in *ms. */
+int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms);
+
+/* ---- host-side small-matrix entry points (no GPU): svd.h facade + CPU tests ---- */
+void sfmb200_host_svd3(const float a[9], float u[9], float s[9], float v[9]);
+void sfmb200_host_solve_hypothesis(const float pts[32], float E[9]);
+void sfmb200_host_null4(const float A[16], float x[4]);
+int sfmb200_host_inv4(const float m[16], float out[16]);
+void sfmb200_host_sample_indices(uint64_t seed, uint64_t h, int n, int32_t idx[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFMB200_H */

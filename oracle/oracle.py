@@ -1,0 +1,359 @@
+"""fp64 CPU restatement of the reference hot path (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product path (cuda-sfm_b200/) never
+does: it fails loudly when the CUDA library is missing.
+
+Reference: Black-Phoenix/CUDA-SfM, files under SfM/.  Each function cites the
+file:line whose *stated* algorithm it restates.  Where the reference's code is
+undefined behaviour (inlier scoring reads uninitialised memory, sfm.cu:208-215;
+arg-max off by one, sfm.cu:137) the restatement follows BASELINE.json's
+north_star definition instead (Sampson error, true arg-max, lowest index on
+ties) - see SURVEY.md section 2.3.
+
+PARITY PINNING: the reference ships no asserting tests and no golden vectors
+(SURVEY.md section 4), so the pins are (1) the literals of its print-only tests
+(tests/test_oracle_reference_literals.py), (2) the reference's own CUDA code
+rebuilt unmodified as oracle/_ref/libsfm_ref.so and run on the GPU box
+(tests/test_gpu_reference_parity.py).  Everything else is "pinned by fp64
+math".
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MASK64 = (1 << 64) - 1
+
+# --------------------------------------------------------------------------
+# Camera + synthetic scene (reference intrinsics: src/main.cpp:292-297)
+# --------------------------------------------------------------------------
+F_REF = 2360.0
+W_REF, H_REF = 720, 576
+
+
+def reference_K(w: int = W_REF, h: int = H_REF):
+    """K and K^-1 exactly as src/main.cpp:292-297 builds them (fp32)."""
+    K = np.array([[F_REF, 0, w / 2.0], [0, F_REF, h / 2.0], [0, 0, 1]], dtype=np.float32)
+    Kinv = np.array(
+        [[1.0 / F_REF, 0, -(w / 2.0) / F_REF], [0, 1.0 / F_REF, -(h / 2.0) / F_REF], [0, 0, 1]],
+        dtype=np.float32,
+    )
+    return K, Kinv
+
+
+def _rot(axis, deg):
+    a = np.asarray(axis, float)
+    a = a / np.linalg.norm(a)
+    t = np.deg2rad(deg)
+    Kx = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(t) * Kx + (1 - np.cos(t)) * Kx @ Kx
+
+
+def synthetic_pair(n: int, outlier_frac: float = 0.3, noise_px: float = 1.0, seed: int = 1234):
+    """Two-view scene of BASELINE.json configs 2-5.
+
+    Camera 1 = [I|0]; camera 2: X2 = R X + t with R = 10 degrees about
+    (0.1, 1, 0.05) verging towards the scene (negative angle: with the positive
+    one the two 720x576 views do not overlap) and unit baseline along
+    (1, 0.05, 0.1).  Depth U[4, 8] baselines.  Gaussian pixel noise on both
+    views; outliers replace the image-2 point by a uniform pixel.
+
+    Returns dict: px (n,4) float32 pixel coords (u1,v1,u2,v2), R, t, is_outlier,
+    X (n,3) ground-truth 3-D points in camera-1 frame.
+    """
+    rng_scene = np.random.Generator(np.random.PCG64(seed))
+    rng_out = np.random.Generator(np.random.PCG64(seed + 1))
+    rng_noise = np.random.Generator(np.random.PCG64(seed + 2))
+    f, cx, cy = F_REF, W_REF / 2.0, H_REF / 2.0
+    R = _rot([0.1, 1.0, 0.05], -10.0)
+    t = np.array([1.0, 0.05, 0.1])
+    t = t / np.linalg.norm(t)
+    chunks, Xs, have = [], [], 0
+    while have < n:
+        m = max(4 * (n - have), 1024)
+        z = rng_scene.uniform(4.0, 8.0, m)
+        x = rng_scene.uniform(-1.2, 1.2, m) * z * (cx / f)
+        y = rng_scene.uniform(-1.2, 1.2, m) * z * (cy / f)
+        X = np.stack([x, y, z], 1)
+        X2 = X @ R.T + t
+        u1 = f * X[:, 0] / X[:, 2] + cx
+        v1 = f * X[:, 1] / X[:, 2] + cy
+        u2 = f * X2[:, 0] / X2[:, 2] + cx
+        v2 = f * X2[:, 1] / X2[:, 2] + cy
+        ok = (u1 >= 0) & (u1 < W_REF) & (v1 >= 0) & (v1 < H_REF) & (u2 >= 0) & (u2 < W_REF) & (v2 >= 0) & (v2 < H_REF) & (X2[:, 2] > 0)
+        chunks.append(np.stack([u1, v1, u2, v2], 1)[ok])
+        Xs.append(X[ok])
+        have += int(ok.sum())
+    px = np.concatenate(chunks)[:n]
+    X = np.concatenate(Xs)[:n]
+    px = px + rng_noise.normal(0.0, noise_px, px.shape)
+    is_out = rng_out.random(n) < outlier_frac
+    k = int(is_out.sum())
+    px[is_out, 2] = rng_out.uniform(0, W_REF, k)
+    px[is_out, 3] = rng_out.uniform(0, H_REF, k)
+    return {"px": px.astype(np.float32), "R": R, "t": t, "is_outlier": is_out, "X": X}
+
+
+def normalise_points(px: np.ndarray, Kinv: np.ndarray) -> np.ndarray:
+    """fillXU (SfM/sfm.cu:80-92, kernels.h:261-279): X = K^-1 [u v 1]^T for both
+    images.  Returns (n,4) fp32 (x1,y1,x2,y2); evaluated in fp32 with the same
+    operation order as the CUDA ingest kernel (fma(k01,v, fma(k00,u, k02)) is
+    within 1 ulp of this; tests use a 2-ulp tolerance)."""
+    px = px.astype(np.float32)
+    k = Kinv.astype(np.float32)
+    out = np.empty_like(px)
+    for c, (iu, iv) in enumerate(((0, 1), (2, 3))):
+        u, v = px[:, iu].astype(np.float64), px[:, iv].astype(np.float64)
+        out[:, 2 * c + 0] = (k[0, 0] * u + k[0, 1] * v + k[0, 2]).astype(np.float32)
+        out[:, 2 * c + 1] = (k[1, 0] * u + k[1, 1] * v + k[1, 2]).astype(np.float32)
+    return out
+
+
+# --------------------------------------------------------------------------
+# Sample indices: counter-based generator, bit-exact mirror of
+# cuda-sfm_b200/csrc/hyp_solver.cuh: sample_indices().  The reference draws
+# H = N/8 disjoint samples from one host std::shuffle seeded by random_device
+# (sfm.cu:95-104) - nondeterministic, so the new API takes explicit indices or
+# this generator.
+# --------------------------------------------------------------------------
+def _splitmix64(z: int) -> int:
+    z = (z + 0x9E3779B97F4A7C15) & MASK64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK64
+    return z ^ (z >> 31)
+
+
+def sample_indices_one(seed: int, h: int, n: int) -> list[int]:
+    key = _splitmix64((seed ^ ((h * 0xD1342543DE82EF95) & MASK64)) & MASK64)
+    ctr, idx = 0, []
+    for _ in range(8):
+        while True:
+            r = _splitmix64((key + ctr) & MASK64)
+            ctr += 1
+            cand = ((r >> 32) * n) >> 32
+            if cand not in idx:
+                break
+        idx.append(cand)
+    return idx
+
+
+def sample_indices(seed: int, H: int, n: int, h0: int = 0) -> np.ndarray:
+    """Vectorised version of sample_indices_one for rows h0..h0+H-1."""
+    def sm(z):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+    with np.errstate(over="ignore"):
+        h = np.arange(h0, h0 + H, dtype=np.uint64)
+        key = sm(np.uint64(seed) ^ (h * np.uint64(0xD1342543DE82EF95)))
+        ctr = np.zeros(H, dtype=np.uint64)
+        out = np.full((H, 8), -1, dtype=np.int64)
+        for j in range(8):
+            todo = np.ones(H, dtype=bool)
+            while todo.any():
+                r = sm(key[todo] + ctr[todo])
+                ctr[todo] += np.uint64(1)
+                cand = (((r >> np.uint64(32)) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+                dup = (out[todo, :j] == cand[:, None]).any(axis=1) if j else np.zeros(cand.shape, bool)
+                rows = np.flatnonzero(todo)
+                okrows = rows[~dup]
+                out[okrows, j] = cand[~dup]
+                todo[okrows] = False
+    return out.astype(np.int32)
+
+
+# --------------------------------------------------------------------------
+# Hypothesis generation (K3-K7)
+# --------------------------------------------------------------------------
+def design_matrix(x: np.ndarray) -> np.ndarray:
+    """kernels::kernels (SfM/kernels.h:247-257): row = kron((x1,y1,1),(x2,y2,1))
+    so that the null vector reshaped row-major satisfies x1^T E x2 = 0."""
+    x1, y1, x2, y2 = (x[..., i].astype(np.float64) for i in range(4))
+    o = np.ones_like(x1)
+    return np.stack([x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, o], -1)
+
+
+def project_essential(E: np.ndarray) -> np.ndarray:
+    """normalizeE (SfM/kernels.h:281-295): E <- U diag(1,1,0) V^T."""
+    U, _, Vt = np.linalg.svd(E)
+    return U[..., :, :2] @ Vt[..., :2, :]
+
+
+def hypotheses(x: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """E candidates (H,3,3) in fp64 for sample rows idx (H,8) over points x (n,4).
+    Null vector of the 8x9 design matrix (regular_svd + row_extraction_kernel,
+    kernels.h:211-234, 452-458), then rank-2 projection.  Sign is arbitrary."""
+    A = design_matrix(x[idx])                       # (H,8,9)
+    _, _, Vt = np.linalg.svd(A)                     # full: (H,9,9)
+    E = Vt[:, -1, :].reshape(-1, 3, 3)
+    return project_essential(E)
+
+
+def e_distance(Ea: np.ndarray, Eb: np.ndarray) -> np.ndarray:
+    """Relative Frobenius distance up to sign and scale (north_star tolerance 1e-4)."""
+    a = Ea.reshape(len(Ea), -1).astype(np.float64)
+    b = Eb.reshape(len(Eb), -1).astype(np.float64)
+    na = np.linalg.norm(a, axis=1, keepdims=True)
+    nb = np.linalg.norm(b, axis=1, keepdims=True)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a, b = a / na, b / nb
+    return np.minimum(np.linalg.norm(a - b, axis=1), np.linalg.norm(a + b, axis=1))
+
+
+# --------------------------------------------------------------------------
+# Inlier scoring (calculateInliers' stated intent, sfm.cu:155-221, with the
+# Sampson error north_star mandates; threshold literal 1e-6 from sfm.cu:220)
+# --------------------------------------------------------------------------
+def sampson_terms(E: np.ndarray, x: np.ndarray):
+    """num^2 and den of the Sampson error for every (hypothesis, point), fp64.
+    Convention x1^T E x2 = 0: l = E x2, m = E^T x1,
+    err = (x1.l)^2 / (l0^2 + l1^2 + m0^2 + m1^2)."""
+    E = E.reshape(-1, 3, 3).astype(np.float64)
+    x1 = np.stack([x[:, 0], x[:, 1], np.ones(len(x))], 0).astype(np.float64)   # (3,n)
+    x2 = np.stack([x[:, 2], x[:, 3], np.ones(len(x))], 0).astype(np.float64)
+    l = E @ x2                                        # (H,3,n)
+    m = np.transpose(E, (0, 2, 1)) @ x1               # (H,3,n)
+    num = (x1[None] * l).sum(1)
+    den = l[:, 0] ** 2 + l[:, 1] ** 2 + m[:, 0] ** 2 + m[:, 1] ** 2
+    return num * num, den
+
+
+def inlier_counts(E: np.ndarray, x: np.ndarray, thr: float = 1e-6, band: float = 1e-6, chunk: int = 256):
+    """Counts (H,) of points with num^2 < thr*den, plus the number of borderline
+    points per hypothesis (|num^2 - thr*den| <= band*thr*den + tiny): the CUDA
+    fp32 count must lie in [count - borderline, count + borderline]."""
+    E = E.reshape(-1, 3, 3)
+    cnt = np.zeros(len(E), np.int64)
+    amb = np.zeros(len(E), np.int64)
+    for s in range(0, len(E), chunk):
+        n2, den = sampson_terms(E[s:s + chunk], x)
+        d = n2 - thr * den
+        cnt[s:s + chunk] = (d < 0).sum(1)
+        amb[s:s + chunk] = (np.abs(d) <= band * thr * den + 1e-300).sum(1)
+    return cnt, amb
+
+
+def argmax_first(counts: np.ndarray) -> int:
+    """thrust::max_element semantics (sfm.cu:135-136): first maximum.  The
+    reference then subtracts one (sfm.cu:137, SURVEY Q13: a bug); we do not."""
+    return int(np.argmax(counts))
+
+
+# --------------------------------------------------------------------------
+# Pose candidates and cheirality (computePosecandidates sfm.cu:238-252,
+# candidate_kernels kernels.h:357-385, choosePose sfm.cu:254-307)
+# --------------------------------------------------------------------------
+def svd_rot(E: np.ndarray):
+    """SVD with the reference svd()'s contract (svd.h:311-335): U, V proper
+    rotations, singular values sorted, the last one carries the sign."""
+    U, S, Vt = np.linalg.svd(E.astype(np.float64))
+    V = Vt.T
+    if np.linalg.det(U) < 0:
+        U[:, 2] = -U[:, 2]
+        S[2] = -S[2]
+    if np.linalg.det(V) < 0:
+        V[:, 2] = -V[:, 2]
+        S[2] = -S[2]
+    return U, S, V
+
+
+def det_reference_typo(a: np.ndarray) -> float:
+    """det() exactly as written at svd.h:337-341 (third term a0*a3*a8)."""
+    a = a.reshape(9)
+    return float(a[0] * a[4] * a[8] - a[0] * a[5] * a[7] - a[0] * a[3] * a[8] + a[1] * a[5] * a[6] + a[2] * a[3] * a[7] - a[2] * a[4] * a[6])
+
+
+def pose_candidates(E: np.ndarray, compat: bool = True) -> np.ndarray:
+    """Four 4x4 candidates.  compat=True replicates the reference
+    (SURVEY Appendix A.4): P_i = [ (U W(^T) V^T)^T | +-u3 ; 0 0 0 1 ],
+    W for i<2, W^T for i>=2, sign - for i in {0,2}, with the det-typo sign fix
+    applied to V.  compat=False is textbook geometry for the x1^T E x2 = 0
+    convention: X2 = R X1 + t with E^T = [t]x R."""
+    U, _, V = svd_rot(E)
+    W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], float)
+    P = np.zeros((4, 4, 4))
+    if compat:
+        tmp = U @ V.T
+        if det_reference_typo(tmp) < 0:
+            V = -V
+        for i in range(4):
+            Rm = U @ (W if i < 2 else W.T) @ V.T
+            s = -1.0 if i in (0, 2) else 1.0
+            P[i, :3, :3] = Rm.T
+            P[i, :3, 3] = s * U[:, 2]
+            P[i, 3, 3] = 1.0
+    else:
+        # x1^T E x2 = 0  <=>  x2^T E^T x1 = 0, so F := E^T = [t]x R maps cam1->cam2.
+        # svd(E) = U S V^T  =>  E^T = V S U^T: R = V W(^T) U^T, t = +-v3.
+        for i in range(4):
+            Rm = V @ (W if i < 2 else W.T) @ U.T
+            if np.linalg.det(Rm) < 0:
+                Rm = -Rm
+            s = -1.0 if i in (0, 2) else 1.0
+            P[i, :3, :3] = Rm
+            P[i, :3, 3] = s * V[:, 2]
+            P[i, 3, 3] = 1.0
+    return P
+
+
+def dlt_rows(x: np.ndarray, M: np.ndarray) -> np.ndarray:
+    """compute_linear_triangulation_A (kernels.h:387-431): per point the 4x4
+    [x1*I[2]-I[0]; y1*I[2]-I[1]; x2*M[2]-M[0]; y2*M[2]-M[1]] with camera 1 = I4."""
+    x = np.atleast_2d(x).astype(np.float64)
+    n = len(x)
+    I4 = np.eye(4)
+    A = np.empty((n, 4, 4))
+    A[:, 0] = x[:, 0:1] * I4[2] - I4[0]
+    A[:, 1] = x[:, 1:2] * I4[2] - I4[1]
+    A[:, 2] = x[:, 2:3] * M[2] - M[0]
+    A[:, 3] = x[:, 3:4] * M[2] - M[1]
+    return A
+
+
+def triangulate(x: np.ndarray, M: np.ndarray) -> np.ndarray:
+    """linear_triangulation (sfm.cu:309-336) + normalize_pt_kernal
+    (kernels.h:433-450): null vector of each A, de-homogenised; (0,0,0,1) when
+    w == 0.  Returns (4,n) SoA like d_final_points."""
+    A = dlt_rows(x, M)
+    _, _, Vt = np.linalg.svd(A)
+    v = Vt[:, -1, :]
+    w = v[:, 3]
+    out = np.zeros((4, len(v)))
+    ok = w != 0
+    out[:3, ok] = (v[ok, :3] / w[ok, None]).T
+    out[3] = 1.0
+    return out
+
+
+def choose_pose(x: np.ndarray, P: np.ndarray, compat: bool = True, mask: np.ndarray | None = None):
+    """choosePose (sfm.cu:254-297).  compat: cheirality of correspondence 0 only,
+    each candidate inverted in place, depth tested in both frames, the LAST
+    passing index wins (default 0); returns (P_ind, P_after) where P_after holds
+    the inverses.  correct mode: vote over (masked) points with
+    X2 = P_i X, arg-max of votes (first max), P unchanged."""
+    if compat:
+        Pinv = np.stack([np.linalg.inv(P[i]) for i in range(4)])
+        ind = 0
+        for i in range(4):
+            X = triangulate(x[0:1], P[i])[:, 0]
+            z1 = X[2]
+            z2 = (Pinv[i] @ X)[2]
+            if z1 > 0 and z2 > 0:
+                ind = i
+        return ind, Pinv
+    xs = x if mask is None else x[mask]
+    votes = []
+    for i in range(4):
+        X = triangulate(xs, P[i])
+        z2 = (P[i] @ X)[2]
+        votes.append(int(((X[2] > 0) & (z2 > 0)).sum()))
+    return int(np.argmax(votes)), P.copy()
+
+
+def to_vbo(points_soa: np.ndarray) -> np.ndarray:
+    """kernCopyPositionsToVBO (kernels.h:471-483): 4xN SoA -> Nx4 AoS (x,y,z,1)."""
+    out = points_soa.T.copy()
+    out[:, 3] = 1.0
+    return out
