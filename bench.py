@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's metric: RANSAC hyp x corr evals/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the whole hot path over one synthetic image pair of
+BASELINE config 2 (10,000 correspondences, 30 % outliers, 1 px noise, 65,536
+hypotheses): ingest (fillXU) -> hypothesis generation -> Sampson scoring + fused
+arg-max -> 4 pose candidates -> cheirality -> linear triangulation.  `value` is
+H*N evaluations per second of device time with the pixel correspondences
+already in HBM; `e2e` is the same through the C-ABI host entry point
+(sfmb200_run_host) with pinned host buffers, copies inside the timed region.
+N > 1: one process per GPU (torchrun), pairs sharded across ranks, no data-path
+collective (weak scaling); the barrier + max over ranks follows the contract.
+
+--impl reference times the reference's OWN implementation of the path, which is
+CUDA (it has no CPU path): its unmodified sources rebuilt for sm_100a as
+oracle/_ref/libsfm_ref.so, same config, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+N_CORR, N_HYP, THR, SEED = 10_000, 65_536, 1e-6, 1237
+FLOP_PER_EVAL = 34.0              # 15 FFMA x2 + 3 FMUL + 1 compare
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows, self.proc = [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(gpus: int):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def cpu_baseline(O, x, full: bool = True) -> dict:
+    """The oracle's C port on the host cores: hypothesis generation (fp64 one-sided
+    Jacobi) + fp32 Sampson scoring + arg-max for the whole config-2 step."""
+    path = os.path.join(ROOT, "oracle", "_ref", "liboracle_c.so")
+    L = C.CDLL(path)
+    L.oracle_threads.restype = C.c_int
+    cores = L.oracle_threads()
+    H = N_HYP if full else N_HYP // 8
+    idx = O.sample_indices(SEED, H, len(x))
+    fp, ip, dp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    E = np.zeros((H, 9))
+    cnt = np.zeros(H, np.int32)
+    t0 = time.perf_counter()
+    L.oracle_hypotheses_f64(x.ctypes.data_as(fp), len(x), idx.ctypes.data_as(ip), H, E.ctypes.data_as(dp))
+    t1 = time.perf_counter()
+    E32 = E.astype(np.float32)
+    L.oracle_counts_f32(E32.ctypes.data_as(fp), H, x.ctypes.data_as(fp), len(x), C.c_float(THR), cnt.ctypes.data_as(ip))
+    best = L.oracle_argmax_first(cnt.ctypes.data_as(ip), H)
+    t2 = time.perf_counter()
+    return {"value": H * len(x) / (t2 - t0), "unit": "hyp*corr evals/s", "cores": cores, "kind": "port",
+            "sample": f"one config-2 estimateE step: {H} hypotheses x {len(x)} correspondences "
+                      f"(hypgen {t1 - t0:.2f} s + scoring/arg-max {t2 - t1:.2f} s), oracle/oracle_c.c with OpenMP",
+            "best_inliers": int(cnt[best])}
+
+
+def cv2_baseline(scene, K) -> dict | None:
+    """OpenCV findEssentialMat(RANSAC) + recoverPose + triangulatePoints on the host
+    cores: ms/pair only - its iteration count is not observable."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    p1 = scene["px"][:, :2].astype(np.float64)
+    p2 = scene["px"][:, 2:].astype(np.float64)
+    Kd = K.astype(np.float64)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        E, mask = cv2.findEssentialMat(p1, p2, Kd, method=cv2.RANSAC, prob=1 - 1e-12, threshold=2.36, maxIters=N_HYP)
+        _, R, t, mask2 = cv2.recoverPose(E, p1, p2, Kd, mask=mask)
+        P1 = Kd @ np.eye(3, 4)
+        P2 = Kd @ np.hstack([R, t])
+        cv2.triangulatePoints(P1, P2, p1.T, p2.T)
+        ts.append(time.perf_counter() - t0)
+    return {"ms_per_pair": 1e3 * min(ts), "threads": cv2.getNumThreads(), "cores": os.cpu_count(),
+            "what": "cv2 4.x findEssentialMat(RANSAC, 5-point, adaptive stop) + recoverPose + triangulatePoints, best of 3",
+            "inliers": int(mask.sum())}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = dist_setup(args.gpus)
+    pkg, O = entry.load_package(), entry.load_oracle()
+    K, Kinv = O.reference_K()
+    # pairs sharded across ranks: each rank owns its own synthetic pair (weak scaling)
+    scene = O.synthetic_pair(N_CORR, 0.3, 1.0, seed=1234 + 10 * rank)
+    px = scene["px"]
+    d_px = torch.from_numpy(px).cuda()
+    h_px = torch.from_numpy(px).pin_memory()
+    h = pkg.BatchedPairs(K, Kinv, 1, N_CORR, N_HYP)
+    h.set_option(4, 1)           # per-stage CUDA events
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def step():
+        h.run_device(d_px, N_HYP, SEED, THR)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+        flush.fill_(1)
+    barrier(world)
+    h.set_option(4, 1)           # reset the stage ring
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = h.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier(world)
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+        flush.fill_(i & 0xFF)    # L2 flush between timed iterations (outside the events)
+    barrier(world)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = h.launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * N_HYP * N_CORR / (ms_per_step * 1e-3)
+    stage = h.stage_times()
+    stage_ms = stage.mean(axis=0) if len(stage) else np.zeros(7)
+    best_idx, best_cnt = h.get_best()
+
+    # ---- end to end through the C-ABI host call: pinned H2D + D2H inside ----
+    out = {"E": np.empty((1, 9), np.float32), "P": np.empty((1, 16), np.float32), "pose_index": np.empty(1, np.int32),
+           "inliers": np.empty(1, np.int32), "points": torch.empty((1, 4, N_CORR), dtype=torch.float32).pin_memory().numpy()}
+    hp = h_px.numpy()
+    for _ in range(3):
+        h.run_host(hp, N_HYP, SEED, THR, out=out)
+    barrier(world)
+    e2e_t = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h.run_host(hp, N_HYP, SEED, THR, out=out)     # returns after its own stream sync
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_total.item()) * 1e3 / args.steps
+    h2d = px.nbytes
+    d2h = 9 * 4 + 16 * 4 + 4 + 4 + 4 * N_CORR * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- rank 0: roofline, probes, CPU baselines, JSON line ----
+    lib = pkg.load_library()
+    probe = {}
+    for mode, name in ((0, "ffma"), (1, "ffma2")):
+        fmas, ms = C.c_double(), C.c_float()
+        lib.call("sfmb200_fma_probe", mode, 2000, C.byref(fmas), C.byref(ms))
+        probe[name + "_tflops"] = 2 * fmas.value / (ms.value * 1e-3) / 1e12
+    peaks = measured_peaks()
+    score_ms = float(stage_ms[2])
+    achieved = FLOP_PER_EVAL * N_HYP * N_CORR / (score_ms * 1e-3) / 1e12 if score_ms > 0 else None
+    fp32_probe = max(probe.values())
+    roofline = {
+        "kernel": "score_kernel (Sampson scoring + fused arg-max)", "bound": "fp32",
+        "achieved": achieved, "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+        "frac": achieved / FP32_NOMINAL_TFLOPS if achieved else None,
+        "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has HBM and bf16 only; "
+                       "this kernel is FP32 CUDA-core bound, not hbm/tensor)",
+        "peak_measured_probe": fp32_probe, "frac_of_measured_probe": achieved / fp32_probe if achieved else None,
+        "probe": probe, "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": N_HYP * N_CORR,
+        "kernel_ms": score_ms, "evals_per_s_kernel": N_HYP * N_CORR / (score_ms * 1e-3) if score_ms > 0 else None,
+        "traffic": None,
+    }
+    tri_ms = float(stage_ms[6])
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tri = {"kernel": "triangulate_kernel", "bound": "hbm", "achieved": 32.0 * N_CORR / (tri_ms * 1e-3) / 1e9 if tri_ms > 0 else None,
+           "peak": hbm, "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback",
+           "bytes_per_point": 32, "kernel_ms": tri_ms,
+           "note": "10k points = 320 KB: launch-latency bound at this size; see profiles/ for the 1M-point run"}
+    tri["frac"] = tri["achieved"] / hbm if tri["achieved"] else None
+    x = O.normalise_points(px, Kinv)
+    cpu = cpu_baseline(O, x)
+    line = {
+        "metric": "RANSAC hyp*corr evals/s", "value": value, "unit": "hyp*corr evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: synthetic two-view scene, 10,000 correspondences, 30% outliers, "
+                               "1 px noise, 65,536 hypotheses, full hot path per pair (ingest, hypgen, scoring+arg-max, "
+                               "pose candidates, cheirality, triangulation)", "pairs_per_step_per_gpu": 1,
+                   "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective",
+                   "l2": "flushed between timed iterations (256 MiB write)", "threshold": THR, "seed": SEED,
+                   "score_plan": h.score_plan()},
+        "e2e": {"value": world * N_HYP * N_CORR / (e2e_ms * 1e-3), "unit": "hyp*corr evals/s", "ms_per_pair": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "sfmb200_run_host (C ABI), pinned host buffers, host wall clock around the call"},
+        "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
+        "stage_ms": {k: float(v) for k, v in zip(pkg.BatchedPairs.STAGES, stage_ms)},
+        "hypotheses_per_s": N_HYP / (float(stage_ms[1]) * 1e-3) if stage_ms[1] > 0 else None,
+        "e_estimate_ms_per_pair": float(stage_ms[1] + stage_ms[2] + stage_ms[3]),
+        "pairs_per_s": world / (ms_per_step * 1e-3),
+        "result": {"best_hypothesis": int(best_idx[0]), "inliers": int(best_cnt[0]), "pose_index": int(out["pose_index"][0])},
+        "roofline": roofline, "roofline_triangulation": tri, "cpu_baseline": cpu, "cv2_baseline": cv2_baseline(scene, K),
+        "clocks": clocks, "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    O = entry.load_oracle()
+    K, Kinv = O.reference_K()
+    scene = O.synthetic_pair(N_CORR, 0.3, 1.0, seed=1234)
+    px = scene["px"]
+    base = {"impl": "reference", "metric": "RANSAC hyp*corr evals/s", "unit": "hyp*corr evals/s", "n_gpus": 1,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    path = os.path.join(ROOT, "oracle", "_ref", "libsfm_ref.so")
+    if not (os.path.exists(path) and torch.cuda.is_available()):
+        # no rebuilt reference (or no GPU for its CUDA-only path): time the oracle port instead
+        x = O.normalise_points(px, Kinv)
+        cpu = cpu_baseline(O, x)
+        line = dict(base, value=cpu["value"], steps=1, warmup=0, ms_per_step=1e3 * N_HYP * N_CORR / cpu["value"],
+                    config={"workload": "BASELINE config 2 estimateE on the host cores (oracle port; oracle/_ref/libsfm_ref.so or GPU missing)"},
+                    cpu_baseline=cpu, e2e={"value": cpu["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+    torch.cuda.set_device(0)
+    L = C.CDLL(path)
+    L.ref_create.restype = C.c_void_p
+    for name in ("ref_estimateE_injected", "ref_computePosecandidates", "ref_choosePose", "ref_linear_triangulation"):
+        getattr(L, name).restype = C.c_float
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    r = C.c_void_p(L.ref_create(K.reshape(9).ctypes.data_as(fp), Kinv.reshape(9).ctypes.data_as(fp), N_CORR))
+    H = N_HYP
+    idx = O.sample_indices(SEED, H, N_CORR)
+
+    def step(Hs):
+        t0 = time.perf_counter()
+        L.ref_fillXU(r, px.ctypes.data_as(fp))
+        t_e = L.ref_estimateE_injected(r, idx.ctypes.data_as(ip), Hs, None)
+        t_pc = L.ref_computePosecandidates(r)
+        t_cp = L.ref_choosePose(r)
+        t_tr = L.ref_linear_triangulation(r)
+        return time.perf_counter() - t0, (t_e, t_pc, t_cp, t_tr)
+
+    # bound the run: first step at full size, then shrink the hypothesis sample if K steps would not fit
+    t_first, _ = step(H)
+    budget = 150.0
+    Hs = H
+    if t_first * (args.steps + max(args.warmup, 1)) > budget:
+        Hs = max(1024, int(H * budget / (t_first * (args.steps + max(args.warmup, 1)))) // 1024 * 1024)
+    for _ in range(max(args.warmup, 1)):
+        step(Hs)
+    ts, stages = [], []
+    for _ in range(args.steps):
+        t, st = step(Hs)
+        ts.append(t)
+        stages.append(st)
+    ms = 1e3 * sum(ts) / len(ts)
+    value = Hs * N_CORR / (ms * 1e-3)
+    st = np.mean(np.array(stages), axis=0)
+    sample = (f"reference's own CUDA path (SfM/sfm.cu rebuilt unmodified for sm_100a, oracle/ref_harness.cu) on the GPU: "
+              f"fillXU + estimateE body with {Hs} of {H} injected hypotheses x {N_CORR} correspondences + "
+              f"computePosecandidates + choosePose + linear_triangulation; host wall clock incl. its cudaMalloc/syncs")
+    line = dict(base, value=value, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms,
+                config={"workload": "BASELINE config 2: 10,000 correspondences, 30% outliers, 65,536 hypotheses, full hot path per pair",
+                        "hypotheses_per_step": Hs, "first_full_size_step_s": t_first},
+                stage_ms={"estimateE": float(st[0]), "computePosecandidates": float(st[1]), "choosePose": float(st[2]),
+                          "linear_triangulation": float(st[3])},
+                cpu_baseline={"value": value, "unit": base["unit"], "cores": 1, "kind": "reference", "sample": sample,
+                              "note": "the reference has no CPU path (README.md:12); this is its CUDA path on the same B200"},
+                e2e={"value": value, "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line), flush=True)
+    L.ref_destroy(r)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

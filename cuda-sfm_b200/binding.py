@@ -62,6 +62,7 @@ SIGNATURES = {
     "sfmb200_device_views": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int)]),
     "sfmb200_score_plan": (C.c_int, [_vp, _i]),
     "sfmb200_launch_count": (C.c_int64, [_vp]),
+    "sfmb200_stage_times": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_int)]),
     "sfmb200_fma_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "sfmb200_host_svd3": (None, [_f, _f, _f, _f]),
     "sfmb200_host_solve_hypothesis": (None, [_f, _f]),

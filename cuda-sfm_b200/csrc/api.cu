@@ -46,7 +46,26 @@ struct sfmb200_handle {
     ScorePlan plan;
     int64_t launches;
     void* arena;
+    // optional per-stage timing (SFMB200_OPT_PROFILE): ring of event sets, one set
+    // per run_device / run_host call, 8 boundary marks -> 7 stage durations
+    int profile;
+    int prof_cur;                 // set being recorded
+    long long prof_total;         // sets started since profiling was enabled
+    cudaEvent_t (*prof_ev)[8];    // [PROF_RING][8]
+    unsigned char* prof_mask;     // [PROF_RING] bit k = mark k recorded
 };
+static const int PROF_RING = 256;
+static inline void prof_mark(sfmb200_handle* h, int k) {
+    if (!h->profile) return;
+    cudaEventRecord(h->prof_ev[h->prof_cur][k], h->stream);
+    h->prof_mask[h->prof_cur] |= (unsigned char)(1u << k);
+}
+static inline void prof_next(sfmb200_handle* h) {
+    if (!h->profile) return;
+    h->prof_cur = (int)(h->prof_total % PROF_RING);
+    h->prof_total++;
+    h->prof_mask[h->prof_cur] = 0;
+}
 
 extern "C" {
 
@@ -133,6 +152,12 @@ int sfmb200_destroy(sfmb200_t* h) {
     if (!h) return SFMB200_OK;
     cudaStreamSynchronize(h->stream);
     if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->prof_ev) {
+        for (int i = 0; i < PROF_RING; i++)
+            for (int k = 0; k < 8; k++) cudaEventDestroy(h->prof_ev[i][k]);
+        delete[] h->prof_ev;
+        delete[] h->prof_mask;
+    }
     cudaFree(h->arena);
     delete h;
     return SFMB200_OK;
@@ -147,6 +172,18 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
             h->score_variant = value;
             break;
         case SFMB200_OPT_TRI_INLIERS_ONLY: h->tri_inliers_only = value ? 1 : 0; break;
+        case SFMB200_OPT_PROFILE:
+            if (value && !h->prof_ev) {
+                h->prof_ev = new cudaEvent_t[PROF_RING][8];
+                h->prof_mask = new unsigned char[PROF_RING]();
+                for (int i = 0; i < PROF_RING; i++)
+                    for (int k = 0; k < 8; k++) CK(cudaEventCreate(&h->prof_ev[i][k]));
+            }
+            h->profile = value ? 1 : 0;
+            h->prof_total = 0;
+            h->prof_cur = 0;
+            if (h->prof_mask) memset(h->prof_mask, 0, PROF_RING);
+            break;
         default: return fail(SFMB200_ERR_ARG, "unknown option%s");
     }
     return SFMB200_OK;
@@ -190,7 +227,9 @@ int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n) {
     int rc = check_n(h, d_px, n);
     if (rc) return rc;
     h->s.n = n;
+    prof_mark(h, 0);
     launch_ingest_xy(h->s, d_px, n, h->stream);
+    prof_mark(h, 1);
     CKL();
     h->launches++;
     h->have_points = true;
@@ -225,10 +264,13 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     h->thr = thr;
     h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
     launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->stream);
+    prof_mark(h, 2);
     CKL();
     launch_score(h->s, h->plan, H, h_begin, thr, h->stream);
+    prof_mark(h, 3);
     CKL();
     launch_select(h->s, h_begin, h->stream);
+    prof_mark(h, 4);
     CKL();
     h->launches += 3;
     h->have_candidates = true;
@@ -260,6 +302,7 @@ int sfmb200_pose_candidates(sfmb200_t* h) {
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_E) return fail(SFMB200_ERR_STATE, "pose_candidates before an essential matrix exists%s");
     launch_pose_candidates(h->s, h->compat, h->stream);
+    prof_mark(h, 5);
     CKL();
     h->launches++;
     h->have_pose = true;
@@ -269,6 +312,7 @@ int sfmb200_choose_pose(sfmb200_t* h) {
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_pose || !h->have_points) return fail(SFMB200_ERR_STATE, "choose_pose before pose_candidates%s");
     launch_choose_pose(h->s, h->compat, h->thr > 0 ? h->thr : 1e-6f, h->stream);
+    prof_mark(h, 6);
     CKL();
     h->launches++;
     return SFMB200_OK;
@@ -277,6 +321,7 @@ int sfmb200_triangulate(sfmb200_t* h) {
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_pose || !h->have_points) return fail(SFMB200_ERR_STATE, "triangulate before pose_candidates%s");
     launch_triangulate(h->s, h->tri_inliers_only, h->thr > 0 ? h->thr : 1e-6f, h->stream);
+    prof_mark(h, 7);
     CKL();
     h->launches++;
     return SFMB200_OK;
@@ -291,6 +336,7 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
 }
 
 int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t seed, float thr) {
+    if (h) prof_next(h);
     int rc = sfmb200_set_points_xy(h, d_px, n);
     if (rc) return rc;
     return run_stages(h, H, seed, thr);
@@ -304,6 +350,7 @@ __global__ void gather_selected_pose_kernel(DeviceState s, float* out) {
 
 int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t seed, float thr, float* h_E, float* h_P,
                      int32_t* h_pose_index, int32_t* h_inliers, float* h_points) {
+    if (h) prof_next(h);
     int rc = sfmb200_set_points_xy_host(h, h_px, n);
     if (rc) return rc;
     if ((rc = run_stages(h, H, seed, thr))) return rc;
@@ -453,6 +500,22 @@ int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]) {
     return SFMB200_OK;
 }
 int64_t sfmb200_launch_count(sfmb200_t* h) { return h ? h->launches : 0; }
+
+int sfmb200_stage_times(sfmb200_t* h, int max_sets, float* ms, int* sets) {
+    if (!h || !ms || !sets) return fail(SFMB200_ERR_ARG, "null argument%s");
+    *sets = 0;
+    if (!h->prof_ev) return fail(SFMB200_ERR_STATE, "profiling was never enabled%s");
+    CK(cudaStreamSynchronize(h->stream));
+    long long have = h->prof_total < PROF_RING ? h->prof_total : PROF_RING;
+    long long first = h->prof_total - have;
+    for (long long t = first; t < h->prof_total && *sets < max_sets; t++) {
+        int i = (int)(t % PROF_RING);
+        if (h->prof_mask[i] != 0xFF) continue;
+        for (int k = 0; k < 7; k++) CK(cudaEventElapsedTime(&ms[(size_t)(*sets) * 7 + k], h->prof_ev[i][k], h->prof_ev[i][k + 1]));
+        (*sets)++;
+    }
+    return SFMB200_OK;
+}
 
 int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms) {
     if (!fmas || !ms || iters < 1 || mode < 0 || mode > 1) return fail(SFMB200_ERR_ARG, "bad argument%s");

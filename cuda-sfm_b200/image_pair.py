@@ -50,6 +50,9 @@ class BatchedPairs:
         self.lib.call("sfmb200_create", self.K.ctypes.data_as(fp), self.Kinv.ctypes.data_as(fp), pairs, max_points,
                       max_hypotheses, C.byref(h))
         self._h = h
+        # Enqueue on torch's current stream so that tensors produced / consumed by
+        # torch around these calls are ordered without extra synchronisation.
+        self.use_torch_stream()
 
     # ---- lifetime ----
     def close(self):
@@ -218,6 +221,15 @@ class BatchedPairs:
         out = (C.c_int32 * 4)()
         self.lib.call("sfmb200_score_plan", self._h, out)
         return {"variant": out[0], "tiles": out[1], "splits": out[2], "pts_per_split": out[3]}
+
+    STAGES = ("ingest", "hypgen", "score", "select", "pose_candidates", "choose_pose", "triangulate")
+
+    def stage_times(self, max_sets: int = 256) -> np.ndarray:
+        """ms [sets][7] of the most recent profiled run_* calls (option 4)."""
+        ms = np.zeros((max_sets, 7), np.float32)
+        sets = C.c_int(0)
+        self.lib.call("sfmb200_stage_times", self._h, max_sets, _hptr(ms), C.byref(sets))
+        return ms[: sets.value]
 
     def launch_count(self) -> int:
         return int(self.lib.raw("sfmb200_launch_count")(self._h))

@@ -48,11 +48,8 @@ def estimate_e_sharded(handle, H_total: int, seed: int, thr: float, rank: int, w
     lo, hi = shard_range(H_total, rank, world)
     handle.estimate_e(hi - lo, seed, thr, d_idx=d_idx, H_total=H_total, h_begin=lo)
     if world > 1:
-        import torch
-
-        best = handle.best_buffer()
-        handle.synchronize()                       # the all-reduce runs on torch's stream
-        allreduce_best(best, group)
-        torch.cuda.current_stream().synchronize()
+        # the handle enqueues on torch's current stream, and torch orders the
+        # collective against that stream, so no host synchronisation is needed
+        allreduce_best(handle.best_buffer(), group)
         handle.adopt_best(H_total, seed, d_idx)
     return lo, hi

@@ -47,7 +47,9 @@ typedef enum {
     SFMB200_OPT_COMPAT = 1,        /* 1 (default): reference semantics for poses / cheirality / triangulation
                                       (SURVEY.md Appendix A); 0: textbook geometry with an inlier vote */
     SFMB200_OPT_SCORE_VARIANT = 2, /* -1 auto (default), 0 scalar FFMA kernel, 1 packed FFMA2 kernel */
-    SFMB200_OPT_TRI_INLIERS_ONLY = 3 /* 0 (default, reference: all N points, sfm.cu:309-336); 1: inliers of E only */
+    SFMB200_OPT_TRI_INLIERS_ONLY = 3, /* 0 (default, reference: all N points, sfm.cu:309-336); 1: inliers of E only */
+    SFMB200_OPT_PROFILE = 4        /* 1: record CUDA events between the stages of run_device / run_host
+                                      (the reference's unused PerformanceTimer, common.h:48-132, done per stage) */
 } sfmb200_option;
 
 const char* sfmb200_last_error(void);
@@ -127,6 +129,10 @@ int sfmb200_device_views(sfmb200_t* h, float** d_E, float** d_P, int32_t** d_pos
 int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t sfmb200_launch_count(sfmb200_t* h);
+/* SFMB200_OPT_PROFILE: device time of the 7 stages (ingest, hypgen, score, select,
+ * pose candidates, choose pose, triangulate) of the most recent run_* calls, oldest
+ * first, ms [sets][7]; synchronises the stream. */
+int sfmb200_stage_times(sfmb200_t* h, int max_sets, float* h_ms, int* sets);
 
 /* ---- measurement helpers ---- */
 /* FP32-pipe probe: runs `iters` iterations of an FFMA (mode 0) or FFMA2 (mode 1)

@@ -1,0 +1,150 @@
+"""GPU tier: our CUDA path against the REFERENCE'S OWN CUDA path, rebuilt
+unmodified for sm_100a as oracle/_ref/libsfm_ref.so (oracle/ref_harness.cu),
+fed identical inputs stage by stage.  Stages whose reference
+behaviour is undefined (inlier scoring reads uninitialised memory, arg-max is
+off by one: SURVEY Q9-Q13) are pinned by the fp64 oracle in test_gpu_parity.py
+instead."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+fp = C.POINTER(C.c_float)
+ip = C.POINTER(C.c_int32)
+
+
+def P(a, t=fp):
+    return a.ctypes.data_as(t)
+
+
+@pytest.fixture(scope="module")
+def ref_pair(ref_lib, scene_small):
+    import torch
+
+    assert torch.cuda.is_available()
+    n = len(scene_small["px"])
+    r = ref_lib.ref_create(P(scene_small["K"].reshape(9).copy()), P(scene_small["Kinv"].reshape(9).copy()), n)
+    assert ref_lib.ref_fillXU(C.c_void_p(r), P(scene_small["px"])) == 0
+    yield C.c_void_p(r)
+    ref_lib.ref_destroy(C.c_void_p(r))
+
+
+def test_fillXU_matches_reference(pkg, ref_lib, ref_pair, scene_small):
+    import torch
+
+    n = len(scene_small["px"])
+    h = pkg.BatchedPairs(scene_small["K"], scene_small["Kinv"], 1, n, 16)
+    h.set_points_xy(torch.from_numpy(scene_small["px"]).cuda())
+    for image in (0, 1):
+        Xr = np.zeros((3, n), np.float32)
+        assert ref_lib.ref_get_X(ref_pair, image, P(Xr)) == 0
+        Xg = h.get_X(image).cpu().numpy()
+        # cuBLAS Sgemm (k = 3) vs our two fmas: same value to 1 ulp of 0.15
+        assert np.abs(Xg - Xr).max() < 3e-8
+        assert np.all(Xr[2] == 1)
+    h.close()
+
+
+def test_E_candidates_match_reference(pkg, O, ref_lib, ref_pair, scene_small):
+    """north_star: per-hypothesis E matches up to sign and scale within 1e-4
+    relative Frobenius norm, same sample rows on both sides."""
+    import torch
+
+    x, n = scene_small["x"], len(scene_small["x"])
+    H = 2000
+    idx = O.sample_indices(1237, H, n)
+    Er = np.zeros((H, 9), np.float32)
+    Ar = np.zeros((H, 72), np.float32)
+    Vr = np.zeros((H, 81), np.float32)
+    assert ref_lib.ref_e_candidates(ref_pair, P(idx, ip), H, P(Er), P(Ar), P(Vr)) == 0
+    # does gesvdjBatched (m=8 < n=9) put the null vector in V's 9th column?
+    null = Vr[:, 72:81].astype(np.float64)
+    resid = np.linalg.norm(np.einsum("hij,hj->hi", Ar.reshape(H, 8, 9).astype(np.float64), null), axis=1)
+    assert np.median(resid) < 1e-5, f"reference null-vector residual {np.median(resid)}"
+    h = pkg.BatchedPairs(scene_small["K"], scene_small["Kinv"], 1, n, H)
+    h.set_points_xy(torch.from_numpy(scene_small["px"]).cuda())
+    h.estimate_e(H, 0, 1e-6, d_idx=torch.from_numpy(idx).cuda())
+    Eg = h.get_E_candidates().cpu().numpy()
+    d = O.e_distance(Eg, Er)
+    E64 = O.hypotheses(x, idx)
+    d_ours, d_ref = O.e_distance(Eg, E64), O.e_distance(Er, E64)
+    print(f"\nE parity vs reference: median {np.median(d):.2e} p99 {np.percentile(d, 99):.2e} "
+          f"within 1e-4: {np.mean(d < 1e-4):.4f}; vs fp64 ours {np.mean(d_ours < 1e-4):.4f} ref {np.mean(d_ref < 1e-4):.4f}")
+    assert np.mean(d < 1e-4) >= 0.99
+    # where the two disagree, ours is the one closer to the fp64 truth (or both are ill-conditioned)
+    bad = d >= 1e-4
+    assert np.mean(d_ours[bad] <= np.maximum(d_ref[bad], 1e-4) * 10) > 0.9 if bad.any() else True
+    h.close()
+
+
+def test_pose_and_triangulation_match_reference(pkg, O, ref_lib, ref_pair, scene_small):
+    """Same E injected into both; compat mode replicates the reference's candidates
+    (incl. the det typo, Q15), the in-place inversion and last-passing-index rule
+    of choosePose (Q17-Q18) and triangulation with the inverted pose (Q19)."""
+    import torch
+
+    x, n = scene_small["x"], len(scene_small["x"])
+    h = pkg.BatchedPairs(scene_small["K"], scene_small["Kinv"], 1, n, 4096)
+    h.set_points_xy(torch.from_numpy(scene_small["px"]).cuda())
+    h.estimate_e(4096, 5, 1e-6)
+    agree_ind = 0
+    trials = []
+    Ebest = h.get_E()[0].reshape(9)
+    cands = h.get_E_candidates().cpu().numpy()
+    for E in [Ebest, -Ebest] + [cands[i] for i in (1, 10, 100, 1000)]:
+        E = np.ascontiguousarray(E, np.float32)
+        if not np.any(E):
+            continue
+        assert ref_lib.ref_set_E(ref_pair, P(E)) == 0
+        ref_lib.ref_computePosecandidates(ref_pair)
+        Pr = np.zeros((4, 4, 4), np.float32)
+        ref_lib.ref_get_P(ref_pair, P(Pr))
+        h.set_E(E)
+        h.pose_candidates()
+        Pg = h.get_poses()[0]
+        # the reference's host svd() runs 4 approximate Jacobi sweeps: ~1e-3 agreement
+        assert np.abs(Pg - Pr).max() < 5e-3, np.abs(Pg - Pr).max()
+        ref_lib.ref_choosePose(ref_pair)
+        ind_r = ref_lib.ref_get_P_ind(ref_pair)
+        ref_lib.ref_get_P(ref_pair, P(Pr))
+        h.choose_pose()
+        ind_g = int(h.get_pose_index()[0])
+        assert np.abs(h.get_poses()[0] - Pr).max() < 5e-3       # both hold the inverses now
+        trials.append((ind_g, ind_r))
+        agree_ind += ind_g == ind_r
+        ref_lib.ref_linear_triangulation(ref_pair)
+        pr = np.zeros((4, n), np.float32)
+        ref_lib.ref_get_points(ref_pair, P(pr))
+        if ind_g != ind_r:
+            continue
+        h.triangulate()
+        pg = h.get_points_host()
+        rel = np.abs(pg[:3] - pr[:3]).max(axis=0) / np.maximum(np.abs(pr[:3]).max(axis=0), 1e-3)
+        inl = ~scene_small["is_outlier"]
+        print(f"\ntriangulation vs reference: median rel {np.median(rel[inl]):.2e}, within 1e-2: {np.mean(rel[inl] < 1e-2):.4f}")
+        # both sides triangulate with their own (1e-3-different) pose: 1e-2 relative
+        assert np.median(rel[inl]) < 5e-3 and np.mean(rel[inl] < 5e-2) > 0.95
+        assert np.all(pg[3] == 1) and np.all(pr[3] == 1)
+        # egress
+        pos_r = np.zeros((n, 4), np.float32)
+        col_r = np.zeros((n, 4), np.float32)
+        ref_lib.ref_vbo(ref_pair, P(pos_r), P(col_r))
+        pos = torch.empty((n, 4), device="cuda")
+        col = torch.empty((n, 4), device="cuda")
+        h.copy_to_vbo(pos, col)
+        assert np.array_equal(col.cpu().numpy(), col_r)
+        assert np.array_equal(pos_r[:, :3], pr[:3].T) and np.array_equal(pos.cpu().numpy()[:, :3], pg[:3].T)
+    print("pose index (ours, reference):", trials)
+    assert agree_ind >= len(trials) - 1
+
+
+def test_reference_as_built_pipeline_runs(ref_lib, ref_pair):
+    """The unmodified pipeline end to end (timing baseline sanity): finite output."""
+    ref_lib.ref_set_seed(4242)
+    t = ref_lib.ref_estimateE(ref_pair)
+    assert t > 0
+    E = np.zeros(9, np.float32)
+    ref_lib.ref_get_E(ref_pair, P(E))
+    assert np.all(np.isfinite(E))
