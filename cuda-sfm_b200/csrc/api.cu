@@ -93,7 +93,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     s.n = 0;
     s.n_stride = (int)align_up(max_points, SCORE_CHUNK);
     s.h_stride = (int)align_up(max_hyp, 1024);
-    s.tiles_max = s.h_stride / 512;
+    s.tiles_max = s.h_stride / SCORE_MIN_TILE;
     memcpy(s.K, K, sizeof(float) * 9);
     memcpy(s.Kinv, Kinv, sizeof(float) * 9);
     // one arena, carved with 256-byte alignment
@@ -168,7 +168,7 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
     switch (option) {
         case SFMB200_OPT_COMPAT: h->compat = value ? 1 : 0; break;
         case SFMB200_OPT_SCORE_VARIANT:
-            if (value < -1 || value > 1) return fail(SFMB200_ERR_ARG, "score variant must be -1, 0 or 1%s");
+            if (value < -1 || value >= score_num_variants()) return fail(SFMB200_ERR_ARG, "score variant out of range%s");
             h->score_variant = value;
             break;
         case SFMB200_OPT_TRI_INLIERS_ONLY: h->tri_inliers_only = value ? 1 : 0; break;

@@ -7,15 +7,15 @@ namespace sfmb200 {
 
 // Launch parameters of the scoring kernel; chosen by the host per problem shape.
 struct ScorePlan {
-    int variant;        // 0: scalar FFMA, 2 hyp/thread; 1: packed FFMA2, 4 hyp/thread
-    int hyp_per_cta;    // hypotheses per CTA (256 threads * hyp/thread)
+    int variant;        // index into the scoring kernel family (score.cu: kVariants)
+    int hyp_per_cta;    // hypotheses per CTA (threads * hyp/thread)
     int tiles;          // ceil(H / hyp_per_cta)
     int splits;         // point-range splits per tile (grid.y)
     int pts_per_split;  // multiple of SCORE_CHUNK
 };
 
-constexpr int SCORE_THREADS = 256;
 constexpr int SCORE_CHUNK = 512;     // points per TMA stage
+constexpr int SCORE_MIN_TILE = 256;  // smallest hypothesis tile of any kernel variant
 
 // Everything one handle owns on the device.  All per-pair arrays are laid out
 // [pair][...] with fixed strides so a batch is one launch (blockIdx.y / z = pair).
@@ -52,6 +52,7 @@ void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cud
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
                    unsigned long long seed, cudaStream_t st);
 ScorePlan make_score_plan(int B, int n, int H, int variant_override);
+int score_num_variants();
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
 void launch_select(const DeviceState& s, int h_offset, cudaStream_t st);
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride,

@@ -93,14 +93,15 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
-template <int HPT, bool PACKED>
-__global__ void __launch_bounds__(SCORE_THREADS)
+template <int HPT, bool PACKED, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 score_kernel(DeviceState s, int H, int h_offset, int splits, int pts_per_split, float thr) {
+    constexpr int SCORE_THREADS = THREADS;
     constexpr int HPC = HPT * SCORE_THREADS;
     constexpr int F4_PER_PT = PACKED ? 2 : 1;
     __shared__ __align__(128) float4 buf[2][SCORE_CHUNK * F4_PER_PT];
     __shared__ __align__(8) uint64_t full[2];
-    __shared__ unsigned long long red[SCORE_THREADS / 32];
+    __shared__ unsigned long long red[THREADS / 32];
     __shared__ int s_ticket;
 
     const int tid = threadIdx.x;
@@ -229,33 +230,95 @@ score_kernel(DeviceState s, int H, int h_offset, int splits, int pts_per_split, 
     }
 }
 
+// Kernel family.  Register-bank pressure is what bounds the FP32 pipe here: an
+// FFMA reads three registers and an FFMA2 three register PAIRS per issue, and
+// the only operand that can come from the operand-reuse cache is the point
+// coordinate shared by the HPT hypotheses of a thread, so more hypotheses per
+// thread = more reuse, at the price of registers (occupancy) and coarser tiles.
+struct ScoreVariant { int hpt; int packed; int threads; };
+static const ScoreVariant kVariants[] = {
+    {2, 0, 256}, {4, 1, 256}, {4, 0, 256}, {8, 0, 256}, {8, 1, 256}, {4, 0, 128}, {4, 1, 128}, {8, 0, 128}, {8, 1, 128},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kDefaultVariant = 1;
+
+template <int HPT, bool PACKED, int THREADS>
+static void launch_one(const DeviceState& s, dim3 grid, int H, int h_offset, int splits, int pps, float thr, cudaStream_t st) {
+    score_kernel<HPT, PACKED, THREADS><<<grid, THREADS, 0, st>>>(s, H, h_offset, splits, pps, thr);
+}
+template <int HPT, bool PACKED, int THREADS>
+static int occupancy_one() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<HPT, PACKED, THREADS>, THREADS, 0);
+    return n > 0 ? n : 1;
+}
+#define SFM_FOR_VARIANT(v, CALL)                  \
+    switch (v) {                                  \
+        case 0: CALL(2, false, 256); break;       \
+        case 1: CALL(4, true, 256); break;        \
+        case 2: CALL(4, false, 256); break;       \
+        case 3: CALL(8, false, 256); break;       \
+        case 4: CALL(8, true, 256); break;        \
+        case 5: CALL(4, false, 128); break;       \
+        case 6: CALL(4, true, 128); break;        \
+        case 7: CALL(8, false, 128); break;       \
+        default: CALL(8, true, 128); break;       \
+    }
+
+static int variant_occupancy(int v) {
+    static int cache[kNumVariants] = {0};
+    if (cache[v] == 0) {
+#define SFM_OCC(h, p, t) cache[v] = occupancy_one<h, p, t>()
+        SFM_FOR_VARIANT(v, SFM_OCC)
+#undef SFM_OCC
+    }
+    return cache[v];
+}
+
+int score_num_variants() { return kNumVariants; }
+
 ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     ScorePlan p;
-    p.variant = variant_override >= 0 ? variant_override : 1;
-    p.hyp_per_cta = (p.variant == 1 ? 4 : 2) * SCORE_THREADS;
+    p.variant = (variant_override >= 0 && variant_override < kNumVariants) ? variant_override : kDefaultVariant;
+    const ScoreVariant& v = kVariants[p.variant];
+    p.hyp_per_cta = v.hpt * v.threads;
     p.tiles = (H + p.hyp_per_cta - 1) / p.hyp_per_cta;
     if (p.tiles < 1) p.tiles = 1;
-    // Enough CTAs for ~4 waves of 148 SMs x 2 resident CTAs, but never split
-    // finer than one TMA stage of points.
-    const int target_ctas = 148 * 2 * 4;
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long slots = (long long)sms * variant_occupancy(p.variant);
     int chunks = (n + SCORE_CHUNK - 1) / SCORE_CHUNK;
     if (chunks < 1) chunks = 1;
-    long long have = (long long)p.tiles * B;
-    int splits = (int)((target_ctas + have - 1) / have);
-    if (splits < 1) splits = 1;
-    if (splits > chunks) splits = chunks;
-    int chunks_per_split = (chunks + splits - 1) / splits;
-    p.pts_per_split = chunks_per_split * SCORE_CHUNK;
-    p.splits = (chunks + chunks_per_split - 1) / chunks_per_split;
+    // Pick the number of point splits that minimises (waves of resident CTAs) x
+    // (TMA stages per CTA + a fixed per-CTA cost): the grid's tail wave is what
+    // costs most at config-2 sizes.  Ties go to fewer splits (fewer atomics).
+    const long long base = (long long)p.tiles * B;
+    double best_cost = 1e300;
+    int best_s = 1;
+    for (int sp = 1; sp <= chunks; sp++) {
+        int cps = (chunks + sp - 1) / sp;
+        int real = (chunks + cps - 1) / cps;
+        if (real != sp) continue;
+        long long ctas = base * sp;
+        long long waves = (ctas + slots - 1) / slots;
+        double cost = (double)waves * (cps + 0.15);
+        if (cost < best_cost * 0.999) { best_cost = cost; best_s = sp; }
+        if (ctas > slots * 64) break;
+    }
+    int cps = (chunks + best_s - 1) / best_s;
+    p.pts_per_split = cps * SCORE_CHUNK;
+    p.splits = (chunks + cps - 1) / cps;
     return p;
 }
 
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {
     dim3 grid(plan.tiles, plan.splits, s.B);
-    if (plan.variant == 1)
-        score_kernel<4, true><<<grid, SCORE_THREADS, 0, st>>>(s, H, h_offset, plan.splits, plan.pts_per_split, thr);
-    else
-        score_kernel<2, false><<<grid, SCORE_THREADS, 0, st>>>(s, H, h_offset, plan.splits, plan.pts_per_split, thr);
+#define SFM_LAUNCH(h, p, t) launch_one<h, p, t>(s, grid, H, h_offset, plan.splits, plan.pts_per_split, thr, st)
+    SFM_FOR_VARIANT(plan.variant, SFM_LAUNCH)
+#undef SFM_LAUNCH
 }
 
 // Selected hypothesis -> E, index, count (per pair).

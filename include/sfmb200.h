@@ -46,7 +46,8 @@ typedef enum {
 typedef enum {
     SFMB200_OPT_COMPAT = 1,        /* 1 (default): reference semantics for poses / cheirality / triangulation
                                       (SURVEY.md Appendix A); 0: textbook geometry with an inlier vote */
-    SFMB200_OPT_SCORE_VARIANT = 2, /* -1 auto (default), 0 scalar FFMA kernel, 1 packed FFMA2 kernel */
+    SFMB200_OPT_SCORE_VARIANT = 2, /* -1 auto (default); >= 0: index into the scoring kernel family
+                                      (0 scalar FFMA 2 hyp/thread, 1 packed FFMA2 4 hyp/thread, ... see score.cu) */
     SFMB200_OPT_TRI_INLIERS_ONLY = 3, /* 0 (default, reference: all N points, sfm.cu:309-336); 1: inliers of E only */
     SFMB200_OPT_PROFILE = 4        /* 1: record CUDA events between the stages of run_device / run_host
                                       (the reference's unused PerformanceTimer, common.h:48-132, done per stage) */

@@ -298,6 +298,21 @@ def pose_candidates(E: np.ndarray, compat: bool = True) -> np.ndarray:
     return P
 
 
+def match_candidates(Pa: np.ndarray, Pb: np.ndarray, tol: float = 1e-3):
+    """Pose-candidate sets are defined up to ONE discrete freedom of the SVD of a
+    rank-2 E under the reference's U, V in SO(3) contract: negating (u1, v1, u3, v3)
+    leaves E, U V^T and the det test unchanged but swaps W <-> W^T and the sign of
+    u3, i.e. permutes the candidates 0<->3, 1<->2.  Which of the two an SVD returns
+    is an artefact of its rotation sequence (for sigma1 == sigma2 it is decided by
+    rounding), so parity of candidates means: equal under the identity or under
+    that permutation.  Returns the permutation perm with Pa[i] ~ Pb[perm[i]], or None."""
+    Pa, Pb = np.asarray(Pa, float).reshape(4, 4, 4), np.asarray(Pb, float).reshape(4, 4, 4)
+    for perm in ((0, 1, 2, 3), (3, 2, 1, 0)):
+        if all(np.abs(Pa[i] - Pb[perm[i]]).max() < tol for i in range(4)):
+            return perm
+    return None
+
+
 def dlt_rows(x: np.ndarray, M: np.ndarray) -> np.ndarray:
     """compute_linear_triangulation_A (kernels.h:387-431): per point the 4x4
     [x1*I[2]-I[0]; y1*I[2]-I[1]; x2*M[2]-M[0]; y2*M[2]-M[1]] with camera 1 = I4."""

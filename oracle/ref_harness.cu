@@ -195,6 +195,10 @@ int ref_get_P(void* p, float* h_P) {
     cudaMemcpy(h_P, ((Image_pair*)p)->d_P, sizeof(float) * 64, cudaMemcpyDeviceToHost);
     return (int)cudaGetLastError();
 }
+int ref_set_P(void* p, const float* h_P) {
+    cudaMemcpy(((Image_pair*)p)->d_P, h_P, sizeof(float) * 64, cudaMemcpyHostToDevice);
+    return (int)cudaGetLastError();
+}
 int ref_get_P_ind(void* p) { return ((Image_pair*)p)->P_ind; }
 int ref_get_points(void* p, float* h_points) {
     Image_pair* ip = (Image_pair*)p;

@@ -80,54 +80,59 @@ def test_E_candidates_match_reference(pkg, O, ref_lib, ref_pair, scene_small):
 
 
 def test_pose_and_triangulation_match_reference(pkg, O, ref_lib, ref_pair, scene_small):
-    """Same E injected into both; compat mode replicates the reference's candidates
-    (incl. the det typo, Q15), the in-place inversion and last-passing-index rule
-    of choosePose (Q17-Q18) and triangulation with the inverted pose (Q19)."""
+    """Same E injected into both sides.  Candidates (incl. the det typo, Q15)
+    match as a set up to the one discrete SVD freedom (oracle.match_candidates);
+    with identical candidates injected, choosePose (in-place inversion,
+    last-passing-index rule, Q17-Q18) gives the same index and inverses, and
+    triangulation with that inverted pose (Q19) the same points."""
     import torch
 
     x, n = scene_small["x"], len(scene_small["x"])
     h = pkg.BatchedPairs(scene_small["K"], scene_small["Kinv"], 1, n, 4096)
     h.set_points_xy(torch.from_numpy(scene_small["px"]).cuda())
     h.estimate_e(4096, 5, 1e-6)
-    agree_ind = 0
-    trials = []
     Ebest = h.get_E()[0].reshape(9)
     cands = h.get_E_candidates().cpu().numpy()
-    for E in [Ebest, -Ebest] + [cands[i] for i in (1, 10, 100, 1000)]:
+    perms = []
+    for E in [Ebest, -Ebest] + [cands[i] for i in (1, 10, 100, 1000, 2000, 3000)]:
         E = np.ascontiguousarray(E, np.float32)
         if not np.any(E):
             continue
+        # 1. candidates from the same E
         assert ref_lib.ref_set_E(ref_pair, P(E)) == 0
         ref_lib.ref_computePosecandidates(ref_pair)
         Pr = np.zeros((4, 4, 4), np.float32)
         ref_lib.ref_get_P(ref_pair, P(Pr))
         h.set_E(E)
         h.pose_candidates()
-        Pg = h.get_poses()[0]
+        Pg = h.get_poses()[0].copy()
         # the reference's host svd() runs 4 approximate Jacobi sweeps: ~1e-3 agreement
-        assert np.abs(Pg - Pr).max() < 5e-3, np.abs(Pg - Pr).max()
+        perm = O.match_candidates(Pg, Pr, tol=5e-3)
+        assert perm is not None, (Pg, Pr)
+        perms.append(perm[0])
+        # 2. choosePose on IDENTICAL candidates (ours injected into the reference)
+        assert ref_lib.ref_set_P(ref_pair, P(Pg)) == 0
         ref_lib.ref_choosePose(ref_pair)
         ind_r = ref_lib.ref_get_P_ind(ref_pair)
         ref_lib.ref_get_P(ref_pair, P(Pr))
         h.choose_pose()
-        ind_g = int(h.get_pose_index()[0])
-        assert np.abs(h.get_poses()[0] - Pr).max() < 5e-3       # both hold the inverses now
-        trials.append((ind_g, ind_r))
-        agree_ind += ind_g == ind_r
+        assert int(h.get_pose_index()[0]) == ind_r
+        assert np.abs(h.get_poses()[0] - Pr).max() < 1e-4       # both hold the inverses now
+        # 3. triangulation with the selected (inverted) pose
         ref_lib.ref_linear_triangulation(ref_pair)
         pr = np.zeros((4, n), np.float32)
         ref_lib.ref_get_points(ref_pair, P(pr))
-        if ind_g != ind_r:
-            continue
         h.triangulate()
         pg = h.get_points_host()
         rel = np.abs(pg[:3] - pr[:3]).max(axis=0) / np.maximum(np.abs(pr[:3]).max(axis=0), 1e-3)
         inl = ~scene_small["is_outlier"]
-        print(f"\ntriangulation vs reference: median rel {np.median(rel[inl]):.2e}, within 1e-2: {np.mean(rel[inl] < 1e-2):.4f}")
-        # both sides triangulate with their own (1e-3-different) pose: 1e-2 relative
-        assert np.median(rel[inl]) < 5e-3 and np.mean(rel[inl] < 5e-2) > 0.95
+        print(f"\ntriangulation vs reference: median rel {np.median(rel[inl]):.2e}, p99 {np.percentile(rel[inl], 99):.2e}, "
+              f"all points within 1e-3: {np.mean(rel < 1e-3):.4f}")
+        # stated tolerance: 1e-3 relative to the point's largest coordinate (fp32
+        # Jacobi on both sides); the tail is ill-conditioned outlier geometry
+        assert np.median(rel[inl]) < 1e-4 and np.mean(rel[inl] < 1e-3) > 0.98
         assert np.all(pg[3] == 1) and np.all(pr[3] == 1)
-        # egress
+        # 4. egress
         pos_r = np.zeros((n, 4), np.float32)
         col_r = np.zeros((n, 4), np.float32)
         ref_lib.ref_vbo(ref_pair, P(pos_r), P(col_r))
@@ -136,8 +141,8 @@ def test_pose_and_triangulation_match_reference(pkg, O, ref_lib, ref_pair, scene
         h.copy_to_vbo(pos, col)
         assert np.array_equal(col.cpu().numpy(), col_r)
         assert np.array_equal(pos_r[:, :3], pr[:3].T) and np.array_equal(pos.cpu().numpy()[:, :3], pg[:3].T)
-    print("pose index (ours, reference):", trials)
-    assert agree_ind >= len(trials) - 1
+    print("candidate permutation per trial (0 = identity, 3 = swapped):", perms)
+    h.close()
 
 
 def test_reference_as_built_pipeline_runs(ref_lib, ref_pair):

@@ -21,7 +21,7 @@ THR = 1e-6
 
 
 def emit(**kw):
-    print(json.dumps(kw), flush=True)
+    print(json.dumps(kw, default=float), flush=True)
 
 
 def probe():
@@ -59,9 +59,10 @@ def stages(n, H, variant, pairs=1, reps=10, label=""):
 if __name__ == "__main__":
     emit(what="device", name=torch.cuda.get_device_name(0), sms=torch.cuda.get_device_properties(0).multi_processor_count)
     probe()
-    for v in (0, 1):
+    for v in range(9):
         stages(10_000, 65_536, v, label="config2")
-    for v in (0, 1):
+    for v in (1, 3, 4):
         stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp (config 3 slice / config 5 triangulation)")
-    stages(4096, 4096, 1, pairs=256, reps=3, label="config4 slice: 256 pairs")
+    for v in (1, 3, 4, 6, 8):
+        stages(4096, 4096, v, pairs=256, reps=3, label="config4 slice: 256 pairs")
     stages(2000, 250, 1, label="config1-like: 2k corr, 250 hyp")
