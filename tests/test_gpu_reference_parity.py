@@ -72,10 +72,16 @@ def test_E_candidates_match_reference(pkg, O, ref_lib, ref_pair, scene_small):
     d_ours, d_ref = O.e_distance(Eg, E64), O.e_distance(Er, E64)
     print(f"\nE parity vs reference: median {np.median(d):.2e} p99 {np.percentile(d, 99):.2e} "
           f"within 1e-4: {np.mean(d < 1e-4):.4f}; vs fp64 ours {np.mean(d_ours < 1e-4):.4f} ref {np.mean(d_ref < 1e-4):.4f}")
-    assert np.mean(d < 1e-4) >= 0.99
-    # where the two disagree, ours is the one closer to the fp64 truth (or both are ill-conditioned)
+    # Measured on B200: the reference itself is within 1e-4 of the fp64 truth for only
+    # ~97 % of hypotheses (its null vector for 98.6 %, and normalizeE's 4-sweep
+    # approximate svd.h loses more), ours for 99.97 %.  So: >= 95 % pairwise agreement,
+    # ours within 1e-4 of fp64 wherever the reference is, and every disagreement is
+    # the reference's error, not ours.
+    assert np.mean(d < 1e-4) >= 0.95
+    assert np.mean(d_ours < 1e-4) >= 0.995 and np.mean(d_ours < 1e-4) >= np.mean(d_ref < 1e-4)
     bad = d >= 1e-4
-    assert np.mean(d_ours[bad] <= np.maximum(d_ref[bad], 1e-4) * 10) > 0.9 if bad.any() else True
+    if bad.any():
+        assert np.mean(d_ours[bad] <= d_ref[bad]) > 0.95
     h.close()
 
 
@@ -145,11 +151,19 @@ def test_pose_and_triangulation_match_reference(pkg, O, ref_lib, ref_pair, scene
     h.close()
 
 
-def test_reference_as_built_pipeline_runs(ref_lib, ref_pair):
-    """The unmodified pipeline end to end (timing baseline sanity): finite output."""
-    ref_lib.ref_set_seed(4242)
-    t = ref_lib.ref_estimateE(ref_pair)
-    assert t > 0
+def test_reference_injected_estimateE_runs(O, ref_lib, ref_pair, scene_small):
+    """The timing baseline used by bench.py --impl reference: the reference's
+    estimateE body with injected rows.  (Its as-built estimateE() cannot run on
+    B200 at all: kernels::kernels' `index > ransac_iterations` guard, kernels.h:242,
+    lets one extra thread gather through out-of-range sample indices and the
+    launch dies with an illegal memory access - SURVEY Q5; the harness pads the
+    index and design-matrix buffers by one row instead.)"""
+    n = len(scene_small["x"])
+    H = 512
+    idx = O.sample_indices(3, H, n)
+    best = C.c_int(-1)
+    ms = ref_lib.ref_estimateE_injected(ref_pair, P(idx, ip), H, C.byref(best))
+    assert ms > 0 and 0 <= best.value < H
     E = np.zeros(9, np.float32)
     ref_lib.ref_get_E(ref_pair, P(E))
     assert np.all(np.isfinite(E))
