@@ -495,8 +495,8 @@ int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]) {
     if (!h || !out) return fail(SFMB200_ERR_ARG, "null argument%s");
     out[0] = h->plan.variant;
     out[1] = h->plan.tiles;
-    out[2] = h->plan.splits;
-    out[3] = h->plan.pts_per_split;
+    out[2] = h->plan.ctas;
+    out[3] = h->plan.hyp_per_cta;
     return SFMB200_OK;
 }
 int64_t sfmb200_launch_count(sfmb200_t* h) { return h ? h->launches : 0; }

@@ -9,12 +9,14 @@ namespace sfmb200 {
 struct ScorePlan {
     int variant;        // index into the scoring kernel family (score.cu: kVariants)
     int hyp_per_cta;    // hypotheses per CTA (threads * hyp/thread)
-    int tiles;          // ceil(H / hyp_per_cta)
-    int splits;         // point-range splits per tile (grid.y)
-    int pts_per_split;  // multiple of SCORE_CHUNK
+    int tiles;          // ceil(H / hyp_per_cta), per pair
+    int n_units;        // grains of SCORE_GRAIN points per tile
+    long long total_units;   // pairs * tiles * n_units
+    int ctas;           // persistent grid size (SMs x resident CTAs, capped by the work)
 };
 
 constexpr int SCORE_CHUNK = 512;     // points per TMA stage
+constexpr int SCORE_GRAIN = 64;      // work-partition granularity in points
 constexpr int SCORE_MIN_TILE = 256;  // smallest hypothesis tile of any kernel variant
 
 // Everything one handle owns on the device.  All per-pair arrays are laid out

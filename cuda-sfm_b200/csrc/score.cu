@@ -4,8 +4,10 @@
 // vecnorm + threshold_count over 88*N*H bytes of temporaries) and the
 // thrust::max_element selection (sfm.cu:135-137).
 //
-// Mapping.  A CTA owns a tile of hypotheses (threads own 2 or 4 hypotheses: E
-// lives in registers for the whole kernel) and a contiguous range of points.
+// Mapping.  A CTA works on a tile of hypotheses (threads own 2, 4 or 8
+// hypotheses: E lives in registers) and a contiguous range of points; the
+// (pair, tile, point) space is cut into equal shares, one per resident CTA
+// (persistent grid, see ChunkWalk), so every SM finishes at the same time.
 // Points stream through shared memory in 512-point stages filled by 1-D TMA
 // bulk copies (cp.async.bulk + mbarrier complete_tx, double buffered); every
 // thread reads the same point per step, so the LDS is a broadcast.  Inlier
@@ -19,10 +21,10 @@
 //   packed : FFMA2 (fma.rn.f32x2, new on sm_100) on hypothesis pairs,
 //            4 hypotheses per thread, points staged as (x1,x1,y1,y1),(x2,x2,y2,y2).
 //
-// Epilogue.  splits == 1: counts written directly, block arg-max from
-// registers.  splits > 1: partial counts are atomically added to counts[];
-// the last CTA to finish a hypothesis tile (ticket counter) reads the totals
-// and does the tile's arg-max.  Either way one atomicMax per tile on the packed
+// Epilogue.  A CTA that saw every point of a tile writes counts directly and
+// reduces from registers.  Otherwise partial counts are atomically added to
+// counts[] and a per-tile counter of points processed tells which CTA completed
+// the tile; that CTA reads the totals and does the tile's arg-max.  Either way one atomicMax per tile on the packed
 // key (count << 32) | (0xFFFFFFFF - global index): highest count, lowest index
 // on ties = thrust::max_element semantics.  No separate arg-max kernel.
 //
@@ -93,25 +95,65 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+// Walks the chunks (<= SCORE_CHUNK points) of this CTA's share of the work.
+// Work space = (pair, hypothesis tile, point) linearised in grains of
+// SCORE_GRAIN points; CTA c owns grains [c*U/G, (c+1)*U/G): every CTA gets the
+// same amount of work to within one grain whatever the problem shape
+// ("stream-K" decomposition along the point axis), so there is no tail wave.
+// A CTA's share is a sequence of segments, each a contiguous point range of one
+// (pair, tile); segments are streamed chunk by chunk.
+struct ChunkWalk {
+    long long u, end;      // grain cursor / end of this CTA's share
+    int n_units, n, T;     // grains per tile, points per pair, tiles per pair
+    int b, t, p0, cnt;     // current chunk: pair, tile, first point, points
+    int seg_p0, seg_pts;   // current segment: first point, total points
+    int left;              // points of the segment not yet handed out
+    bool seg_first, seg_last;
+    __device__ __forceinline__ void init(long long u0, long long u1, int n_units_, int n_, int T_) {
+        u = u0; end = u1; n_units = n_units_; n = n_; T = T_;
+        left = 0; cnt = 0; p0 = 0;
+    }
+    __device__ __forceinline__ bool next() {
+        if (left == 0) {
+            if (u >= end) return false;
+            long long bt = u / n_units;
+            int pu = (int)(u - bt * n_units);
+            long long seg_units = end - u;
+            if (seg_units > n_units - pu) seg_units = n_units - pu;
+            b = (int)(bt / T);
+            t = (int)(bt - (long long)b * T);
+            seg_p0 = pu * SCORE_GRAIN;
+            int p1 = (pu + (int)seg_units) * SCORE_GRAIN;
+            if (p1 > n) p1 = n;
+            seg_pts = p1 - seg_p0;
+            left = seg_pts;
+            u += seg_units;
+            p0 = seg_p0;
+            seg_first = true;
+        } else {
+            p0 += cnt;
+            seg_first = false;
+        }
+        cnt = left < SCORE_CHUNK ? left : SCORE_CHUNK;
+        left -= cnt;
+        seg_last = (left == 0);
+        return true;
+    }
+};
+
 template <int HPT, bool PACKED, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-score_kernel(DeviceState s, int H, int h_offset, int splits, int pts_per_split, float thr) {
-    constexpr int SCORE_THREADS = THREADS;
-    constexpr int HPC = HPT * SCORE_THREADS;
+score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, int n_units, float thr) {
+    constexpr int HPC = HPT * THREADS;
     constexpr int F4_PER_PT = PACKED ? 2 : 1;
     __shared__ __align__(128) float4 buf[2][SCORE_CHUNK * F4_PER_PT];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ unsigned long long red[THREADS / 32];
-    __shared__ int s_ticket;
+    __shared__ int s_last;
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
-    const int p0 = split * pts_per_split;
-    const int p1 = min(s.n, p0 + pts_per_split);
-    const int npts = max(0, p1 - p0);
-    const int nchunks = (npts + SCORE_CHUNK - 1) / SCORE_CHUNK;
-    const float4* src = (PACKED ? s.corr_dup + (size_t)b * s.n_stride * 2 + (size_t)p0 * 2
-                                : s.corr + (size_t)b * s.n_stride + p0);
+    const long long u0 = total_units * blockIdx.x / gridDim.x;
+    const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
 
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -119,43 +161,54 @@ score_kernel(DeviceState s, int H, int h_offset, int splits, int pts_per_split, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int c) {
-        int cnt = min(SCORE_CHUNK, npts - c * SCORE_CHUNK);
-        uint32_t bytes = (uint32_t)cnt * 16u * F4_PER_PT;
-        mbar_expect_tx(&full[c & 1], bytes);
-        tma_load_1d(&buf[c & 1][0], src + (size_t)c * SCORE_CHUNK * F4_PER_PT, bytes, &full[c & 1]);
+
+    ChunkWalk prod, cons;
+    cons.init(u0, u1, n_units, s.n, T);
+    auto issue = [&](const ChunkWalk& w, int stage) {
+        const float4* src = PACKED ? s.corr_dup + ((size_t)w.b * s.n_stride + w.p0) * 2
+                                   : s.corr + (size_t)w.b * s.n_stride + w.p0;
+        uint32_t bytes = (uint32_t)w.cnt * 16u * F4_PER_PT;
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_1d(&buf[stage][0], src, bytes, &full[stage]);
     };
-    if (tid == 0 && nchunks > 0) issue(0);
-
-    // Essential matrices of this thread's hypotheses -> registers.
-    const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
-    float e[HPT][9];
-    int hl[HPT];
-#pragma unroll
-    for (int j = 0; j < HPT; j++) {
-        hl[j] = tile * HPC + j * SCORE_THREADS + tid;
-        bool valid = hl[j] < H;
-#pragma unroll
-        for (int k = 0; k < 9; k++) e[j][k] = valid ? __ldg(Eb + (size_t)k * s.h_stride + hl[j]) : 0.0f;
+    if (tid == 0) {
+        prod.init(u0, u1, n_units, s.n, T);
+        if (prod.next()) issue(prod, 0);
     }
-    unsigned int cnt[HPT];
-#pragma unroll
-    for (int j = 0; j < HPT; j++) cnt[j] = 0u;
-    const float nthr = -thr;
 
-    if constexpr (PACKED) {
-        static_assert(!PACKED || HPT % 2 == 0, "packed path works on hypothesis pairs");
-        float2 e2[HPT / 2][9];
+    float e[PACKED ? 1 : HPT][9];               // scalar path: one E per hypothesis
+    float2 e2[PACKED ? HPT / 2 : 1][9];         // packed path: E of a hypothesis pair per float2
+    int hl[HPT];
+    unsigned int cnt[HPT];
+    const float nthr = -thr;
+    const float2 nthr2 = make_float2(nthr, nthr);
+    (void)e; (void)e2; (void)nthr2;
+
+    for (int k = 0; cons.next(); k++) {
+        if (tid == 0 && prod.next()) issue(prod, (k + 1) & 1);
+        if (cons.seg_first) {
+            // essential matrices of this thread's hypotheses -> registers
+            const float* Eb = s.Ecand + (size_t)cons.b * 9 * s.h_stride;
 #pragma unroll
-        for (int j = 0; j < HPT / 2; j++)
+            for (int j = 0; j < HPT; j++) {
+                hl[j] = cons.t * HPC + j * THREADS + tid;
+                bool valid = hl[j] < H;
 #pragma unroll
-            for (int k = 0; k < 9; k++) e2[j][k] = make_float2(e[2 * j][k], e[2 * j + 1][k]);
-        const float2 nthr2 = make_float2(nthr, nthr);
-        for (int c = 0; c < nchunks; c++) {
-            if (tid == 0 && c + 1 < nchunks) issue(c + 1);
-            mbar_wait(&full[c & 1], (c >> 1) & 1);
-            const float4* pb = buf[c & 1];
-            const int n_here = min(SCORE_CHUNK, npts - c * SCORE_CHUNK);
+                for (int q = 0; q < 9; q++) {
+                    float v = valid ? __ldg(Eb + (size_t)q * s.h_stride + hl[j]) : 0.0f;
+                    if constexpr (PACKED) {
+                        if (j & 1) e2[j / 2][q].y = v; else e2[j / 2][q].x = v;
+                    } else {
+                        e[j][q] = v;
+                    }
+                }
+                cnt[j] = 0u;
+            }
+        }
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        const float4* pb = buf[k & 1];
+        const int n_here = cons.cnt;
+        if constexpr (PACKED) {
 #pragma unroll 4
             for (int i = 0; i < n_here; i++) {
                 float4 a = pb[2 * i], q = pb[2 * i + 1];
@@ -168,14 +221,7 @@ score_kernel(DeviceState s, int H, int h_offset, int splits, int pts_per_split, 
                     cnt[2 * j + 1] += __float_as_uint(d.y) >> 31;
                 }
             }
-            __syncthreads();
-        }
-    } else {
-        for (int c = 0; c < nchunks; c++) {
-            if (tid == 0 && c + 1 < nchunks) issue(c + 1);
-            mbar_wait(&full[c & 1], (c >> 1) & 1);
-            const float4* pb = buf[c & 1];
-            const int n_here = min(SCORE_CHUNK, npts - c * SCORE_CHUNK);
+        } else {
 #pragma unroll 4
             for (int i = 0; i < n_here; i++) {
                 float4 p = pb[i];
@@ -185,66 +231,80 @@ score_kernel(DeviceState s, int H, int h_offset, int splits, int pts_per_split, 
                     cnt[j] += __float_as_uint(d) >> 31;
                 }
             }
-            __syncthreads();
         }
-    }
+        __syncthreads();   // buf[k & 1] is free for the chunk issued at the top of iteration k + 1
+        if (!cons.seg_last) continue;
 
-    // ---- epilogue: counts + fused arg-max ----
-    int* counts = s.counts + (size_t)b * s.h_stride;
-    unsigned long long key = 0ull;
-    if (splits == 1) {
+        // ---- end of a segment: counts + fused arg-max for (pair b, tile t) ----
+        int* counts = s.counts + (size_t)cons.b * s.h_stride;
+        unsigned long long key = 0ull;
+        bool do_argmax;
+        if (cons.seg_pts == s.n) {          // this CTA saw every point of the tile
 #pragma unroll
-        for (int j = 0; j < HPT; j++)
-            if (hl[j] < H) {
-                counts[hl[j]] = (int)cnt[j];
-                unsigned long long k =
-                    ((unsigned long long)cnt[j] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + hl[j]));
-                key = k > key ? k : key;
+            for (int j = 0; j < HPT; j++)
+                if (hl[j] < H) {
+                    counts[hl[j]] = (int)cnt[j];
+                    unsigned long long kk = ((unsigned long long)cnt[j] << 32) |
+                                            (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + hl[j]));
+                    key = kk > key ? kk : key;
+                }
+            do_argmax = true;
+        } else {                             // partial: add, the CTA completing the tile reduces it
+#pragma unroll
+            for (int j = 0; j < HPT; j++)
+                if (hl[j] < H && cnt[j] != 0u) atomicAdd(&counts[hl[j]], (int)cnt[j]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                int before = atomicAdd(&s.tile_done[(size_t)cons.b * s.tiles_max + cons.t], cons.seg_pts);
+                s_last = (before + cons.seg_pts == s.n);
             }
-    } else {
+            __syncthreads();
+            do_argmax = s_last != 0;
+            if (do_argmax) {
+                __threadfence();
 #pragma unroll
-        for (int j = 0; j < HPT; j++)
-            if (hl[j] < H && cnt[j] != 0u) atomicAdd(&counts[hl[j]], (int)cnt[j]);
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(&s.tile_done[(size_t)b * s.tiles_max + tile], 1);
-        __syncthreads();
-        if (s_ticket != splits - 1) return;
-        __threadfence();
-#pragma unroll
-        for (int j = 0; j < HPT; j++)
-            if (hl[j] < H) {
-                unsigned int total = (unsigned int)__ldcg(&counts[hl[j]]);
-                unsigned long long k =
-                    ((unsigned long long)total << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + hl[j]));
-                key = k > key ? k : key;
+                for (int j = 0; j < HPT; j++)
+                    if (hl[j] < H) {
+                        unsigned int total = (unsigned int)__ldcg(&counts[hl[j]]);
+                        unsigned long long kk = ((unsigned long long)total << 32) |
+                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + hl[j]));
+                        key = kk > key ? kk : key;
+                    }
             }
-    }
-    key = warp_max_u64(key);
-    if ((tid & 31) == 0) red[tid >> 5] = key;
-    __syncthreads();
-    if (tid < 32) {
-        unsigned long long v = tid < SCORE_THREADS / 32 ? red[tid] : 0ull;
-        v = warp_max_u64(v);
-        if (tid == 0 && v != 0ull) atomicMax(&s.best[b], v);
+        }
+        if (do_argmax) {                     // uniform across the CTA
+            key = warp_max_u64(key);
+            if ((tid & 31) == 0) red[tid >> 5] = key;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned long long v = tid < THREADS / 32 ? red[tid] : 0ull;
+                v = warp_max_u64(v);
+                if (tid == 0 && v != 0ull) atomicMax(&s.best[cons.b], v);
+            }
+            __syncthreads();                 // red[] is reused by the next segment
+        }
     }
 }
 
-// Kernel family.  Register-bank pressure is what bounds the FP32 pipe here: an
-// FFMA reads three registers and an FFMA2 three register PAIRS per issue, and
-// the only operand that can come from the operand-reuse cache is the point
-// coordinate shared by the HPT hypotheses of a thread, so more hypotheses per
-// thread = more reuse, at the price of registers (occupancy) and coarser tiles.
+// Kernel family.  Register-bank bandwidth is what bounds the FP32 pipe here: an
+// FFMA reads three registers (an FFMA2 three register PAIRS) per issue and the
+// only operand the operand-reuse cache can supply is the point coordinate
+// shared by the HPT hypotheses of a thread, so more hypotheses per thread =
+// more reuse, at the price of registers (occupancy) and coarser tiles.
+// Measured on B200 (profiles/): scalar FFMA with 8 hypotheses per thread is the
+// fastest at scale; the small-tile kernels serve small hypothesis counts.
 struct ScoreVariant { int hpt; int packed; int threads; };
 static const ScoreVariant kVariants[] = {
-    {2, 0, 256}, {4, 1, 256}, {4, 0, 256}, {8, 0, 256}, {8, 1, 256}, {4, 0, 128}, {4, 1, 128}, {8, 0, 128}, {8, 1, 128},
+    {2, 0, 256}, {4, 1, 256}, {4, 0, 256}, {8, 0, 256}, {8, 1, 256},
+    {4, 0, 128}, {4, 1, 128}, {8, 0, 128}, {8, 1, 128}, {2, 0, 128},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kDefaultVariant = 1;
 
 template <int HPT, bool PACKED, int THREADS>
-static void launch_one(const DeviceState& s, dim3 grid, int H, int h_offset, int splits, int pps, float thr, cudaStream_t st) {
-    score_kernel<HPT, PACKED, THREADS><<<grid, THREADS, 0, st>>>(s, H, h_offset, splits, pps, thr);
+static void launch_one(const DeviceState& s, int ctas, int H, int h_offset, int T, long long units, int n_units, float thr,
+                       cudaStream_t st) {
+    score_kernel<HPT, PACKED, THREADS><<<ctas, THREADS, 0, st>>>(s, H, h_offset, T, units, n_units, thr);
 }
 template <int HPT, bool PACKED, int THREADS>
 static int occupancy_one() {
@@ -262,7 +322,8 @@ static int occupancy_one() {
         case 5: CALL(4, false, 128); break;       \
         case 6: CALL(4, true, 128); break;        \
         case 7: CALL(8, false, 128); break;       \
-        default: CALL(8, true, 128); break;       \
+        case 8: CALL(8, true, 128); break;        \
+        default: CALL(2, false, 128); break;      \
     }
 
 static int variant_occupancy(int v) {
@@ -279,7 +340,12 @@ int score_num_variants() { return kNumVariants; }
 
 ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     ScorePlan p;
-    p.variant = (variant_override >= 0 && variant_override < kNumVariants) ? variant_override : kDefaultVariant;
+    if (variant_override >= 0 && variant_override < kNumVariants) {
+        p.variant = variant_override;
+    } else {
+        // largest tile that the hypothesis count still fills reasonably
+        p.variant = H >= 1536 ? 3 : (H >= 384 ? 6 : 9);
+    }
     const ScoreVariant& v = kVariants[p.variant];
     p.hyp_per_cta = v.hpt * v.threads;
     p.tiles = (H + p.hyp_per_cta - 1) / p.hyp_per_cta;
@@ -289,34 +355,17 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const long long slots = (long long)sms * variant_occupancy(p.variant);
-    int chunks = (n + SCORE_CHUNK - 1) / SCORE_CHUNK;
-    if (chunks < 1) chunks = 1;
-    // Pick the number of point splits that minimises (waves of resident CTAs) x
-    // (TMA stages per CTA + a fixed per-CTA cost): the grid's tail wave is what
-    // costs most at config-2 sizes.  Ties go to fewer splits (fewer atomics).
-    const long long base = (long long)p.tiles * B;
-    double best_cost = 1e300;
-    int best_s = 1;
-    for (int sp = 1; sp <= chunks; sp++) {
-        int cps = (chunks + sp - 1) / sp;
-        int real = (chunks + cps - 1) / cps;
-        if (real != sp) continue;
-        long long ctas = base * sp;
-        long long waves = (ctas + slots - 1) / slots;
-        double cost = (double)waves * (cps + 0.15);
-        if (cost < best_cost * 0.999) { best_cost = cost; best_s = sp; }
-        if (ctas > slots * 64) break;
-    }
-    int cps = (chunks + best_s - 1) / best_s;
-    p.pts_per_split = cps * SCORE_CHUNK;
-    p.splits = (chunks + cps - 1) / cps;
+    p.n_units = (n + SCORE_GRAIN - 1) / SCORE_GRAIN;
+    p.total_units = (long long)B * p.tiles * p.n_units;
+    long long ctas = (long long)sms * variant_occupancy(p.variant);   // persistent: all CTAs co-resident
+    if (ctas > p.total_units) ctas = p.total_units;
+    if (ctas < 1) ctas = 1;
+    p.ctas = (int)ctas;
     return p;
 }
 
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {
-    dim3 grid(plan.tiles, plan.splits, s.B);
-#define SFM_LAUNCH(h, p, t) launch_one<h, p, t>(s, grid, H, h_offset, plan.splits, plan.pts_per_split, thr, st)
+#define SFM_LAUNCH(h, p, t) launch_one<h, p, t>(s, plan.ctas, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr, st)
     SFM_FOR_VARIANT(plan.variant, SFM_LAUNCH)
 #undef SFM_LAUNCH
 }

@@ -220,7 +220,7 @@ class BatchedPairs:
     def score_plan(self) -> dict:
         out = (C.c_int32 * 4)()
         self.lib.call("sfmb200_score_plan", self._h, out)
-        return {"variant": out[0], "tiles": out[1], "splits": out[2], "pts_per_split": out[3]}
+        return {"variant": out[0], "tiles": out[1], "ctas": out[2], "hyp_per_cta": out[3]}
 
     STAGES = ("ingest", "hypgen", "score", "select", "pose_candidates", "choose_pose", "triangulate")
 

@@ -126,7 +126,7 @@ int sfmb200_get_inlier_mask(sfmb200_t* h, int pair, uint8_t* d_mask /* device [n
 /* Raw device views for zero-copy consumers (valid until destroy). */
 int sfmb200_device_views(sfmb200_t* h, float** d_E, float** d_P, int32_t** d_pose_index, float** d_points,
                          int* point_stride);
-/* how the last estimate was launched: variant, tiles, splits, points per split */
+/* how the last estimate was launched: kernel variant, hypothesis tiles per pair, persistent CTAs, hypotheses per CTA */
 int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t sfmb200_launch_count(sfmb200_t* h);
