@@ -327,11 +327,35 @@ int sfmb200_triangulate(sfmb200_t* h) {
     return SFMB200_OK;
 }
 
+// Whole path in 5 launches: ingest (done by the caller), hypgen, score, the fused
+// select + pose candidates + cheirality kernel, [inlier vote in non-compat mode],
+// triangulation.  Stage marks 4..6 collapse onto the fused kernel.
 static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
-    int rc = sfmb200_estimate_e(h, nullptr, H, seed, thr);
-    if (rc) return rc;
-    if ((rc = sfmb200_pose_candidates(h))) return rc;
-    if ((rc = sfmb200_choose_pose(h))) return rc;
+    if (!h->have_points) return fail(SFMB200_ERR_STATE, "run before set_points%s");
+    if (H < 1 || H > h->s.h_max) return fail(SFMB200_ERR_ARG, "H out of range / above max_hypotheses%s");
+    if (!(thr > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
+    h->H = H;
+    h->h_begin = 0;
+    h->thr = thr;
+    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
+    launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->stream);
+    prof_mark(h, 2);
+    CKL();
+    launch_score(h->s, h->plan, H, 0, thr, h->stream);
+    prof_mark(h, 3);
+    CKL();
+    launch_select_pose_choose(h->s, 0, h->compat, h->stream);
+    prof_mark(h, 4);
+    prof_mark(h, 5);
+    CKL();
+    h->launches += 3;
+    if (!h->compat) {
+        launch_choose_pose(h->s, 0, thr, h->stream);
+        CKL();
+        h->launches++;
+    }
+    prof_mark(h, 6);
+    h->have_candidates = h->have_E = h->have_pose = true;
     return sfmb200_triangulate(h);
 }
 

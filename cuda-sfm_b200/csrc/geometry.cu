@@ -73,12 +73,9 @@ void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cud
 // compat = 1: P_i = [ (U W(^T) V^T)^T | +-u3 ], det-typo sign fix (Q15, Q16).
 // compat = 0: textbook pose for x1^T E x2 = 0: X2 = R X1 + t, R = V W(^T) U^T, t = +-v3.
 // ---------------------------------------------------------------------------
-__global__ void pose_candidates_kernel(DeviceState s, int compat) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= s.B) return;
-    float E[9], u[9], sg[9], v[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) E[i] = s.E[(size_t)b * 9 + i];
+// Candidate c (0..3) of E into P[16].
+__device__ __forceinline__ void pose_candidate(const float* E, int c, int compat, float* P) {
+    float u[9], sg[9], v[9];
     svd3<5>(E, u, sg, v);
     const float W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
     const float Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
@@ -90,42 +87,54 @@ __global__ void pose_candidates_kernel(DeviceState s, int compat) {
             for (int i = 0; i < 9; i++) v[i] = -v[i];
         }
     }
-    float* Pb = s.P + (size_t)b * 64;
+    float t1[9], R[9];
+    const bool first = c < 2;
+    float Wc[9];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        float t1[9], R[9];
-        const float* Wc = (c < 2) ? W : Wt;
-        float sign = (c == 0 || c == 2) ? -1.0f : 1.0f;
-        float tx, ty, tz;
-        if (compat) {
-            mul33_ABt(Wc, v, t1);     // W V^T
-            mul33(u, t1, R);          // U W V^T ; stored transposed
-            float Rt[9];
+    for (int i = 0; i < 9; i++) Wc[i] = first ? W[i] : Wt[i];
+    float sign = (c == 0 || c == 2) ? -1.0f : 1.0f;
+    float tx, ty, tz;
+    if (compat) {
+        mul33_ABt(Wc, v, t1);     // W V^T
+        mul33(u, t1, R);          // U W V^T ; stored transposed
+        float Rt[9];
 #pragma unroll
-            for (int i = 0; i < 3; i++)
+        for (int i = 0; i < 3; i++)
 #pragma unroll
-                for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
+            for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
 #pragma unroll
-            for (int i = 0; i < 9; i++) R[i] = Rt[i];
-            tx = sign * u[2]; ty = sign * u[5]; tz = sign * u[8];
-        } else {
-            mul33_ABt(Wc, u, t1);     // W U^T
-            mul33(v, t1, R);          // V W U^T
-            if (det33(R) < 0.0f) {
+        for (int i = 0; i < 9; i++) R[i] = Rt[i];
+        tx = sign * u[2]; ty = sign * u[5]; tz = sign * u[8];
+    } else {
+        mul33_ABt(Wc, u, t1);     // W U^T
+        mul33(v, t1, R);          // V W U^T
+        if (det33(R) < 0.0f) {
 #pragma unroll
-                for (int i = 0; i < 9; i++) R[i] = -R[i];
-            }
-            tx = sign * v[2]; ty = sign * v[5]; tz = sign * v[8];
+            for (int i = 0; i < 9; i++) R[i] = -R[i];
         }
-        float* P = Pb + 16 * c;
-        P[0] = R[0]; P[1] = R[1]; P[2] = R[2];  P[3] = tx;
-        P[4] = R[3]; P[5] = R[4]; P[6] = R[5];  P[7] = ty;
-        P[8] = R[6]; P[9] = R[7]; P[10] = R[8]; P[11] = tz;
-        P[12] = 0.0f; P[13] = 0.0f; P[14] = 0.0f; P[15] = 1.0f;
+        tx = sign * v[2]; ty = sign * v[5]; tz = sign * v[8];
     }
+    P[0] = R[0]; P[1] = R[1]; P[2] = R[2];  P[3] = tx;
+    P[4] = R[3]; P[5] = R[4]; P[6] = R[5];  P[7] = ty;
+    P[8] = R[6]; P[9] = R[7]; P[10] = R[8]; P[11] = tz;
+    P[12] = 0.0f; P[13] = 0.0f; P[14] = 0.0f; P[15] = 1.0f;
+}
+
+// one thread per (pair, candidate)
+__global__ void pose_candidates_kernel(DeviceState s, int compat) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = g >> 2, c = g & 3;
+    if (b >= s.B) return;
+    float E[9], P[16];
+#pragma unroll
+    for (int i = 0; i < 9; i++) E[i] = s.E[(size_t)b * 9 + i];
+    pose_candidate(E, c, compat, P);
+#pragma unroll
+    for (int i = 0; i < 16; i++) s.P[(size_t)b * 64 + 16 * c + i] = P[i];
 }
 void launch_pose_candidates(const DeviceState& s, int compat, cudaStream_t st) {
-    pose_candidates_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s, compat);
+    int threads = 4 * s.B;
+    pose_candidates_kernel<<<(threads + 63) / 64, 64, 0, st>>>(s, compat);
 }
 
 // DLT rows for one correspondence, camera 1 = I4, camera 2 = M
@@ -166,27 +175,83 @@ __device__ __forceinline__ float sampson_d_geom(const float* e, float x1, float 
 //   X2 = P_i X); arg-max of votes, first on ties; P is left untouched.
 //   One 256-thread CTA per pair.
 // ---------------------------------------------------------------------------
+// Cheirality of candidate M on correspondence c0 (reference semantics): returns
+// whether the triangulated point is in front of both cameras; Minv = M^-1.
+__device__ __forceinline__ bool cheirality_compat(const float4& c0, const float* M, float* Minv) {
+    float A[16], v[4];
+    dlt_matrix(c0.x, c0.y, c0.z, c0.w, M, A);
+    null4<5>(A, v);
+    float X, Y, Z;
+    dehomogenise(v, X, Y, Z);
+    inv4(M, Minv);
+    float z2 = fmaf(Minv[8], X, fmaf(Minv[9], Y, fmaf(Minv[10], Z, Minv[11])));
+    return Z > 0.0f && z2 > 0.0f;
+}
+
+// 4 lanes per pair (one per candidate); the pairs of a warp vote with one ballot.
 __global__ void choose_pose_compat_kernel(DeviceState s) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= s.B) return;
-    float4 c0 = s.corr[(size_t)b * s.n_stride];
-    float* Pb = s.P + (size_t)b * 64;
-    int ind = 0;
-    for (int c = 0; c < 4; c++) {
-        float M[16], A[16], v[4], Minv[16];
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = g >> 2, c = g & 3;
+    bool active = b < s.B;
+    bool pass = false;
+    if (active) {
+        float4 c0 = s.corr[(size_t)b * s.n_stride];
+        float M[16], Minv[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) M[i] = Pb[16 * c + i];
-        dlt_matrix(c0.x, c0.y, c0.z, c0.w, M, A);
-        null4<5>(A, v);
-        float X, Y, Z;
-        dehomogenise(v, X, Y, Z);
-        inv4(M, Minv);
-        float z2 = fmaf(Minv[8], X, fmaf(Minv[9], Y, fmaf(Minv[10], Z, Minv[11])));
-        if (Z > 0.0f && z2 > 0.0f) ind = c;
+        for (int i = 0; i < 16; i++) M[i] = s.P[(size_t)b * 64 + 16 * c + i];
+        pass = cheirality_compat(c0, M, Minv);
 #pragma unroll
-        for (int i = 0; i < 16; i++) Pb[16 * c + i] = Minv[i];
+        for (int i = 0; i < 16; i++) s.P[(size_t)b * 64 + 16 * c + i] = Minv[i];
     }
-    s.P_ind[b] = ind;
+    unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+    if (active && c == 0) {
+        unsigned mine = (m >> ((threadIdx.x & 31) & ~3)) & 0xFu;
+        s.P_ind[b] = mine ? 31 - __clz(mine) : 0;      // last passing index, default 0 (sfm.cu:284-297)
+    }
+}
+
+// Whole-path fusion of select + pose candidates + (compat) cheirality: the three
+// are each a few microseconds of latency-bound work, so as separate launches the
+// gaps cost more than the math.  4 lanes per pair.
+__global__ void select_pose_choose_kernel(DeviceState s, int h_offset, int compat) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = g >> 2, c = g & 3;
+    bool active = b < s.B;
+    bool pass = false;
+    if (active) {
+        unsigned long long packed = s.best[b];
+        unsigned int hg = 0xFFFFFFFFu - (unsigned int)(packed & 0xFFFFFFFFull);
+        int local = (int)hg - h_offset;
+        const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
+        float E[9], P[16];
+#pragma unroll
+        for (int k = 0; k < 9; k++) E[k] = (local >= 0 && local < s.h_stride) ? Eb[(size_t)k * s.h_stride + local] : 0.0f;
+        if (c == 0) {
+            s.best_idx[b] = (int)hg;
+            s.best_count[b] = (int)(packed >> 32);
+#pragma unroll
+            for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = E[k];
+        }
+        pose_candidate(E, c, compat, P);
+        if (compat) {
+            float4 c0 = s.corr[(size_t)b * s.n_stride];
+            float Minv[16];
+            pass = cheirality_compat(c0, P, Minv);
+#pragma unroll
+            for (int i = 0; i < 16; i++) P[i] = Minv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) s.P[(size_t)b * 64 + 16 * c + i] = P[i];
+    }
+    unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+    if (active && c == 0 && compat) {
+        unsigned mine = (m >> ((threadIdx.x & 31) & ~3)) & 0xFu;
+        s.P_ind[b] = mine ? 31 - __clz(mine) : 0;
+    }
+}
+void launch_select_pose_choose(const DeviceState& s, int h_offset, int compat, cudaStream_t st) {
+    int threads = 4 * s.B;
+    select_pose_choose_kernel<<<(threads + 63) / 64, 64, 0, st>>>(s, h_offset, compat);
 }
 
 __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, float thr) {
@@ -232,7 +297,7 @@ __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, fl
 }
 void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_t st) {
     if (compat)
-        choose_pose_compat_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s);
+        choose_pose_compat_kernel<<<(4 * s.B + 63) / 64, 64, 0, st>>>(s);
     else
         choose_pose_vote_kernel<<<s.B, 256, 0, st>>>(s, thr);
 }

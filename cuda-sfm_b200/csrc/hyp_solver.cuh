@@ -25,6 +25,9 @@ struct Corr { float x1, y1, x2, y2; };
 #ifndef SFM_HYP_REFINE
 #define SFM_HYP_REFINE 3
 #endif
+#ifndef SFM_HYP_FAST_ANGLE
+#define SFM_HYP_FAST_ANGLE 1     // device: approximate rotation angles in the 9x9 eigensolve
+#endif
 
 SFM_HD void design_row(float x1, float y1, float x2, float y2, float* a) {
     a[0] = x1 * x2; a[1] = x1 * y2; a[2] = x1;
@@ -92,7 +95,11 @@ SFM_HD void solve_hypothesis(const Corr* pts, float* E) {
 #pragma unroll
             for (int q = p + 1; q < 9; q++) {
                 float c, s, t;
+#if SFM_HYP_FAST_ANGLE
+                jacobi_angle_fast(g[p][p], g[q][q], g[p][q], c, s, t);
+#else
                 jacobi_angle(g[p][p], g[q][q], g[p][q], c, s, t);
+#endif
                 g[p][p] = fmaf(-t, g[p][q], g[p][p]);
                 g[q][q] = fmaf(t, g[p][q], g[q][q]);
                 g[p][q] = 0.0f;

@@ -5,6 +5,8 @@
 // Roofline: FP32 pipe.  ~5 sweeps x 36 rotations x ~80 FP32 instructions plus
 // Gram build / refinement / 3x3 SVD ~= 17 k FP32 instructions per hypothesis;
 // memory traffic is 8 gathered 16-byte correspondences (L2 hits) in and 36 B out.
+#include <stdlib.h>
+
 #include "hyp_solver.cuh"
 #include "internal.cuh"
 
@@ -41,7 +43,8 @@ __device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int
     return ok;
 }
 
-__global__ void __launch_bounds__(HYP_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(HYP_THREADS, MINB)
 hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride, int H, int h_offset,
               unsigned long long seed) {
     const int b = blockIdx.y;
@@ -66,7 +69,18 @@ void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pai
                    unsigned long long seed, cudaStream_t st) {
     int need = H > s.tiles_max ? H : s.tiles_max;
     dim3 grid((need + HYP_THREADS - 1) / HYP_THREADS, s.B);
-    hypgen_kernel<<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+    // Resident CTAs per SM: 2 (200 registers, no spills) or 3 (168 registers).
+    static int minb = [] {
+        const char* e = getenv("SFMB200_HYPGEN_MINB");
+        int v = e ? atoi(e) : 2;
+        return (v >= 2 && v <= 4) ? v : 2;
+    }();
+    if (minb == 2)
+        hypgen_kernel<2><<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+    else if (minb == 3)
+        hypgen_kernel<3><<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+    else
+        hypgen_kernel<4><<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
 }
 
 // Multi-GPU single-pair case: after the (count, index) all-reduce every rank

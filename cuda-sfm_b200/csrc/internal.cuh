@@ -60,6 +60,7 @@ void launch_select(const DeviceState& s, int h_offset, cudaStream_t st);
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride,
                        unsigned long long seed, cudaStream_t st);
 void launch_pose_candidates(const DeviceState& s, int compat, cudaStream_t st);
+void launch_select_pose_choose(const DeviceState& s, int h_offset, int compat, cudaStream_t st);
 void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_t st);
 void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st);
 void launch_vbo(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, cudaStream_t st);

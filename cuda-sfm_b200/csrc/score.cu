@@ -141,61 +141,83 @@ struct ChunkWalk {
     }
 };
 
-template <int HPT, bool PACKED, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// Chunk descriptor handed from the producer thread to the consumers through
+// shared memory (published by the mbarrier the chunk's TMA completes on).
+struct ChunkDesc {
+    int b, t;          // pair, hypothesis tile
+    int cnt_flags;     // points in the chunk | seg_first << 30 | seg_last << 31; 0 = no more work
+    int seg_pts;       // points of the whole segment (valid when seg_last)
+};
+
+template <int HPT, bool PACKED, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, int n_units, float thr) {
     constexpr int HPC = HPT * THREADS;
     constexpr int F4_PER_PT = PACKED ? 2 : 1;
     __shared__ __align__(128) float4 buf[2][SCORE_CHUNK * F4_PER_PT];
     __shared__ __align__(8) uint64_t full[2];
+    __shared__ __align__(16) ChunkDesc desc[2];
+    __shared__ ChunkWalk walk;          // producer state lives here, not in loop-carried registers:
+                                        // the FFMA stream needs every register for operand reuse
     __shared__ unsigned long long red[THREADS / 32];
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
-    const long long u0 = total_units * blockIdx.x / gridDim.x;
-    const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
-
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ChunkWalk w;
+        w.init(total_units * blockIdx.x / gridDim.x, total_units * (blockIdx.x + 1) / gridDim.x, n_units, s.n, T);
+        walk = w;
     }
     __syncthreads();
 
-    ChunkWalk prod, cons;
-    cons.init(u0, u1, n_units, s.n, T);
-    auto issue = [&](const ChunkWalk& w, int stage) {
-        const float4* src = PACKED ? s.corr_dup + ((size_t)w.b * s.n_stride + w.p0) * 2
-                                   : s.corr + (size_t)w.b * s.n_stride + w.p0;
-        uint32_t bytes = (uint32_t)w.cnt * 16u * F4_PER_PT;
-        mbar_expect_tx(&full[stage], bytes);
-        tma_load_1d(&buf[stage][0], src, bytes, &full[stage]);
+    // Producer step (thread 0): advance the walk, publish the descriptor of the
+    // next chunk and start its TMA; an empty descriptor + plain arrive ends the loop.
+    auto produce = [&](int stage) {
+        ChunkWalk w = walk;
+        bool more = w.next();
+        walk = w;
+        ChunkDesc d;
+        d.b = w.b; d.t = w.t; d.seg_pts = w.seg_pts;
+        d.cnt_flags = more ? (w.cnt | (w.seg_first ? (1 << 30) : 0) | (w.seg_last ? (1 << 31) : 0)) : 0;
+        desc[stage] = d;
+        if (more) {
+            const float4* src = PACKED ? s.corr_dup + ((size_t)w.b * s.n_stride + w.p0) * 2
+                                       : s.corr + (size_t)w.b * s.n_stride + w.p0;
+            uint32_t bytes = (uint32_t)w.cnt * 16u * F4_PER_PT;
+            mbar_expect_tx(&full[stage], bytes);
+            tma_load_1d(&buf[stage][0], src, bytes, &full[stage]);
+        } else {
+            mbar_expect_tx(&full[stage], 0);
+        }
     };
-    if (tid == 0) {
-        prod.init(u0, u1, n_units, s.n, T);
-        if (prod.next()) issue(prod, 0);
-    }
+    if (tid == 0) produce(0);
 
     float e[PACKED ? 1 : HPT][9];               // scalar path: one E per hypothesis
     float2 e2[PACKED ? HPT / 2 : 1][9];         // packed path: E of a hypothesis pair per float2
-    int hl[HPT];
     unsigned int cnt[HPT];
     const float nthr = -thr;
     const float2 nthr2 = make_float2(nthr, nthr);
     (void)e; (void)e2; (void)nthr2;
 
-    for (int k = 0; cons.next(); k++) {
-        if (tid == 0 && prod.next()) issue(prod, (k + 1) & 1);
-        if (cons.seg_first) {
-            // essential matrices of this thread's hypotheses -> registers
-            const float* Eb = s.Ecand + (size_t)cons.b * 9 * s.h_stride;
+    for (int k = 0;; k++) {
+        if (tid == 0) produce((k + 1) & 1);     // safe: stage (k+1)&1 was released by the barrier ending iteration k-1
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        const ChunkDesc d = desc[k & 1];
+        if (d.cnt_flags == 0) break;
+        const int n_here = d.cnt_flags & 0x3FFFFFFF;
+        if (d.cnt_flags & (1 << 30)) {
+            // first chunk of a segment: this thread's essential matrices -> registers
+            const float* Eb = s.Ecand + (size_t)d.b * 9 * s.h_stride;
 #pragma unroll
             for (int j = 0; j < HPT; j++) {
-                hl[j] = cons.t * HPC + j * THREADS + tid;
-                bool valid = hl[j] < H;
+                int h = d.t * HPC + j * THREADS + tid;
+                bool valid = h < H;
 #pragma unroll
                 for (int q = 0; q < 9; q++) {
-                    float v = valid ? __ldg(Eb + (size_t)q * s.h_stride + hl[j]) : 0.0f;
+                    float v = valid ? __ldg(Eb + (size_t)q * s.h_stride + h) : 0.0f;
                     if constexpr (PACKED) {
                         if (j & 1) e2[j / 2][q].y = v; else e2[j / 2][q].x = v;
                     } else {
@@ -205,9 +227,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
                 cnt[j] = 0u;
             }
         }
-        mbar_wait(&full[k & 1], (k >> 1) & 1);
         const float4* pb = buf[k & 1];
-        const int n_here = cons.cnt;
         if constexpr (PACKED) {
 #pragma unroll 4
             for (int i = 0; i < n_here; i++) {
@@ -216,9 +236,9 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
                 float2 x2 = make_float2(q.x, q.y), y2 = make_float2(q.z, q.w);
 #pragma unroll
                 for (int j = 0; j < HPT / 2; j++) {
-                    float2 d = sampson_d2(e2[j], x1, y1, x2, y2, nthr2);
-                    cnt[2 * j] += __float_as_uint(d.x) >> 31;
-                    cnt[2 * j + 1] += __float_as_uint(d.y) >> 31;
+                    float2 dd = sampson_d2(e2[j], x1, y1, x2, y2, nthr2);
+                    cnt[2 * j] += __float_as_uint(dd.x) >> 31;
+                    cnt[2 * j + 1] += __float_as_uint(dd.y) >> 31;
                 }
             }
         } else {
@@ -227,50 +247,56 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
                 float4 p = pb[i];
 #pragma unroll
                 for (int j = 0; j < HPT; j++) {
-                    float d = sampson_d(e[j], p.x, p.y, p.z, p.w, nthr);
-                    cnt[j] += __float_as_uint(d) >> 31;
+                    float dd = sampson_d(e[j], p.x, p.y, p.z, p.w, nthr);
+                    cnt[j] += __float_as_uint(dd) >> 31;
                 }
             }
         }
-        __syncthreads();   // buf[k & 1] is free for the chunk issued at the top of iteration k + 1
-        if (!cons.seg_last) continue;
+        __syncthreads();   // buf / desc [k & 1] are free for the chunk produced at the top of iteration k + 1
+        if (d.cnt_flags >= 0) continue;   // bit 31 clear: segment continues
 
         // ---- end of a segment: counts + fused arg-max for (pair b, tile t) ----
-        int* counts = s.counts + (size_t)cons.b * s.h_stride;
+        int* counts = s.counts + (size_t)d.b * s.h_stride;
         unsigned long long key = 0ull;
         bool do_argmax;
-        if (cons.seg_pts == s.n) {          // this CTA saw every point of the tile
+        if (d.seg_pts == s.n) {             // this CTA saw every point of the tile
 #pragma unroll
-            for (int j = 0; j < HPT; j++)
-                if (hl[j] < H) {
-                    counts[hl[j]] = (int)cnt[j];
+            for (int j = 0; j < HPT; j++) {
+                int h = d.t * HPC + j * THREADS + tid;
+                if (h < H) {
+                    counts[h] = (int)cnt[j];
                     unsigned long long kk = ((unsigned long long)cnt[j] << 32) |
-                                            (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + hl[j]));
+                                            (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + h));
                     key = kk > key ? kk : key;
                 }
+            }
             do_argmax = true;
         } else {                             // partial: add, the CTA completing the tile reduces it
 #pragma unroll
-            for (int j = 0; j < HPT; j++)
-                if (hl[j] < H && cnt[j] != 0u) atomicAdd(&counts[hl[j]], (int)cnt[j]);
+            for (int j = 0; j < HPT; j++) {
+                int h = d.t * HPC + j * THREADS + tid;
+                if (h < H && cnt[j] != 0u) atomicAdd(&counts[h], (int)cnt[j]);
+            }
             __threadfence();
             __syncthreads();
             if (tid == 0) {
-                int before = atomicAdd(&s.tile_done[(size_t)cons.b * s.tiles_max + cons.t], cons.seg_pts);
-                s_last = (before + cons.seg_pts == s.n);
+                int before = atomicAdd(&s.tile_done[(size_t)d.b * s.tiles_max + d.t], d.seg_pts);
+                s_last = (before + d.seg_pts == s.n);
             }
             __syncthreads();
             do_argmax = s_last != 0;
             if (do_argmax) {
                 __threadfence();
 #pragma unroll
-                for (int j = 0; j < HPT; j++)
-                    if (hl[j] < H) {
-                        unsigned int total = (unsigned int)__ldcg(&counts[hl[j]]);
+                for (int j = 0; j < HPT; j++) {
+                    int h = d.t * HPC + j * THREADS + tid;
+                    if (h < H) {
+                        unsigned int total = (unsigned int)__ldcg(&counts[h]);
                         unsigned long long kk = ((unsigned long long)total << 32) |
-                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + hl[j]));
+                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + h));
                         key = kk > key ? kk : key;
                     }
+                }
             }
         }
         if (do_argmax) {                     // uniform across the CTA
@@ -280,7 +306,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
             if (tid < 32) {
                 unsigned long long v = tid < THREADS / 32 ? red[tid] : 0ull;
                 v = warp_max_u64(v);
-                if (tid == 0 && v != 0ull) atomicMax(&s.best[cons.b], v);
+                if (tid == 0 && v != 0ull) atomicMax(&s.best[d.b], v);
             }
             __syncthreads();                 // red[] is reused by the next segment
         }
@@ -294,42 +320,49 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
 // more reuse, at the price of registers (occupancy) and coarser tiles.
 // Measured on B200 (profiles/): scalar FFMA with 8 hypotheses per thread is the
 // fastest at scale; the small-tile kernels serve small hypothesis counts.
-struct ScoreVariant { int hpt; int packed; int threads; };
+struct ScoreVariant { int hpt; int packed; int threads; int minb; };
 static const ScoreVariant kVariants[] = {
-    {2, 0, 256}, {4, 1, 256}, {4, 0, 256}, {8, 0, 256}, {8, 1, 256},
-    {4, 0, 128}, {4, 1, 128}, {8, 0, 128}, {8, 1, 128}, {2, 0, 128},
+    {2, 0, 256, 1}, {4, 1, 256, 1}, {4, 0, 256, 1}, {8, 0, 256, 2}, {8, 1, 256, 1},
+    {4, 0, 128, 1}, {4, 1, 128, 1}, {8, 0, 128, 4}, {8, 1, 128, 2}, {2, 0, 128, 1},
+    {8, 0, 256, 1}, {8, 0, 128, 3}, {8, 0, 128, 2}, {16, 0, 128, 1}, {16, 0, 128, 2}, {12, 0, 128, 2},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-template <int HPT, bool PACKED, int THREADS>
+template <int HPT, bool PACKED, int THREADS, int MINB>
 static void launch_one(const DeviceState& s, int ctas, int H, int h_offset, int T, long long units, int n_units, float thr,
                        cudaStream_t st) {
-    score_kernel<HPT, PACKED, THREADS><<<ctas, THREADS, 0, st>>>(s, H, h_offset, T, units, n_units, thr);
+    score_kernel<HPT, PACKED, THREADS, MINB><<<ctas, THREADS, 0, st>>>(s, H, h_offset, T, units, n_units, thr);
 }
-template <int HPT, bool PACKED, int THREADS>
+template <int HPT, bool PACKED, int THREADS, int MINB>
 static int occupancy_one() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<HPT, PACKED, THREADS>, THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<HPT, PACKED, THREADS, MINB>, THREADS, 0);
     return n > 0 ? n : 1;
 }
-#define SFM_FOR_VARIANT(v, CALL)                  \
-    switch (v) {                                  \
-        case 0: CALL(2, false, 256); break;       \
-        case 1: CALL(4, true, 256); break;        \
-        case 2: CALL(4, false, 256); break;       \
-        case 3: CALL(8, false, 256); break;       \
-        case 4: CALL(8, true, 256); break;        \
-        case 5: CALL(4, false, 128); break;       \
-        case 6: CALL(4, true, 128); break;        \
-        case 7: CALL(8, false, 128); break;       \
-        case 8: CALL(8, true, 128); break;        \
-        default: CALL(2, false, 128); break;      \
+#define SFM_FOR_VARIANT(v, CALL)                     \
+    switch (v) {                                     \
+        case 0: CALL(2, false, 256, 1); break;       \
+        case 1: CALL(4, true, 256, 1); break;        \
+        case 2: CALL(4, false, 256, 1); break;       \
+        case 3: CALL(8, false, 256, 2); break;       \
+        case 4: CALL(8, true, 256, 1); break;        \
+        case 5: CALL(4, false, 128, 1); break;       \
+        case 6: CALL(4, true, 128, 1); break;        \
+        case 7: CALL(8, false, 128, 4); break;       \
+        case 8: CALL(8, true, 128, 2); break;        \
+        case 9: CALL(2, false, 128, 1); break;       \
+        case 10: CALL(8, false, 256, 1); break;      \
+        case 11: CALL(8, false, 128, 3); break;      \
+        case 12: CALL(8, false, 128, 2); break;      \
+        case 13: CALL(16, false, 128, 1); break;     \
+        case 14: CALL(16, false, 128, 2); break;     \
+        default: CALL(12, false, 128, 2); break;     \
     }
 
 static int variant_occupancy(int v) {
     static int cache[kNumVariants] = {0};
     if (cache[v] == 0) {
-#define SFM_OCC(h, p, t) cache[v] = occupancy_one<h, p, t>()
+#define SFM_OCC(h, p, t, m) cache[v] = occupancy_one<h, p, t, m>()
         SFM_FOR_VARIANT(v, SFM_OCC)
 #undef SFM_OCC
     }
@@ -365,7 +398,7 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
 }
 
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {
-#define SFM_LAUNCH(h, p, t) launch_one<h, p, t>(s, plan.ctas, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr, st)
+#define SFM_LAUNCH(h, p, t, m) launch_one<h, p, t, m>(s, plan.ctas, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr, st)
     SFM_FOR_VARIANT(plan.variant, SFM_LAUNCH)
 #undef SFM_LAUNCH
 }

@@ -36,6 +36,29 @@ SFM_HD void jacobi_angle(float app, float aqq, float apq, float& c, float& s, fl
     t = tt;
 }
 
+// Same rotation from hardware approximations (MUFU.RSQ / MUFU.RCP): a Jacobi
+// sweep converges for any angle close to the annihilating one, and (c, s) stays
+// orthonormal to ~2 ulp because s = t*c with c = rsqrt(1 + t^2).  Used where
+// the rotation sequence is followed by a refinement against the original
+// matrix (hyp_solver.cuh); it shortens the serial angle chain ~4x.
+//   t = beta / (alpha + sgn(alpha) * sqrt(alpha^2 + beta^2)), alpha = (a_qq - a_pp)/2, beta = a_pq
+SFM_HD void jacobi_angle_fast(float app, float aqq, float apq, float& c, float& s, float& t) {
+#if defined(__CUDA_ARCH__)
+    float alpha = 0.5f * (aqq - app);
+    float rho2 = fmaf(alpha, alpha, apq * apq);
+    bool skip = !(rho2 > 1e-36f) || apq == 0.0f;
+    float rho = rho2 * rsqrtf(rho2);
+    float denom = alpha + copysignf(rho, alpha);
+    float tt = skip ? 0.0f : __fdividef(apq, denom);
+    float cc = rsqrtf(fmaf(tt, tt, 1.0f));
+    c = cc;
+    s = tt * cc;
+    t = tt;
+#else
+    jacobi_angle(app, aqq, apq, c, s, t);
+#endif
+}
+
 // Givens pair (c, s) with c*a + s*b = r >= 0 and -s*a + c*b = 0.
 SFM_HD void givens(float a, float b, float& c, float& s) {
     float r2 = fmaf(a, a, b * b);

@@ -57,12 +57,20 @@ def stages(n, H, variant, pairs=1, reps=10, label=""):
 
 
 if __name__ == "__main__":
-    emit(what="device", name=torch.cuda.get_device_name(0), sms=torch.cuda.get_device_properties(0).multi_processor_count)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    emit(what="device", name=torch.cuda.get_device_name(0), sms=torch.cuda.get_device_properties(0).multi_processor_count,
+         hypgen_minb=os.environ.get("SFMB200_HYPGEN_MINB", "2"))
+    if which == "hypgen":
+        stages(10_000, 65_536, -1, label="config2")
+        stages(4096, 4096, -1, pairs=256, reps=3, label="config4 slice: 256 pairs")
+        sys.exit(0)
     probe()
-    for v in range(9):
+    nv = 16
+    for v in range(nv):
         stages(10_000, 65_536, v, label="config2")
-    for v in (1, 3, 4):
-        stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp (config 3 slice / config 5 triangulation)")
-    for v in (1, 3, 4, 6, 8):
+    for v in (3, 4, 10, 11, 12, 13, 14, 15):
+        stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp")
+    for v in (3, 4, 10, 12, 13, 15):
         stages(4096, 4096, v, pairs=256, reps=3, label="config4 slice: 256 pairs")
-    stages(2000, 250, 1, label="config1-like: 2k corr, 250 hyp")
+    stages(2000, 250, -1, label="config1-like: 2k corr, 250 hyp")
+    stages(10_000, 65_536, -1, label="config2 auto")
