@@ -376,8 +376,10 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     if (variant_override >= 0 && variant_override < kNumVariants) {
         p.variant = variant_override;
     } else {
-        // largest tile that the hypothesis count still fills reasonably
-        p.variant = H >= 1536 ? 3 : (H >= 384 ? 6 : 9);
+        // Measured on B200 (profiles/r01_variant_sweep.md): packed FFMA2 with 8
+        // hypotheses per thread and one 256-thread CTA per SM is the fastest at
+        // every large shape; smaller tiles only when H cannot fill a 2048 tile.
+        p.variant = H >= 1536 ? 4 : (H >= 768 ? 1 : (H >= 384 ? 6 : 9));
     }
     const ScoreVariant& v = kVariants[p.variant];
     p.hyp_per_cta = v.hpt * v.threads;
