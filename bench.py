@@ -37,6 +37,9 @@ import __graft_entry__ as entry  # noqa: E402
 
 N_CORR, N_HYP, THR, SEED = 10_000, 65_536, 1e-6, 1237
 FLOP_PER_EVAL = 34.0              # 15 FFMA x2 + 3 FMUL + 1 compare
+# dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch at this config,
+# from the ncu --set full capture summarised in profiles/r01_ncu_summary.md
+SCORE_TRAFFIC_BYTES_NCU = 2_969_856
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4
 
 
@@ -58,7 +61,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -253,7 +256,7 @@ def run_ours(args):
         "peak_measured_probe": fp32_probe, "frac_of_measured_probe": achieved / fp32_probe if achieved else None,
         "probe": probe, "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": N_HYP * N_CORR,
         "kernel_ms": score_ms, "evals_per_s_kernel": N_HYP * N_CORR / (score_ms * 1e-3) if score_ms > 0 else None,
-        "traffic": None,
+        "traffic": SCORE_TRAFFIC_BYTES_NCU, "traffic_unit": "bytes per launch (ncu r01 capture; algorithmic input 2.36 MB of E candidates + 0.32 MB of points)",
     }
     tri_ms = float(stage_ms[6])
     hbm = peaks.get("hbm_gbs", 6650.0)
@@ -367,7 +370,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
