@@ -67,6 +67,7 @@ SIGNATURES = {
     "sfmb200_host_svd3": (None, [_f, _f, _f, _f]),
     "sfmb200_host_solve_hypothesis": (None, [_f, _f]),
     "sfmb200_host_null4": (None, [_f, _f]),
+    "sfmb200_host_null4_fast": (C.c_int, [_f, _f]),
     "sfmb200_host_inv4": (C.c_int, [_f, _f]),
     "sfmb200_host_sample_indices": (None, [C.c_uint64, C.c_uint64, C.c_int, _i]),
     # kernels.h facade wrappers (la_wrappers.cu)

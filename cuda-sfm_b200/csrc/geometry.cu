@@ -324,7 +324,9 @@ __global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inl
     if (keep) {
         float A[16], v[4];
         dlt_matrix(p.x, p.y, p.z, p.w, sM, A);
-        null4<5>(A, v);
+        // inverse iteration (8 solves on one Cholesky factor); Jacobi only for the
+        // rare point whose two smallest singular values nearly coincide
+        if (!null4_inverse_iteration<8>(A, v)) null4<5>(A, v);
         dehomogenise(v, X, Y, Z);
     }
     float* out = s.points + (size_t)b * 4 * s.n_stride;

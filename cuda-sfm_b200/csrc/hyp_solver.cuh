@@ -55,6 +55,18 @@ SFM_HD void hartley(const float* x, const float* y, float& s, float& cx, float& 
 // pts: the 8 sampled correspondences in normalised camera coordinates.
 // E (row-major 3x3): projected essential matrix, Frobenius norm sqrt(2);
 // all zeros when the sample is degenerate (non-finite anywhere).
+// SYNC (device only): 0 = none; 1 = __syncthreads() before every sweep; 2 = before
+// every row of rotations.  A sweep is ~3,000 unrolled instructions (~46 KB), more
+// than the instruction cache: keeping the CTA's warps in step lets them share
+// each fetched line instead of thrashing it.  Every thread of the CTA must call.
+template <int SYNC>
+SFM_HD void sweep_sync() {
+#if defined(__CUDA_ARCH__)
+    if (SYNC > 0) __syncthreads();
+#endif
+}
+
+template <int SYNC = 0>
 SFM_HD void solve_hypothesis(const Corr* pts, float* E) {
     float x1[8], y1[8], x2[8], y2[8];
 #pragma unroll
@@ -90,8 +102,10 @@ SFM_HD void solve_hypothesis(const Corr* pts, float* E) {
 
 #pragma unroll 1
     for (int sw = 0; sw < SFM_HYP_SWEEPS; sw++) {
+        sweep_sync<(SYNC >= 1) ? 1 : 0>();
 #pragma unroll
-        for (int p = 0; p < 8; p++)
+        for (int p = 0; p < 8; p++) {
+            if (p > 0) sweep_sync<(SYNC >= 2) ? 1 : 0>();
 #pragma unroll
             for (int q = p + 1; q < 9; q++) {
                 float c, s, t;
@@ -119,6 +133,7 @@ SFM_HD void solve_hypothesis(const Corr* pts, float* E) {
                     V[k][q] = fmaf(s, a, c * b);
                 }
             }
+        }
     }
     float lam[9];
 #pragma unroll

@@ -5,6 +5,7 @@
 // Roofline: FP32 pipe.  ~5 sweeps x 36 rotations x ~80 FP32 instructions plus
 // Gram build / refinement / 3x3 SVD ~= 17 k FP32 instructions per hypothesis;
 // memory traffic is 8 gathered 16-byte correspondences (L2 hits) in and 36 B out.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "hyp_solver.cuh"
@@ -12,7 +13,6 @@
 
 namespace sfmb200 {
 
-constexpr int HYP_THREADS = 128;
 
 // Loads the 8 sampled correspondences of hypothesis (pair b, global index hg).
 // A sample with an out-of-range or repeated index is degenerate: returns false.
@@ -43,44 +43,63 @@ __device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int
     return ok;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(HYP_THREADS, MINB)
+template <int THREADS, int MINB, int SYNC>
+__global__ void __launch_bounds__(THREADS, MINB)
 hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride, int H, int h_offset,
               unsigned long long seed) {
     const int b = blockIdx.y;
-    const int j = blockIdx.x * HYP_THREADS + threadIdx.x;   // local hypothesis slot
+    const int j = blockIdx.x * THREADS + threadIdx.x;   // local hypothesis slot
     // Reset the per-launch accumulators of this pair (scoring adds into them).
     if (j < s.tiles_max) s.tile_done[(size_t)b * s.tiles_max + j] = 0;
     if (j == 0) s.best[b] = 0ull;
-    if (j >= H) return;
+    const bool live = j < H;
+    if (SYNC == 0 && !live) return;                     // with barriers every thread must stay
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     const int32_t* rows = d_idx ? d_idx + (size_t)b * idx_pair_stride : nullptr;
     Corr pts[8];
     float E[9];
-    bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b, (long long)h_offset + j, pts);
-    solve_hypothesis(pts, E);
+    bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b,
+                          (long long)h_offset + (live ? j : 0), pts);
+    solve_hypothesis<SYNC>(pts, E);
+    if (!live) return;
     float* out = s.Ecand + (size_t)b * 9 * s.h_stride + j;
 #pragma unroll
     for (int k = 0; k < 9; k++) out[(size_t)k * s.h_stride] = ok ? E[k] : 0.0f;
     s.counts[(size_t)b * s.h_stride + j] = 0;
 }
 
+// Variant for experiments: SFMB200_HYPGEN=<threads>,<minb>,<sync>  (default 128,2,0)
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
                    unsigned long long seed, cudaStream_t st) {
-    int need = H > s.tiles_max ? H : s.tiles_max;
-    dim3 grid((need + HYP_THREADS - 1) / HYP_THREADS, s.B);
-    // Resident CTAs per SM: 2 (200 registers, no spills) or 3 (168 registers).
-    static int minb = [] {
-        const char* e = getenv("SFMB200_HYPGEN_MINB");
-        int v = e ? atoi(e) : 2;
-        return (v >= 2 && v <= 4) ? v : 2;
+    static int cfg = [] {
+        const char* e = getenv("SFMB200_HYPGEN");
+        int t = 128, m = 2, y = 0;
+        if (e) sscanf(e, "%d,%d,%d", &t, &m, &y);
+        return t * 100 + m * 10 + y;
     }();
-    if (minb == 2)
-        hypgen_kernel<2><<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
-    else if (minb == 3)
-        hypgen_kernel<3><<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
-    else
-        hypgen_kernel<4><<<grid, HYP_THREADS, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+    int need = H > s.tiles_max ? H : s.tiles_max;
+#define SFM_HG(T, M, Y)                                                                              \
+    case (T * 100 + M * 10 + Y): {                                                                   \
+        dim3 grid((need + T - 1) / T, s.B);                                                          \
+        hypgen_kernel<T, M, Y><<<grid, T, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);    \
+        break;                                                                                       \
+    }
+    switch (cfg) {
+        SFM_HG(128, 2, 0)
+        SFM_HG(128, 2, 1)
+        SFM_HG(128, 2, 2)
+        SFM_HG(256, 1, 0)
+        SFM_HG(256, 1, 1)
+        SFM_HG(256, 1, 2)
+        SFM_HG(64, 4, 0)
+        SFM_HG(64, 4, 1)
+        SFM_HG(64, 4, 2)
+        default: {
+            dim3 grid((need + 127) / 128, s.B);
+            hypgen_kernel<128, 2, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+        }
+    }
+#undef SFM_HG
 }
 
 // Multi-GPU single-pair case: after the (count, index) all-reduce every rank
@@ -98,7 +117,7 @@ __global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_i
     Corr pts[8];
     float E[9];
     bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b, (long long)hg, pts);
-    solve_hypothesis(pts, E);
+    solve_hypothesis<0>(pts, E);
 #pragma unroll
     for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = ok ? E[k] : 0.0f;
     s.best_idx[b] = (int)hg;

@@ -144,6 +144,8 @@ int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms);
 void sfmb200_host_svd3(const float a[9], float u[9], float s[9], float v[9]);
 void sfmb200_host_solve_hypothesis(const float pts[32], float E[9]);
 void sfmb200_host_null4(const float A[16], float x[4]);
+/* inverse-iteration fast path of the same null vector; returns 1 when it did not converge (caller falls back) */
+int sfmb200_host_null4_fast(const float A[16], float x[4]);
 int sfmb200_host_inv4(const float m[16], float out[16]);
 void sfmb200_host_sample_indices(uint64_t seed, uint64_t h, int n, int32_t idx[8]);
 

@@ -148,6 +148,35 @@ def test_host_null4_and_inv4(lib):
     assert lib.raw("sfmb200_host_inv4")(P(Z), P(np.zeros(16, np.float32))) != 0
 
 
+def test_host_null4_fast_path_matches_jacobi_on_dlt_matrices(lib, O):
+    """Triangulation's inverse-iteration solve vs the Jacobi solve vs fp64, on real
+    DLT matrices (inliers and outliers, true and inverted pose)."""
+    K, Kinv = O.reference_K()
+    sc = O.synthetic_pair(1500, seed=5, noise_px=2.0)
+    x = O.normalise_points(sc["px"], Kinv)
+    M = np.eye(4)
+    M[:3, :3], M[:3, 3] = sc["R"], sc["t"]
+    for MM in (M, np.linalg.inv(M)):
+        A = O.dlt_rows(x, MM).astype(np.float32)
+        ref = O.triangulate(x, MM)
+        fast = np.zeros((len(x), 4), np.float32)
+        fails = 0
+        for i in range(len(x)):
+            f = lib.raw("sfmb200_host_null4_fast")(P(A[i]), P(fast[i]))
+            fails += f
+            if f:
+                lib.raw("sfmb200_host_null4")(P(A[i]), P(fast[i]))
+        X = fast[:, :3] / fast[:, 3:4]
+        rel = np.abs(X.T - ref[:3]).max(0) / np.maximum(np.abs(ref[:3]).max(0), 1e-3)
+        assert fails <= 2                       # the fallback exists for pathological geometry only
+        assert np.median(rel) < 1e-6 and np.percentile(rel, 99) < 1e-4 and rel.max() < 5e-3
+    # a matrix with a repeated smallest singular value must report non-convergence or a valid null vector
+    A = np.diag([1.0, 1.0, 1e-3, 1e-3]).astype(np.float32)
+    v = np.zeros(4, np.float32)
+    f = lib.raw("sfmb200_host_null4_fast")(P(A), P(v))
+    assert f == 1 or abs(np.linalg.norm(A @ v)) < 2e-3
+
+
 def test_shard_range_and_keys(pkg):
     sh = pkg.sharding
     for total in (0, 1, 7, 8, 65536, 1000003):
