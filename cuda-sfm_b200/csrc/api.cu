@@ -32,6 +32,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 
 struct sfmb200_handle {
     DeviceState s;
+    RefitState refit;
     cudaStream_t stream;
     bool own_stream;
     int device;
@@ -113,6 +114,13 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_pi = carve(B * sizeof(int));
     size_t o_pts = carve(B * 4 * (size_t)s.n_stride * sizeof(float));
     size_t o_tc = carve(B * sizeof(int));
+    const int refit_blocks = 64;
+    size_t o_rc = carve(B * 9 * sizeof(float));
+    size_t o_rT = carve(B * 8 * sizeof(float));
+    size_t o_rf = carve(B * 4 * sizeof(int));
+    size_t o_ri = carve(B * sizeof(int));
+    size_t o_rm = carve(B * refit_blocks * 7 * sizeof(float));
+    size_t o_rg = carve(B * refit_blocks * 45 * sizeof(float));
     cudaError_t e = cudaMalloc(&h->arena, off);
     if (e != cudaSuccess) {
         delete h;
@@ -133,6 +141,13 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     s.P_ind = (int*)(base + o_pi);
     s.points = (float*)(base + o_pts);
     s.tri_count = (int*)(base + o_tc);
+    h->refit.cand = (float*)(base + o_rc);
+    h->refit.T = (float*)(base + o_rT);
+    h->refit.flags = (int*)(base + o_rf);
+    h->refit.iters_done = (int*)(base + o_ri);
+    h->refit.mom_part = (float*)(base + o_rm);
+    h->refit.gram_part = (float*)(base + o_rg);
+    h->refit.max_blocks = refit_blocks;
     e = cudaMemset(h->arena, 0, off);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -295,6 +310,23 @@ int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t
     h->launches++;
     h->have_E = true;
     h->have_pose = false;
+    return SFMB200_OK;
+}
+
+int sfmb200_refine_e(sfmb200_t* h, int iterations) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (iterations < 0 || iterations > 64) return fail(SFMB200_ERR_ARG, "iterations must be in [0, 64]%s");
+    if (!h->have_E || !h->have_points) return fail(SFMB200_ERR_STATE, "refine_e before an essential matrix exists%s");
+    if (iterations == 0) return SFMB200_OK;
+    h->launches += launch_refit(h->s, h->refit, h->thr > 0 ? h->thr : 1e-6f, iterations, h->stream);
+    CKL();
+    h->have_pose = false;
+    return SFMB200_OK;
+}
+int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_iters) {
+    if (!h || !h_iters) return fail(SFMB200_ERR_ARG, "null argument%s");
+    CK(cudaMemcpyAsync(h_iters, h->refit.iters_done, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return SFMB200_OK;
 }
 

@@ -48,6 +48,18 @@ struct DeviceState {
     int* tri_count;     // [B] points triangulated in front of both cameras (diagnostic)
 };
 
+// Scratch of the local-optimisation (refit) stage, per pair.
+struct RefitState {
+    float* cand;        // [B][9]  next candidate E
+    float* T;           // [B][8]  Hartley similarity of the incumbent's inliers: s1,c1x,c1y,s2,c2x,c2y
+    int* flags;         // [B][4]  active, incumbent inlier count, eval ticket, solve ticket
+    int* iters_done;    // [B]     accepted refits
+    float* mom_part;    // [B][max_blocks][7]
+    float* gram_part;   // [B][max_blocks][45]
+    int max_blocks;
+};
+int launch_refit(const DeviceState& s, const RefitState& r, float thr, int iterations, cudaStream_t st);
+
 void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStream_t st);
 void launch_ingest_xy(const DeviceState& s, const float* d_px, int n, cudaStream_t st);
 void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cudaStream_t st);

@@ -117,6 +117,13 @@ class BatchedPairs:
     def adopt_best(self, H_total: int, seed: int = 0, d_idx=None):
         self.lib.call("sfmb200_adopt_best", self._h, _dptr(d_idx), H_total, C.c_uint64(seed))
 
+    def refine_e(self, iterations: int = 4) -> np.ndarray:
+        """LO-RANSAC refit on the inlier set; returns accepted refits per pair."""
+        self.lib.call("sfmb200_refine_e", self._h, iterations)
+        out = np.empty(self.pairs, np.int32)
+        self.lib.call("sfmb200_get_refit_iterations", self._h, _hptr(out))
+        return out
+
     def pose_candidates(self):
         self.lib.call("sfmb200_pose_candidates", self._h)
 

@@ -93,6 +93,13 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
 int sfmb200_best_buffer(sfmb200_t* h, uint64_t** d_best);
 int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed);
 
+/* ---- local optimisation (not in the reference; its README.md:65-69 lists it as future work,
+ * SURVEY.md 8f rank 2): up to `iterations` rounds of { normalised 8-point fit on ALL inliers of
+ * the current E through the 9x9 Jacobi eigensolve, rank-2 projection, re-score }, each accepted
+ * only if it has more inliers.  Updates E and the inlier count in place; call after estimate_e. */
+int sfmb200_refine_e(sfmb200_t* h, int iterations);
+int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_accepted /* [pairs] */);
+
 /* ---- poses: computePosecandidates (sfm.cu:238-252), choosePose (254-307) ---- */
 int sfmb200_pose_candidates(sfmb200_t* h);
 int sfmb200_choose_pose(sfmb200_t* h);

@@ -235,6 +235,63 @@ def inlier_counts(E: np.ndarray, x: np.ndarray, thr: float = 1e-6, band: float =
     return cnt, amb
 
 
+def sampson_mask_f32(E: np.ndarray, x: np.ndarray, thr: float = 1e-6) -> np.ndarray:
+    """Inlier mask with the SAME fp32 fma tree as the CUDA kernels (score.cu: sampson_d),
+    emulated with exactly-rounded fp64 products: every fp32 fma(a,b,c) is computed as
+    float32(float64(a)*float64(b) + float64(c)), which is correctly rounded because the
+    fp64 product of two fp32 numbers is exact.  (The sum can still double-round in rare
+    half-way cases; tests allow for a handful of such points.)"""
+    f32, f64 = np.float32, np.float64
+    e = E.reshape(9).astype(f32)
+    x1, y1, x2, y2 = (x[:, i].astype(f32) for i in range(4))
+
+    def fma(a, b, c):
+        return (a.astype(f64) * np.asarray(b, f64) + np.asarray(c, f64)).astype(f32)
+
+    l0 = fma(x2, e[0], fma(y2, e[1], np.full_like(x1, e[2])))
+    l1 = fma(x2, e[3], fma(y2, e[4], np.full_like(x1, e[5])))
+    l2 = fma(x2, e[6], fma(y2, e[7], np.full_like(x1, e[8])))
+    num = fma(x1, l0, fma(y1, l1, l2))
+    m0 = fma(x1, e[0], fma(y1, e[3], np.full_like(x1, e[6])))
+    m1 = fma(x1, e[1], fma(y1, e[4], np.full_like(x1, e[7])))
+    den = fma(l0, l0, fma(l1, l1, fma(m0, m0, (m1 * m1).astype(f32))))
+    d = fma(den, f32(-thr), (num * num).astype(f32))
+    return d < 0
+
+
+def refit_on_inliers(x: np.ndarray, E0: np.ndarray, thr: float = 1e-6, iterations: int = 4):
+    """LO-RANSAC local optimisation (README.md:65-69 future work),
+    restating cuda-sfm_b200/csrc/refit.cu in fp64: repeat { Hartley-normalise the
+    inliers of the incumbent E (centroid, sqrt(2)/RMS scale), null vector of the
+    Gram matrix of the design rows kron(x1h, x2h), E = T1^T Eh T2, rank-2
+    projection, accept iff strictly more inliers }.  Returns (E, count, accepted)."""
+    E = np.asarray(E0, np.float64).reshape(3, 3)
+    mask = sampson_mask_f32(E, x, thr)
+    count, accepted = int(mask.sum()), 0
+    for _ in range(iterations):
+        if count < 8:
+            break
+        xi = x[mask].astype(np.float64)
+        T = []
+        xh = np.empty_like(xi)
+        for c in (0, 2):
+            cen = xi[:, c:c + 2].mean(0)
+            var = (xi[:, c:c + 2] ** 2).sum(1).mean() - (cen ** 2).sum()
+            sc = np.sqrt(2.0 / var) if var > 0 else 1.0
+            xh[:, c:c + 2] = sc * (xi[:, c:c + 2] - cen)
+            T.append(np.array([[sc, 0, -sc * cen[0]], [0, sc, -sc * cen[1]], [0, 0, 1]]))
+        A = design_matrix(xh)
+        w, V = np.linalg.eigh(A.T @ A)
+        Eh = V[:, 0].reshape(3, 3)
+        cand = project_essential(T[0].T @ Eh @ T[1])
+        cmask = sampson_mask_f32(cand.astype(np.float32), x, thr)
+        if int(cmask.sum()) > count:
+            E, mask, count, accepted = cand, cmask, int(cmask.sum()), accepted + 1
+        else:
+            break
+    return E, count, accepted
+
+
 def argmax_first(counts: np.ndarray) -> int:
     """thrust::max_element semantics (sfm.cu:135-136): first maximum.  The
     reference then subtracts one (sfm.cu:137, SURVEY Q13: a bug); we do not."""

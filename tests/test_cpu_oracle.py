@@ -155,3 +155,31 @@ def test_reference_host_svd_contract(O, ref_lib):
         # Jacobi sweeps, hence the loose tolerance
         if sv[1] + sv[2] > 0.5:
             assert np.abs(U @ V.T - Uo @ Vo.T).max() < 2e-2
+
+
+def test_f32_mask_emulation_matches_c_port(O, oracle_c, scene_small):
+    """oracle.sampson_mask_f32 (numpy emulation of the kernels' fp32 fma tree) against
+    the C port that uses real fmaf: identical counts up to rare double-rounding ties."""
+    x = scene_small["x"]
+    idx = O.sample_indices(5, 64, len(x))
+    E32 = O.hypotheses(x, idx).reshape(-1, 9).astype(np.float32)
+    cnt32 = np.zeros(len(E32), np.int32)
+    oracle_c.oracle_counts_f32(P(E32), len(E32), P(x), len(x), C.c_float(1e-6), P(cnt32, ip))
+    mine = np.array([O.sampson_mask_f32(e, x, 1e-6).sum() for e in E32])
+    assert np.abs(mine - cnt32).max() <= 1
+
+
+def test_refit_on_inliers_improves_a_noisy_minimal_hypothesis(O):
+    K, Kinv = O.reference_K()
+    sc = O.synthetic_pair(4000, outlier_frac=0.3, noise_px=0.5, seed=12)
+    x = O.normalise_points(sc["px"], Kinv)
+    idx = O.sample_indices(9, 2000, len(x))
+    E = O.hypotheses(x, idx)
+    cnt, _ = O.inlier_counts(E.reshape(-1, 9).astype(np.float32).astype(np.float64), x, 1e-6)
+    b = int(np.argmax(cnt))
+    E1, c1, acc = O.refit_on_inliers(x, E[b].astype(np.float32), 1e-6, 6)
+    assert acc >= 1 and c1 > cnt[b]
+    t, R = sc["t"], sc["R"]
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Etrue = (tx @ R).T[None]
+    assert O.e_distance(E1[None], Etrue)[0] < O.e_distance(E[b][None], Etrue)[0]

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
+every kernel of the path at sizes that exercise partial tiles, partial TMA stages and the
+split (atomic) epilogue, in every scoring variant family member used by default."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry
+
+pkg, O = entry.load_package(), entry.load_oracle()
+K, Kinv = O.reference_K()
+for n, H, pairs, variant in ((700, 300, 1, -1), (1100, 2500, 2, -1), (520, 1030, 1, 0), (2049, 700, 1, 6), (600, 2100, 1, 3)):
+    px = np.stack([O.synthetic_pair(n, seed=3 + b)["px"] for b in range(pairs)])
+    h = pkg.BatchedPairs(K, Kinv, pairs, n, H)
+    h.set_option(2, variant)
+    out = h.run_host(px, H, 11, 1e-6)
+    h.set_option(1, 0)
+    h.set_option(3, 1)
+    out2 = h.run_host(px, H, 11, 1e-6)
+    pos = torch.empty((n, 4), device="cuda")
+    col = torch.empty((n, 4), device="cuda")
+    h.copy_to_vbo(pos, col)
+    h.get_E_candidates(); h.get_inlier_counts(); h.get_inlier_mask(); h.get_X(0)
+    lo, hi = pkg.sharding.shard_range(H, 1, 2)
+    h.estimate_e(hi - lo, 11, 1e-6, H_total=H, h_begin=lo)
+    h.adopt_best(H, 11)
+    h.synchronize()
+    print(n, H, pairs, variant, "inliers", out["inliers"].tolist(), out2["inliers"].tolist(), h.score_plan())
+    h.close()
+print("sanitize run done")
