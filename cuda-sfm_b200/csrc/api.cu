@@ -119,7 +119,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_rT = carve(B * 8 * sizeof(float));
     size_t o_rf = carve(B * 4 * sizeof(int));
     size_t o_ri = carve(B * sizeof(int));
-    size_t o_rm = carve(B * refit_blocks * 7 * sizeof(float));
+    size_t o_rm = carve(B * refit_blocks * 8 * sizeof(float));
     size_t o_rg = carve(B * refit_blocks * 45 * sizeof(float));
     cudaError_t e = cudaMalloc(&h->arena, off);
     if (e != cudaSuccess) {

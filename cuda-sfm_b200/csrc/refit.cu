@@ -4,15 +4,18 @@
 // next component after the hot path: normalised 8-point on ALL inliers through
 // the same 9x9 symmetric Jacobi eigensolve, re-score, keep if better.
 //
+// A chain of models m_0 = RANSAC winner, m_{k+1} = fit(inliers of m_k at
+// mult_k * thr) with mult_k = 4, 2, 1, 1, ... (the usual LO-RANSAC shrinking
+// threshold); the incumbent E is the chain member with the most inliers at thr.
 // One iteration = two launches per batch, no host round trip:
-//   refit_eval_kernel  : inlier mask of a candidate E (same fp32 Sampson test as
-//                        the scoring kernel), its count and the first/second
-//                        moments of the inlier set; the last CTA to finish
-//                        accepts the candidate iff it has MORE inliers than the
-//                        incumbent and derives the Hartley similarity (centroid,
-//                        sqrt(2)/RMS scale) of both images.
+//   refit_eval_kernel  : for the chain model: inlier count at thr (same fp32
+//                        Sampson test as the scoring kernel) and the first/second
+//                        moments of its inliers at the fitting threshold; the
+//                        last CTA to finish adopts the model as E iff it has MORE
+//                        inliers than the incumbent and derives the Hartley
+//                        similarity (centroid, sqrt(2)/RMS scale) of both images.
 //   refit_solve_kernel : 9x9 Gram matrix of the normalised design rows of the
-//                        incumbent's inliers (45 sums); the last CTA reduces the
+//                        chain model's fitting inliers (45 sums); the last CTA reduces the
 //                        per-CTA partials in a fixed order (fp64), runs a
 //                        warp-cooperative two-sided Jacobi (one lane per row of G
 //                        and V, shared memory), de-normalises, projects to rank 2
@@ -63,34 +66,35 @@ __device__ __forceinline__ void block_reduce(float* v, float* smem /* [warps][NV
 // moments: [0] count, [1..2] sum x1,y1, [3..4] sum x2,y2, [5] sum x1^2+y1^2, [6] sum x2^2+y2^2
 constexpr int NMOM = 7;
 
-__global__ void __launch_bounds__(REFIT_THREADS) refit_eval_kernel(DeviceState s, RefitState r, float thr, int first) {
+__global__ void __launch_bounds__(REFIT_THREADS) refit_eval_kernel(DeviceState s, RefitState r, float thr, float thr_fit, int first) {
     const int b = blockIdx.y;
-    __shared__ float red[(REFIT_THREADS / 32) * NMOM];
+    __shared__ float red[(REFIT_THREADS / 32) * (NMOM + 1)];
     __shared__ float sE[9];
     __shared__ int s_last;
     int* flags = r.flags + (size_t)b * 4;             // [0] active, [1] incumbent count, [2] eval ticket, [3] solve ticket
-    if (!first && flags[0] == 0) return;              // already converged
-    const float* cand = first ? s.E + (size_t)b * 9 : r.cand + (size_t)b * 9;
+    if (!first && flags[0] == 0) return;              // chain ended (fewer than 8 fitting inliers)
+    const float* cand = r.cand + (size_t)b * 9;
     if (threadIdx.x < 9) sE[threadIdx.x] = cand[threadIdx.x];
     __syncthreads();
-    float m[NMOM];
+    float m[NMOM + 1];                                // [NMOM] = count at thr (acceptance)
 #pragma unroll
-    for (int i = 0; i < NMOM; i++) m[i] = 0.0f;
+    for (int i = 0; i <= NMOM; i++) m[i] = 0.0f;
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = blockIdx.x * REFIT_THREADS + threadIdx.x; i < s.n; i += gridDim.x * REFIT_THREADS) {
         float4 p = corr[i];
-        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f) {
+        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f) m[NMOM] += 1.0f;
+        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
             m[0] += 1.0f;
             m[1] += p.x; m[2] += p.y; m[3] += p.z; m[4] += p.w;
             m[5] += fmaf(p.x, p.x, p.y * p.y);
             m[6] += fmaf(p.z, p.z, p.w * p.w);
         }
     }
-    block_reduce<NMOM>(m, red);
-    float* part = r.mom_part + ((size_t)b * gridDim.x + blockIdx.x) * NMOM;
+    block_reduce<NMOM + 1>(m, red);
+    float* part = r.mom_part + ((size_t)b * gridDim.x + blockIdx.x) * (NMOM + 1);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < NMOM; i++) part[i] = m[i];
+        for (int i = 0; i <= NMOM; i++) part[i] = m[i];
         __threadfence();
         s_last = (atomicAdd(&flags[2], 1) == (int)gridDim.x - 1);
     }
@@ -98,37 +102,36 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_eval_kernel(DeviceState s
     if (!s_last || threadIdx.x != 0) return;
     __threadfence();
     flags[2] = 0;                                      // ticket reset for the next launch
-    double tot[NMOM];
-    for (int i = 0; i < NMOM; i++) tot[i] = 0.0;
-    const float* all = r.mom_part + (size_t)b * gridDim.x * NMOM;
+    double tot[NMOM + 1];
+    for (int i = 0; i <= NMOM; i++) tot[i] = 0.0;
+    const float* all = r.mom_part + (size_t)b * gridDim.x * (NMOM + 1);
     for (unsigned k = 0; k < gridDim.x; k++)
-        for (int i = 0; i < NMOM; i++) tot[i] += (double)__ldcg(all + k * NMOM + i);
-    int count = (int)(tot[0] + 0.5);
-    bool accept = first || count > flags[1];
-    if (accept && count >= 8) {
-        flags[0] = 1;
+        for (int i = 0; i <= NMOM; i++) tot[i] += (double)__ldcg(all + k * (NMOM + 1) + i);
+    const int count = (int)(tot[NMOM] + 0.5);          // inliers at thr: the acceptance score
+    if (count > flags[1]) {                            // strictly better than the incumbent (first call: always)
         flags[1] = count;
-        if (!first) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) s.E[(size_t)b * 9 + i] = sE[i];
-            s.best_count[b] = count;
-        }
-        // Hartley similarity from the moments: centroid, scale = sqrt(2) / RMS distance
-        double n = tot[0];
+        for (int i = 0; i < 9; i++) s.E[(size_t)b * 9 + i] = sE[i];
+        s.best_count[b] = count;
+        if (!first) r.iters_done[b] += 1;
+    }
+    // Hartley similarity of the fitting inliers from their moments: centroid, scale = sqrt(2) / RMS distance
+    const double n = tot[0];
+    if (n >= 8.0) {
         double c1x = tot[1] / n, c1y = tot[2] / n, c2x = tot[3] / n, c2y = tot[4] / n;
         double v1 = tot[5] / n - (c1x * c1x + c1y * c1y), v2 = tot[6] / n - (c2x * c2x + c2y * c2y);
         float* T = r.T + (size_t)b * 8;
         T[0] = (float)(v1 > 0 ? sqrt(2.0 / v1) : 1.0); T[1] = (float)c1x; T[2] = (float)c1y;
         T[3] = (float)(v2 > 0 ? sqrt(2.0 / v2) : 1.0); T[4] = (float)c2x; T[5] = (float)c2y;
+        flags[0] = 1;
     } else {
-        flags[0] = 0;                                  // candidate rejected: keep the incumbent, stop iterating
+        flags[0] = 0;
     }
-    r.iters_done[b] += (accept && !first) ? 1 : 0;
 }
 
 constexpr int NG = 45;
 
-__global__ void __launch_bounds__(REFIT_THREADS) refit_solve_kernel(DeviceState s, RefitState r, float thr) {
+__global__ void __launch_bounds__(REFIT_THREADS) refit_solve_kernel(DeviceState s, RefitState r, float thr_fit) {
     const int b = blockIdx.y;
     __shared__ float red[(REFIT_THREADS / 32) * NG];
     __shared__ float sE[9], sT[6];
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_solve_kernel(DeviceState 
     __shared__ int s_last;
     int* flags = r.flags + (size_t)b * 4;
     if (flags[0] == 0) return;
-    if (threadIdx.x < 9) sE[threadIdx.x] = s.E[(size_t)b * 9 + threadIdx.x];
+    if (threadIdx.x < 9) sE[threadIdx.x] = r.cand[(size_t)b * 9 + threadIdx.x];
     if (threadIdx.x < 6) sT[threadIdx.x] = r.T[(size_t)b * 8 + threadIdx.x];
     __syncthreads();
     float g[NG];
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_solve_kernel(DeviceState 
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = blockIdx.x * REFIT_THREADS + threadIdx.x; i < s.n; i += gridDim.x * REFIT_THREADS) {
         float4 p = corr[i];
-        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f) {
+        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
             float x1 = sT[0] * (p.x - sT[1]), y1 = sT[0] * (p.y - sT[2]);
             float x2 = sT[3] * (p.z - sT[4]), y2 = sT[3] * (p.w - sT[5]);
             float a[9] = {x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, 1.0f};
@@ -232,28 +235,32 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_solve_kernel(DeviceState 
     for (int i = 0; i < 9; i++) r.cand[(size_t)b * 9 + i] = finite ? E[i] : 0.0f;
 }
 
-__global__ void refit_reset_kernel(RefitState r, int B) {
+__global__ void refit_reset_kernel(DeviceState s, RefitState r) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    if (b >= s.B) return;
     r.flags[(size_t)b * 4 + 0] = 0;
     r.flags[(size_t)b * 4 + 1] = -1;
     r.flags[(size_t)b * 4 + 2] = 0;
     r.flags[(size_t)b * 4 + 3] = 0;
     r.iters_done[b] = 0;
+    for (int i = 0; i < 9; i++) r.cand[(size_t)b * 9 + i] = s.E[(size_t)b * 9 + i];   // chain starts at the RANSAC winner
 }
+
+// fitting-threshold multiplier of chain step k: 4, 2, 1, 1, ...
+static float refit_mult(int k) { return k == 0 ? 4.0f : (k == 1 ? 2.0f : 1.0f); }
 
 int launch_refit(const DeviceState& s, const RefitState& r, float thr, int iterations, cudaStream_t st) {
     int blocks = (s.n + REFIT_THREADS * 8 - 1) / (REFIT_THREADS * 8);
     if (blocks < 1) blocks = 1;
     if (blocks > r.max_blocks) blocks = r.max_blocks;
     dim3 grid(blocks, s.B);
-    refit_reset_kernel<<<(s.B + 127) / 128, 128, 0, st>>>(r, s.B);
+    refit_reset_kernel<<<(s.B + 127) / 128, 128, 0, st>>>(s, r);
     int launches = 1;
-    refit_eval_kernel<<<grid, REFIT_THREADS, 0, st>>>(s, r, thr, 1);
+    refit_eval_kernel<<<grid, REFIT_THREADS, 0, st>>>(s, r, thr, thr * refit_mult(0), 1);
     launches++;
     for (int it = 0; it < iterations; it++) {
-        refit_solve_kernel<<<grid, REFIT_THREADS, 0, st>>>(s, r, thr);
-        refit_eval_kernel<<<grid, REFIT_THREADS, 0, st>>>(s, r, thr, 0);
+        refit_solve_kernel<<<grid, REFIT_THREADS, 0, st>>>(s, r, thr * refit_mult(it));
+        refit_eval_kernel<<<grid, REFIT_THREADS, 0, st>>>(s, r, thr, thr * refit_mult(it + 1), 0);
         launches += 2;
     }
     return launches;

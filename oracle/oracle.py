@@ -261,17 +261,20 @@ def sampson_mask_f32(E: np.ndarray, x: np.ndarray, thr: float = 1e-6) -> np.ndar
 
 def refit_on_inliers(x: np.ndarray, E0: np.ndarray, thr: float = 1e-6, iterations: int = 4):
     """LO-RANSAC local optimisation (README.md:65-69 future work),
-    restating cuda-sfm_b200/csrc/refit.cu in fp64: repeat { Hartley-normalise the
-    inliers of the incumbent E (centroid, sqrt(2)/RMS scale), null vector of the
-    Gram matrix of the design rows kron(x1h, x2h), E = T1^T Eh T2, rank-2
-    projection, accept iff strictly more inliers }.  Returns (E, count, accepted)."""
-    E = np.asarray(E0, np.float64).reshape(3, 3)
-    mask = sampson_mask_f32(E, x, thr)
-    count, accepted = int(mask.sum()), 0
-    for _ in range(iterations):
-        if count < 8:
+    restating cuda-sfm_b200/csrc/refit.cu in fp64.  A chain of models m_0 = E0,
+    m_{k+1} = fit(inliers of m_k at mult_k * thr), mult = 4, 2, 1, 1, ...; fit =
+    Hartley-normalise (centroid, sqrt(2)/RMS scale), null vector of the Gram matrix
+    of the design rows kron(x1h, x2h), E = T1^T Eh T2, rank-2 projection.  The
+    incumbent is the chain member with strictly the most inliers at thr.
+    Returns (E, count, accepted)."""
+    mult = lambda k: 4.0 if k == 0 else (2.0 if k == 1 else 1.0)
+    model = np.asarray(E0, np.float64).reshape(3, 3)
+    E, count, accepted = model, int(sampson_mask_f32(model, x, thr).sum()), 0
+    for k in range(iterations):
+        fit_mask = sampson_mask_f32(model, x, np.float32(thr) * np.float32(mult(k)))
+        if int(fit_mask.sum()) < 8:
             break
-        xi = x[mask].astype(np.float64)
+        xi = x[fit_mask].astype(np.float64)
         T = []
         xh = np.empty_like(xi)
         for c in (0, 2):
@@ -282,13 +285,10 @@ def refit_on_inliers(x: np.ndarray, E0: np.ndarray, thr: float = 1e-6, iteration
             T.append(np.array([[sc, 0, -sc * cen[0]], [0, sc, -sc * cen[1]], [0, 0, 1]]))
         A = design_matrix(xh)
         w, V = np.linalg.eigh(A.T @ A)
-        Eh = V[:, 0].reshape(3, 3)
-        cand = project_essential(T[0].T @ Eh @ T[1])
-        cmask = sampson_mask_f32(cand.astype(np.float32), x, thr)
-        if int(cmask.sum()) > count:
-            E, mask, count, accepted = cand, cmask, int(cmask.sum()), accepted + 1
-        else:
-            break
+        model = project_essential(T[0].T @ V[:, 0].reshape(3, 3) @ T[1])
+        c = int(sampson_mask_f32(model.astype(np.float32), x, thr).sum())
+        if c > count:
+            E, count, accepted = model, c, accepted + 1
     return E, count, accepted
 
 
