@@ -68,6 +68,7 @@ SIGNATURES = {
     "sfmb200_fma_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "sfmb200_host_svd3": (None, [_f, _f, _f, _f]),
     "sfmb200_host_solve_hypothesis": (None, [_f, _f]),
+    "sfmb200_host_solve_hypothesis_projector": (None, [_f, _f]),
     "sfmb200_host_null4": (None, [_f, _f]),
     "sfmb200_host_null4_fast": (C.c_int, [_f, _f]),
     "sfmb200_host_inv4": (C.c_int, [_f, _f]),

@@ -39,6 +39,7 @@ struct sfmb200_handle {
     int compat;
     int score_variant;
     int tri_inliers_only;
+    int hyp_solver;
     // state of the last estimate
     int H;            // hypotheses in the local slice
     int h_begin;
@@ -187,6 +188,10 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
             h->score_variant = value;
             break;
         case SFMB200_OPT_TRI_INLIERS_ONLY: h->tri_inliers_only = value ? 1 : 0; break;
+        case SFMB200_OPT_HYP_SOLVER:
+            if (value < 0 || value > 1) return fail(SFMB200_ERR_ARG, "hypothesis solver must be 0 (Jacobi) or 1 (Cholesky projector)%s");
+            h->hyp_solver = value;
+            break;
         case SFMB200_OPT_PROFILE:
             if (value && !h->prof_ev) {
                 h->prof_ev = new cudaEvent_t[PROF_RING][8];
@@ -278,7 +283,7 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     h->h_begin = h_begin;
     h->thr = thr;
     h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
-    launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->stream);
+    launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->hyp_solver, h->stream);
     prof_mark(h, 2);
     CKL();
     launch_score(h->s, h->plan, H, h_begin, thr, h->stream);
@@ -305,7 +310,7 @@ int sfmb200_best_buffer(sfmb200_t* h, uint64_t** d_best) {
 int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed) {
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_points) return fail(SFMB200_ERR_STATE, "adopt_best before set_points%s");
-    launch_regen_best(h->s, d_idx, (long long)H_total * 8, seed, h->stream);
+    launch_regen_best(h->s, d_idx, (long long)H_total * 8, seed, h->hyp_solver, h->stream);
     CKL();
     h->launches++;
     h->have_E = true;
@@ -370,7 +375,7 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
     h->h_begin = 0;
     h->thr = thr;
     h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
-    launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->stream);
+    launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->hyp_solver, h->stream);
     prof_mark(h, 2);
     CKL();
     launch_score(h->s, h->plan, H, 0, thr, h->stream);

@@ -17,6 +17,12 @@ void sfmb200_host_solve_hypothesis(const float pts[32], float E[9]) {
     solve_hypothesis<0>(c, E);
 }
 
+void sfmb200_host_solve_hypothesis_projector(const float pts[32], float E[9]) {
+    Corr c[8];
+    for (int i = 0; i < 8; i++) c[i] = Corr{pts[4 * i], pts[4 * i + 1], pts[4 * i + 2], pts[4 * i + 3]};
+    solve_hypothesis_projector(c, E);
+}
+
 void sfmb200_host_null4(const float A[16], float x[4]) { null4<5>(A, x); }
 
 int sfmb200_host_null4_fast(const float A[16], float x[4]) { return null4_inverse_iteration<8>(A, x) ? 0 : 1; }

@@ -210,6 +210,164 @@ SFM_HD void solve_hypothesis(const Corr* pts, float* E) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Alternative null-vector solve (SFMB200_OPT_HYP_SOLVER = 1): orthogonal
+// projector onto null(A) through ONE 8x8 Cholesky factorisation,
+//     e = (I - A^T (A A^T)^-1 A) r,
+// ~8x fewer instructions than the 9x9 Jacobi eigensolve.  K = A A^T needs no
+// design rows at all: <kron(p,q), kron(p',q')> = <p,p'><q,q'>.  The start
+// vector r = e_i is the basis vector with the largest null-space component
+// (diag of the projector, so |<r, n>| >= 1/3), and two re-projections against
+// the design rows bring the error down to eps*cond like the Jacobi path's
+// refinement.  Same pre/post-processing as solve_hypothesis().
+// ---------------------------------------------------------------------------
+struct Chol8 {
+    float l[8][8];      // lower triangle; the diagonal holds 1 / L_ii
+    bool ok;
+};
+SFM_HD void chol8_factor(float k[8][8], Chol8& c) {
+    c.ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        float d = k[j][j];
+#pragma unroll
+        for (int m = 0; m < j; m++) d = fmaf(-c.l[j][m], c.l[j][m], d);
+        c.ok = c.ok && (d > 0.0f);
+        float inv = 1.0f / sqrtf(fmaxf(d, 1e-30f));
+        c.l[j][j] = inv;
+#pragma unroll
+        for (int i = j + 1; i < 8; i++) {
+            float v = k[i][j];
+#pragma unroll
+            for (int m = 0; m < j; m++) v = fmaf(-c.l[i][m], c.l[j][m], v);
+            c.l[i][j] = v * inv;
+        }
+    }
+}
+// y <- K^-1 y  (forward + backward substitution)
+SFM_HD void chol8_solve(const Chol8& c, float* y) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float v = y[i];
+#pragma unroll
+        for (int m = 0; m < i; m++) v = fmaf(-c.l[i][m], y[m], v);
+        y[i] = v * c.l[i][i];
+    }
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        float v = y[i];
+#pragma unroll
+        for (int m = i + 1; m < 8; m++) v = fmaf(-c.l[m][i], y[m], v);
+        y[i] = v * c.l[i][i];
+    }
+}
+// |L^-1 y|^2 = y^T K^-1 y (forward substitution only)
+SFM_HD float chol8_quad(const Chol8& c, const float* y0) {
+    float y[8], q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float v = y0[i];
+#pragma unroll
+        for (int m = 0; m < i; m++) v = fmaf(-c.l[i][m], y[m], v);
+        y[i] = v * c.l[i][i];
+        q = fmaf(y[i], y[i], q);
+    }
+    return q;
+}
+
+SFM_HD void solve_hypothesis_projector(const Corr* pts, float* E) {
+    float x1[8], y1[8], x2[8], y2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x1[i] = pts[i].x1; y1[i] = pts[i].y1; x2[i] = pts[i].x2; y2[i] = pts[i].y2; }
+    float s1, c1x, c1y, s2, c2x, c2y;
+    hartley(x1, y1, s1, c1x, c1y);
+    hartley(x2, y2, s2, c2x, c2y);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        x1[i] = s1 * (x1[i] - c1x); y1[i] = s1 * (y1[i] - c1y);
+        x2[i] = s2 * (x2[i] - c2x); y2[i] = s2 * (y2[i] - c2y);
+    }
+    // K = A A^T through the Kronecker identity
+    float k[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            float a = fmaf(x1[i], x1[j], fmaf(y1[i], y1[j], 1.0f));
+            float b = fmaf(x2[i], x2[j], fmaf(y2[i], y2[j], 1.0f));
+            k[i][j] = a * b;
+        }
+    Chol8 ch;
+    chol8_factor(k, ch);
+    // diag of the projector: 1 - a_c^T K^-1 a_c for every column c of A; pick the largest
+    int best = 0;
+    float bestv = -1.0f;
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+        float col[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            float a[9];
+            design_row(x1[r], y1[r], x2[r], y2[r], a);
+            col[r] = a[c];
+        }
+        float v = 1.0f - chol8_quad(ch, col);
+        if (v > bestv) { bestv = v; best = c; }
+    }
+    float e[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) e[c] = (c == best) ? 1.0f : 0.0f;
+    // e <- e - A^T K^-1 (A e), three times (projection + two re-projections)
+#pragma unroll 1
+    for (int it = 0; it < 3; it++) {
+        float y[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            float a[9];
+            design_row(x1[r], y1[r], x2[r], y2[r], a);
+            float res = a[0] * e[0];
+#pragma unroll
+            for (int c = 1; c < 9; c++) res = fmaf(a[c], e[c], res);
+            y[r] = res;
+        }
+        chol8_solve(ch, y);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            float a[9];
+            design_row(x1[r], y1[r], x2[r], y2[r], a);
+#pragma unroll
+            for (int c = 0; c < 9; c++) e[c] = fmaf(-a[c], y[r], e[c]);
+        }
+        float n2 = e[0] * e[0];
+#pragma unroll
+        for (int c = 1; c < 9; c++) n2 = fmaf(e[c], e[c], n2);
+        float inv = 1.0f / sqrtf(n2);
+#pragma unroll
+        for (int c = 0; c < 9; c++) e[c] *= inv;
+    }
+    float M[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        M[3 * i + 0] = e[3 * i + 0] * s2;
+        M[3 * i + 1] = e[3 * i + 1] * s2;
+        M[3 * i + 2] = fmaf(-s2 * c2x, e[3 * i + 0], fmaf(-s2 * c2y, e[3 * i + 1], e[3 * i + 2]));
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        E[0 + j] = s1 * M[0 + j];
+        E[3 + j] = s1 * M[3 + j];
+        E[6 + j] = fmaf(-s1 * c1x, M[0 + j], fmaf(-s1 * c1y, M[3 + j], M[6 + j]));
+    }
+    project_essential(E);
+    bool finite = ch.ok;
+#pragma unroll
+    for (int i = 0; i < 9; i++) finite = finite && (fabsf(E[i]) <= 3.0e38f);
+    if (!finite) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) E[i] = 0.0f;
+    }
+}
+
 // Counter-based sample-index generator shared (bit-exactly) with the oracle
 // (oracle/oracle.py: sample_indices).  Hypothesis h of a pair draws 8 distinct
 // indices in [0, n): splitmix64 of (seed, h, draw counter), mapped with a

@@ -5,9 +5,6 @@
 // Roofline: FP32 pipe.  ~5 sweeps x 36 rotations x ~80 FP32 instructions plus
 // Gram build / refinement / 3x3 SVD ~= 17 k FP32 instructions per hypothesis;
 // memory traffic is 8 gathered 16-byte correspondences (L2 hits) in and 36 B out.
-#include <stdio.h>
-#include <stdlib.h>
-
 #include "hyp_solver.cuh"
 #include "internal.cuh"
 
@@ -43,7 +40,7 @@ __device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int
     return ok;
 }
 
-template <int THREADS, int MINB, int SYNC>
+template <int THREADS, int MINB, int SYNC, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB)
 hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride, int H, int h_offset,
               unsigned long long seed) {
@@ -60,7 +57,8 @@ hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pa
     float E[9];
     bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b,
                           (long long)h_offset + (live ? j : 0), pts);
-    solve_hypothesis<SYNC>(pts, E);
+    if (SOLVER == 0) solve_hypothesis<SYNC>(pts, E);
+    else solve_hypothesis_projector(pts, E);
     if (!live) return;
     float* out = s.Ecand + (size_t)b * 9 * s.h_stride + j;
 #pragma unroll
@@ -68,45 +66,23 @@ hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pa
     s.counts[(size_t)b * s.h_stride + j] = 0;
 }
 
-// Variant for experiments: SFMB200_HYPGEN=<threads>,<minb>,<sync>  (default 128,2,0)
+// solver 0: 9x9 Jacobi eigensolve (255 registers, 2 CTAs of 128 threads per SM);
+// solver 1: 8x8 Cholesky projector (see hyp_solver.cuh), 4 CTAs of 128 threads per SM.
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
-                   unsigned long long seed, cudaStream_t st) {
-    static int cfg = [] {
-        const char* e = getenv("SFMB200_HYPGEN");
-        int t = 128, m = 2, y = 0;
-        if (e) sscanf(e, "%d,%d,%d", &t, &m, &y);
-        return t * 100 + m * 10 + y;
-    }();
+                   unsigned long long seed, int solver, cudaStream_t st) {
     int need = H > s.tiles_max ? H : s.tiles_max;
-#define SFM_HG(T, M, Y)                                                                              \
-    case (T * 100 + M * 10 + Y): {                                                                   \
-        dim3 grid((need + T - 1) / T, s.B);                                                          \
-        hypgen_kernel<T, M, Y><<<grid, T, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);    \
-        break;                                                                                       \
-    }
-    switch (cfg) {
-        SFM_HG(128, 2, 0)
-        SFM_HG(128, 2, 1)
-        SFM_HG(128, 2, 2)
-        SFM_HG(256, 1, 0)
-        SFM_HG(256, 1, 1)
-        SFM_HG(256, 1, 2)
-        SFM_HG(64, 4, 0)
-        SFM_HG(64, 4, 1)
-        SFM_HG(64, 4, 2)
-        default: {
-            dim3 grid((need + 127) / 128, s.B);
-            hypgen_kernel<128, 2, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
-        }
-    }
-#undef SFM_HG
+    dim3 grid((need + 127) / 128, s.B);
+    if (solver == 0)
+        hypgen_kernel<128, 2, 0, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+    else
+        hypgen_kernel<128, 4, 0, 1><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
 }
 
 // Multi-GPU single-pair case: after the (count, index) all-reduce every rank
 // regenerates the winning hypothesis from its global index instead of
 // broadcasting 36 bytes.  best[] already holds the reduced value.
 __global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride,
-                                  unsigned long long seed) {
+                                  unsigned long long seed, int solver) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= s.B) return;
     unsigned long long packed = s.best[b];
@@ -117,7 +93,8 @@ __global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_i
     Corr pts[8];
     float E[9];
     bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b, (long long)hg, pts);
-    solve_hypothesis<0>(pts, E);
+    if (solver == 0) solve_hypothesis<0>(pts, E);      // same code path as hypgen_kernel: bit-identical E
+    else solve_hypothesis_projector(pts, E);
 #pragma unroll
     for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = ok ? E[k] : 0.0f;
     s.best_idx[b] = (int)hg;
@@ -125,8 +102,8 @@ __global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_i
 }
 
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, unsigned long long seed,
-                       cudaStream_t st) {
-    regen_best_kernel<<<(s.B + 31) / 32, 32, 0, st>>>(s, d_idx, idx_pair_stride, seed);
+                       int solver, cudaStream_t st) {
+    regen_best_kernel<<<(s.B + 31) / 32, 32, 0, st>>>(s, d_idx, idx_pair_stride, seed, solver);
 }
 
 }  // namespace sfmb200

@@ -64,13 +64,13 @@ void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStr
 void launch_ingest_xy(const DeviceState& s, const float* d_px, int n, cudaStream_t st);
 void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cudaStream_t st);
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
-                   unsigned long long seed, cudaStream_t st);
+                   unsigned long long seed, int solver, cudaStream_t st);
 ScorePlan make_score_plan(int B, int n, int H, int variant_override);
 int score_num_variants();
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
 void launch_select(const DeviceState& s, int h_offset, cudaStream_t st);
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride,
-                       unsigned long long seed, cudaStream_t st);
+                       unsigned long long seed, int solver, cudaStream_t st);
 void launch_pose_candidates(const DeviceState& s, int compat, cudaStream_t st);
 void launch_select_pose_choose(const DeviceState& s, int h_offset, int compat, cudaStream_t st);
 void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_t st);

@@ -49,6 +49,9 @@ typedef enum {
     SFMB200_OPT_SCORE_VARIANT = 2, /* -1 auto (default); >= 0: index into the scoring kernel family
                                       (0 scalar FFMA 2 hyp/thread, 1 packed FFMA2 4 hyp/thread, ... see score.cu) */
     SFMB200_OPT_TRI_INLIERS_ONLY = 3, /* 0 (default, reference: all N points, sfm.cu:309-336); 1: inliers of E only */
+    SFMB200_OPT_HYP_SOLVER = 5,    /* null vector of the 8x9 design matrix: 0 (default) register-resident 9x9 Jacobi
+                                      eigensolve + design-row refinement; 1: 8x8 Cholesky projector (~8x fewer
+                                      instructions, same accuracy; see hyp_solver.cuh) */
     SFMB200_OPT_PROFILE = 4        /* 1: record CUDA events between the stages of run_device / run_host
                                       (the reference's unused PerformanceTimer, common.h:48-132, done per stage) */
 } sfmb200_option;
@@ -149,7 +152,8 @@ int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms);
 
 /* ---- host-side small-matrix entry points (no GPU): svd.h facade + CPU tests ---- */
 void sfmb200_host_svd3(const float a[9], float u[9], float s[9], float v[9]);
-void sfmb200_host_solve_hypothesis(const float pts[32], float E[9]);
+void sfmb200_host_solve_hypothesis(const float pts[32], float E[9]);            /* 9x9 Jacobi eigensolve */
+void sfmb200_host_solve_hypothesis_projector(const float pts[32], float E[9]);  /* 8x8 Cholesky projector */
 void sfmb200_host_null4(const float A[16], float x[4]);
 /* inverse-iteration fast path of the same null vector; returns 1 when it did not converge (caller falls back) */
 int sfmb200_host_null4_fast(const float A[16], float x[4]);

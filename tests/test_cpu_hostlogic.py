@@ -60,13 +60,15 @@ def test_host_sample_indices_match_oracle(lib, O):
         assert list(out) == O.sample_indices_one(seed, h, n)
 
 
-def test_host_hypothesis_solver_matches_fp64_oracle(lib, O, scene_small):
+@pytest.mark.parametrize("entry_point", ["sfmb200_host_solve_hypothesis", "sfmb200_host_solve_hypothesis_projector"])
+def test_host_hypothesis_solver_matches_fp64_oracle(lib, O, scene_small, entry_point):
+    """Both null-vector solvers (9x9 Jacobi eigensolve, 8x8 Cholesky projector)."""
     x = scene_small["x"]
     H = 1500
     idx = O.sample_indices(1237, H, len(x))
     E64 = O.hypotheses(x, idx)
     E32 = np.zeros((H, 9), np.float32)
-    solve = lib.raw("sfmb200_host_solve_hypothesis")
+    solve = lib.raw(entry_point)
     for h in range(H):
         p = np.ascontiguousarray(x[idx[h]], dtype=np.float32)
         solve(P(p), P(E32[h]))
@@ -82,9 +84,11 @@ def test_host_hypothesis_degenerate_sample_is_zero(lib):
     # eight identical points (dyadic, so the centroid is exact): Hartley scale is
     # 1/0 -> non-finite -> the solver must return the all-zero matrix (count 0)
     p = np.tile(np.array([[0.5, 0.25, 0.125, 0.75]], np.float32), (8, 1))
+    for name in ("sfmb200_host_solve_hypothesis", "sfmb200_host_solve_hypothesis_projector"):
+        E = np.ones(9, np.float32)
+        lib.raw(name)(P(p), P(E))
+        assert np.all(E == 0)
     E = np.ones(9, np.float32)
-    lib.raw("sfmb200_host_solve_hypothesis")(P(p), P(E))
-    assert np.all(E == 0)
     # rank-deficient but finite samples stay finite (never NaN into the scorer)
     p = np.tile(np.array([[0.1, 0.2, 0.3, 0.4]], np.float32), (8, 1))
     p[:, 0] += np.arange(8, dtype=np.float32) * 1e-3

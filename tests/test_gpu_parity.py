@@ -86,13 +86,14 @@ def test_ingest_matches_oracle(pkg, O, torch_cuda, scene_small):
     assert np.array_equal(ipair.get_X(1).cpu().numpy(), X1)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_estimate_e_against_oracle(pkg, O, oracle_c, torch_cuda, scene_small, variant):
+@pytest.mark.parametrize("variant,solver", [(0, 0), (1, 0), (4, 0), (4, 1), (9, 1)])
+def test_estimate_e_against_oracle(pkg, O, oracle_c, torch_cuda, scene_small, variant, solver):
     torch = torch_cuda
     x, n = scene_small["x"], len(scene_small["x"])
     H, seed = 3000, 1237          # H not a multiple of any tile size
     h = make_handle(pkg, scene_small, H)
     h.set_option(2, variant)
+    h.set_option(5, solver)       # 0: 9x9 Jacobi eigensolve, 1: 8x8 Cholesky projector
     h.set_points_xy(torch.from_numpy(scene_small["px"]).cuda())
     h.estimate_e(H, seed, THR)
     Eg = h.get_E_candidates().cpu().numpy()
@@ -190,6 +191,15 @@ def test_hypothesis_slices_reproduce_the_full_run(pkg, torch_cuda, scene_small):
     full = make_handle(pkg, scene_small, H)
     full.set_points_xy(dpx)
     full.estimate_e(H, seed, THR)
+    # the other solver reproduces itself through adopt_best as well
+    alt = make_handle(pkg, scene_small, H)
+    alt.set_option(5, 1)
+    alt.set_points_xy(dpx)
+    alt.estimate_e(H, seed, THR)
+    E_alt, best_alt = alt.get_E().copy(), alt.get_best()
+    alt.adopt_best(H, seed)
+    assert np.array_equal(alt.get_E(), E_alt) and alt.get_best()[0][0] == best_alt[0][0]
+    alt.close()
     Ef, cf = full.get_E_candidates().cpu().numpy(), full.get_inlier_counts().cpu().numpy()
     keys = []
     for world in (2, 3):

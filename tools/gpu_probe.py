@@ -33,12 +33,13 @@ def probe():
                  lane_fma_per_clk_per_sm_at_1965=fmas.value / (ms.value * 1e-3) / 148 / 1.965e9)
 
 
-def stages(n, H, variant, pairs=1, reps=10, label=""):
+def stages(n, H, variant, pairs=1, reps=10, label="", solver=0):
     scenes = [O.synthetic_pair(n, seed=1234 + b) for b in range(min(pairs, 4))]
     px = np.stack([scenes[b % len(scenes)]["px"] for b in range(pairs)])
     d_px = torch.from_numpy(px).cuda()
     h = pkg.BatchedPairs(K, Kinv, pairs, n, H)
     h.set_option(2, variant)
+    h.set_option(5, solver)
     h.set_option(4, 1)
     for _ in range(3):
         h.run_device(d_px, H, 1237, THR, n=n)
@@ -48,7 +49,7 @@ def stages(n, H, variant, pairs=1, reps=10, label=""):
     st = h.stage_times()
     m = st.mean(axis=0)
     evals = pairs * n * H
-    emit(what="stages", label=label, n=n, H=H, pairs=pairs, variant=variant, plan=h.score_plan(),
+    emit(what="stages", label=label, n=n, H=H, pairs=pairs, variant=variant, solver=solver, plan=h.score_plan(),
          stage_ms=dict(zip(h.STAGES, [float(v) for v in m])), stage_min_ms=dict(zip(h.STAGES, [float(v) for v in st.min(axis=0)])),
          score_evals_per_s=evals / (m[2] * 1e-3), score_tflops_34=34 * evals / (m[2] * 1e-3) / 1e12,
          hyp_per_s=pairs * H / (m[1] * 1e-3), tri_points_per_s=pairs * n / (m[6] * 1e-3), tri_gbs=32 * pairs * n / (m[6] * 1e-3) / 1e9,
@@ -61,8 +62,9 @@ if __name__ == "__main__":
     emit(what="device", name=torch.cuda.get_device_name(0), sms=torch.cuda.get_device_properties(0).multi_processor_count,
          hypgen_minb=os.environ.get("SFMB200_HYPGEN_MINB", "2"))
     if which == "hypgen":
-        stages(10_000, 65_536, -1, label="config2")
-        stages(4096, 4096, -1, pairs=256, reps=3, label="config4 slice: 256 pairs")
+        for solver in (0, 1):
+            stages(10_000, 65_536, -1, label="config2", solver=solver)
+            stages(4096, 4096, -1, pairs=256, reps=3, label="config4 slice: 256 pairs", solver=solver)
         sys.exit(0)
     if which == "score":
         for v in (4, 16, 17, 18, 19):
