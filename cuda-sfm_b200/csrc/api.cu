@@ -158,6 +158,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     }
     h->own_stream = true;
     h->compat = 1;
+    h->hyp_solver = 1;     // Cholesky projector: same parity as the Jacobi eigensolve, 3.5-4.4x faster (profiles/)
     h->score_variant = -1;
     h->tri_inliers_only = 0;
     *out = h;
