@@ -115,6 +115,13 @@ public:
         check(sfmb200_set_points_xy(h_, d_pixels_u1v1u2v2, n), "fillXU");
         num_points = n;
     }
+    // keep only matches with score > minScore && ambiguity < maxAmbiguity (CudaSift's FindHomography test);
+    // returns the number kept
+    int fillXU(SiftPoint* data, float minScore, float maxAmbiguity, int32_t* d_kept_index = nullptr) {
+        int32_t kept = 0;
+        check(sfmb200_set_points_sift_filtered(h_, data, num_points, minScore, maxAmbiguity, d_kept_index, &kept), "fillXU");
+        return kept;
+    }
     void setCompat(bool reference_semantics) { check(sfmb200_set_option(h_, SFMB200_OPT_COMPAT, reference_semantics), "setCompat"); }
     void getE(float E[9]) { check(sfmb200_get_E(h_, E), "getE"); }
     void getPoses(float P[64]) { check(sfmb200_get_poses(h_, P), "getPoses"); }

@@ -35,6 +35,7 @@ SIGNATURES = {
     "sfmb200_set_stream": (C.c_int, [_vp, _vp]),
     "sfmb200_synchronize": (C.c_int, [_vp]),
     "sfmb200_set_points_sift": (C.c_int, [_vp, _vp, C.c_int]),
+    "sfmb200_set_points_sift_filtered": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, _vp, C.POINTER(C.c_int32)]),
     "sfmb200_set_points_xy": (C.c_int, [_vp, _vp, C.c_int]),
     "sfmb200_set_points_xy_host": (C.c_int, [_vp, _vp, C.c_int]),
     "sfmb200_set_points_normalised": (C.c_int, [_vp, _vp, C.c_int]),

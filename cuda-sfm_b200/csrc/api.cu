@@ -47,6 +47,7 @@ struct sfmb200_handle {
     bool have_points, have_E, have_candidates, have_pose;
     ScorePlan plan;
     int64_t launches;
+    int* filter_scratch;   // [n_max / 256 + 2] per-CTA counts / offsets of the filtered ingest
     void* arena;
     // optional per-stage timing (SFMB200_OPT_PROFILE): ring of event sets, one set
     // per run_device / run_host call, 8 boundary marks -> 7 stage durations
@@ -79,6 +80,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_points, int max_hyp, sfmb200_t** out) {
     if (!K || !Kinv || !out) return fail(SFMB200_ERR_ARG, "null argument%s");
     if (pairs < 1 || max_points < 8 || max_hyp < 1) return fail(SFMB200_ERR_ARG, "pairs >= 1, max_points >= 8, max_hypotheses >= 1 required%s");
+    if (pairs > 65535) return fail(SFMB200_ERR_ARG, "at most 65535 pairs per handle (grid.y / grid.z limit)%s");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -115,6 +117,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_pi = carve(B * sizeof(int));
     size_t o_pts = carve(B * 4 * (size_t)s.n_stride * sizeof(float));
     size_t o_tc = carve(B * sizeof(int));
+    size_t o_fs = carve(((size_t)max_points / 256 + 2) * sizeof(int));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
     size_t o_rT = carve(B * 8 * sizeof(float));
@@ -142,6 +145,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     s.P_ind = (int*)(base + o_pi);
     s.points = (float*)(base + o_pts);
     s.tri_count = (int*)(base + o_tc);
+    h->filter_scratch = (int*)(base + o_fs);
     h->refit.cand = (float*)(base + o_rc);
     h->refit.T = (float*)(base + o_rT);
     h->refit.flags = (int*)(base + o_rf);
@@ -241,6 +245,26 @@ int sfmb200_set_points_sift(sfmb200_t* h, const void* d_sift, int n) {
     launch_ingest_sift(h->s, d_sift, n, h->stream);
     CKL();
     h->launches++;
+    h->have_points = true;
+    return SFMB200_OK;
+}
+int sfmb200_set_points_sift_filtered(sfmb200_t* h, const void* d_sift, int n, float min_score, float max_ambiguity,
+                                     int32_t* d_kept_index, int32_t* h_kept) {
+    int rc = check_n(h, d_sift, n);
+    if (rc) return rc;
+    if (h->s.B != 1) return fail(SFMB200_ERR_ARG, "SiftPoint ingest needs pairs == 1%s");
+    h->have_points = false;
+    launch_ingest_sift_filtered(h->s, d_sift, n, min_score, max_ambiguity, h->filter_scratch, d_kept_index, h->stream);
+    CKL();
+    h->launches += 3;
+    int kept = 0;
+    int blocks = (n + 255) / 256;
+    // the survivor count sizes every later launch, so it has to come back to the host
+    CK(cudaMemcpyAsync(&kept, h->filter_scratch + blocks, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h_kept) *h_kept = kept;
+    if (kept < 8) return fail(SFMB200_ERR_STATE, "fewer than 8 correspondences survive the match filter%s");
+    h->s.n = kept;
     h->have_points = true;
     return SFMB200_OK;
 }

@@ -49,6 +49,92 @@ __global__ void ingest_xy_kernel(DeviceState s, const float4* __restrict__ px, i
     float4 p = __ldg(px + (size_t)b * n + i);
     normalise_store(s, b, i, p.x, p.y, p.z, p.w, k);
 }
+// ---------------------------------------------------------------------------
+// Ingest with match filtering.  The reference feeds every
+// SIFT point of image 1 to the estimator unfiltered (main.cpp:298-299; its
+// homography pre-filter is commented out, main.cpp:283-290).  This keeps a match
+// iff score > min_score && ambiguity < max_ambiguity - the test CudaSift's own
+// FindHomography applies (CudaSift/matching.cu:1035) - and compacts the
+// survivors in their original order (deterministic): per-CTA counts, a
+// single-CTA scan, then an ordered scatter fused with the K^-1 normalisation.
+// SiftPoint: score @ float 6, ambiguity @ float 7 (CudaSift/cudaSift.h:6-22).
+// ---------------------------------------------------------------------------
+constexpr int FILTER_THREADS = 256;
+__device__ __forceinline__ bool sift_keep(const float* p, float min_score, float max_ambiguity) {
+    return __ldg(p + 6) > min_score && __ldg(p + 7) < max_ambiguity;
+}
+__global__ void __launch_bounds__(FILTER_THREADS)
+sift_filter_count_kernel(const float* __restrict__ sift, int n, float min_score, float max_ambiguity, int* block_counts) {
+    int i = blockIdx.x * FILTER_THREADS + threadIdx.x;
+    bool keep = i < n && sift_keep(sift + (size_t)i * SIFT_STRIDE_F, min_score, max_ambiguity);
+    int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+// exclusive scan of nblocks counts in place; total -> counts[nblocks]
+__global__ void sift_filter_scan_kernel(int* counts, int nblocks) {
+    __shared__ int carry;
+    __shared__ int warp_sums[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < nblocks ? counts[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_sums[threadIdx.x], z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xFFFFFFFFu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            warp_sums[threadIdx.x] = z - w;          // exclusive warp offsets
+        }
+        __syncthreads();
+        int excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < nblocks) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[nblocks] = carry;
+}
+__global__ void __launch_bounds__(FILTER_THREADS)
+sift_filter_scatter_kernel(DeviceState s, const float* __restrict__ sift, int n, float min_score, float max_ambiguity,
+                           const int* __restrict__ block_offsets, int* kept_index, Mat9 k) {
+    __shared__ int warp_counts[FILTER_THREADS / 32];
+    int i = blockIdx.x * FILTER_THREADS + threadIdx.x;
+    const float* p = sift + (size_t)i * SIFT_STRIDE_F;
+    bool keep = i < n && sift_keep(p, min_score, max_ambiguity);
+    unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_counts[warp] = __popc(m);
+    __syncthreads();
+    int off = block_offsets[blockIdx.x];
+    for (int w = 0; w < warp; w++) off += warp_counts[w];
+    if (!keep) return;
+    int dst = off + __popc(m & ((1u << lane) - 1u));
+    float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    normalise_store(s, 0, dst, a.x, a.y, __ldg(p + 9), __ldg(p + 10), k);
+    if (kept_index) kept_index[dst] = i;
+}
+void launch_ingest_sift_filtered(const DeviceState& s, const void* d_sift, int n, float min_score, float max_ambiguity,
+                                 int* d_scratch, int* d_kept_index, cudaStream_t st) {
+    Mat9 k;
+    for (int i = 0; i < 9; i++) k.v[i] = s.Kinv[i];
+    int blocks = (n + FILTER_THREADS - 1) / FILTER_THREADS;
+    sift_filter_count_kernel<<<blocks, FILTER_THREADS, 0, st>>>((const float*)d_sift, n, min_score, max_ambiguity, d_scratch);
+    sift_filter_scan_kernel<<<1, 1024, 0, st>>>(d_scratch, blocks);
+    sift_filter_scatter_kernel<<<blocks, FILTER_THREADS, 0, st>>>(s, (const float*)d_sift, n, min_score, max_ambiguity, d_scratch,
+                                                                   d_kept_index, k);
+}
+
 void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStream_t st) {
     Mat9 k;
     for (int i = 0; i < 9; i++) k.v[i] = s.Kinv[i];

@@ -61,6 +61,8 @@ struct RefitState {
 int launch_refit(const DeviceState& s, const RefitState& r, float thr, int iterations, cudaStream_t st);
 
 void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStream_t st);
+void launch_ingest_sift_filtered(const DeviceState& s, const void* d_sift, int n, float min_score, float max_ambiguity,
+                                 int* d_scratch, int* d_kept_index, cudaStream_t st);
 void launch_ingest_xy(const DeviceState& s, const float* d_px, int n, cudaStream_t st);
 void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cudaStream_t st);
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,

@@ -82,6 +82,15 @@ class BatchedPairs:
         self.lib.call("sfmb200_set_points_sift", self._h, _dptr(d_sift), n)
         self.n = n
 
+    def set_points_sift_filtered(self, d_sift, n: int, min_score: float, max_ambiguity: float, d_kept_index=None) -> int:
+        kept = C.c_int32(0)
+        try:
+            self.lib.call("sfmb200_set_points_sift_filtered", self._h, _dptr(d_sift), n, C.c_float(min_score),
+                          C.c_float(max_ambiguity), _dptr(d_kept_index), C.byref(kept))
+        finally:
+            self.n = kept.value
+        return kept.value
+
     def set_points_xy(self, d_px, n: int | None = None):
         n = n if n is not None else d_px.shape[-2]
         self.lib.call("sfmb200_set_points_xy", self._h, _dptr(d_px), n)
@@ -270,9 +279,14 @@ class ImagePair(BatchedPairs):
         self.image_count, self.num_points = image_count, num_points
         super().__init__(k, k_inv, 1, num_points, max_hypotheses or max(num_points // 8, 1), lib)
 
-    def fillXU(self, data, n: int | None = None):
-        """data: device SiftPoint array (raw address or uint8 CUDA tensor)."""
-        self.set_points_sift(data, n or self.num_points)
+    def fillXU(self, data, n: int | None = None, min_score: float | None = None, max_ambiguity: float | None = None):
+        """data: device SiftPoint array (raw address or CUDA tensor).  With
+        min_score / max_ambiguity: keep only matches passing CudaSift's own test."""
+        if min_score is None and max_ambiguity is None:
+            self.set_points_sift(data, n or self.num_points)
+            return self.n
+        return self.set_points_sift_filtered(data, n or self.num_points, min_score if min_score is not None else -np.inf,
+                                             max_ambiguity if max_ambiguity is not None else np.inf)
 
     def estimateE(self, H: int | None = None, seed: int = 0, thr: float = 1e-6, d_idx=None):
         self.estimate_e(H or max(self.n // 8, 1), seed, thr, d_idx)

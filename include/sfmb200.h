@@ -72,6 +72,13 @@ int sfmb200_synchronize(sfmb200_t* h);
 /* ---- ingest: Image_pair::fillXU (SfM/sfm.cu:80-92; kernels::copy_point kernels.h:261-279) ---- */
 /* d_sift: device array of n CudaSift SiftPoint structs (576 B each, CudaSift/cudaSift.h:6-22). pairs must be 1. */
 int sfmb200_set_points_sift(sfmb200_t* h, const void* d_sift, int n);
+/* Same with match filtering (not in the reference, which feeds every match unfiltered: main.cpp:298-299,
+ * 283-290): keeps SiftPoint i iff score > min_score && ambiguity < max_ambiguity (the
+ * test of CudaSift's FindHomography, matching.cu:1035), compacted in original order.  d_kept_index (device
+ * int32 [n], nullable) receives the original index of every kept correspondence; *h_kept their number.
+ * SFMB200_ERR_STATE when fewer than 8 survive.  Synchronises (the count sizes the later launches). */
+int sfmb200_set_points_sift_filtered(sfmb200_t* h, const void* d_sift, int n, float min_score, float max_ambiguity,
+                                     int32_t* d_kept_index, int32_t* h_kept);
 /* d_px: device [pairs][n][4] pixel coordinates (u1, v1, u2, v2). */
 int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n);
 /* same from host memory (pinned or pageable); copied on the handle's stream. */

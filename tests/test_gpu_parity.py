@@ -387,3 +387,35 @@ def test_full_size_properties_config2(pkg, O, torch_cuda):
     cnt, amb = O.inlier_counts(E.cpu().numpy()[sel].astype(np.float64), x, THR, band=BAND)
     assert np.all(np.abs(c.cpu().numpy()[sel] - cnt) <= amb)
     h.close()
+
+
+def test_filtered_sift_ingest(pkg, O, torch_cuda, scene_small):
+    """match filtering fused into ingest, ordered compaction."""
+    torch = torch_cuda
+    n = len(scene_small["px"])
+    rng = np.random.default_rng(7)
+    sift = np.zeros((n, 144), np.float32)
+    sift[:, 0], sift[:, 1], sift[:, 9], sift[:, 10] = scene_small["px"].T
+    sift[:, 6] = rng.uniform(0.5, 1.0, n)           # score
+    sift[:, 7] = rng.uniform(0.5, 1.0, n)           # ambiguity
+    d_sift = torch.from_numpy(sift).cuda()
+    for min_score, max_amb in ((0.85, 0.95), (0.0, 2.0), (0.5, 0.75)):
+        keep = (sift[:, 6] > np.float32(min_score)) & (sift[:, 7] < np.float32(max_amb))
+        ip_f = pkg.ImagePair(scene_small["K"], scene_small["Kinv"], 2, n)
+        kept_idx = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        kept = ip_f.set_points_sift_filtered(d_sift, n, min_score, max_amb, kept_idx)
+        assert kept == int(keep.sum())
+        assert np.array_equal(kept_idx.cpu().numpy()[:kept], np.flatnonzero(keep).astype(np.int32))
+        # same bits as an unfiltered ingest of the surviving records
+        ip_u = pkg.ImagePair(scene_small["K"], scene_small["Kinv"], 2, n)
+        ip_u.fillXU(torch.from_numpy(np.ascontiguousarray(sift[keep])).cuda(), n=kept)
+        for image in (0, 1):
+            assert np.array_equal(ip_f.get_X(image).cpu().numpy(), ip_u.get_X(image).cpu().numpy())
+        ip_f.estimateE(256, 3, THR)
+        ip_u.estimateE(256, 3, THR)
+        assert np.array_equal(ip_f.get_E(), ip_u.get_E()) and ip_f.get_best()[1][0] == ip_u.get_best()[1][0]
+        ip_f.close(); ip_u.close()
+    ip_f = pkg.ImagePair(scene_small["K"], scene_small["Kinv"], 2, n)
+    with pytest.raises(pkg.SfmError) as e:
+        ip_f.set_points_sift_filtered(d_sift, n, 2.0, 0.0)       # nothing survives
+    assert e.value.code == -3
