@@ -48,6 +48,9 @@ struct sfmb200_handle {
     ScorePlan plan;
     int64_t launches;
     int* filter_scratch;   // [n_max / 256 + 2] per-CTA counts / offsets of the filtered ingest
+    float* pack_header;    // device [B][32]: E 9, selected P 16, pose index, inliers, best index (run_host results)
+    float* pack_points;    // device [B][4][n] compact copy of the triangulated points
+    float* host_header;    // pinned mirror of pack_header
     void* arena;
     // optional per-stage timing (SFMB200_OPT_PROFILE): ring of event sets, one set
     // per run_device / run_host call, 8 boundary marks -> 7 stage durations
@@ -118,6 +121,8 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_pts = carve(B * 4 * (size_t)s.n_stride * sizeof(float));
     size_t o_tc = carve(B * sizeof(int));
     size_t o_fs = carve(((size_t)max_points / 256 + 2) * sizeof(int));
+    size_t o_ph = carve(B * 32 * sizeof(float));
+    size_t o_pp = carve(B * 4 * (size_t)max_points * sizeof(float));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
     size_t o_rT = carve(B * 8 * sizeof(float));
@@ -146,6 +151,8 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     s.points = (float*)(base + o_pts);
     s.tri_count = (int*)(base + o_tc);
     h->filter_scratch = (int*)(base + o_fs);
+    h->pack_header = (float*)(base + o_ph);
+    h->pack_points = (float*)(base + o_pp);
     h->refit.cand = (float*)(base + o_rc);
     h->refit.T = (float*)(base + o_rT);
     h->refit.flags = (int*)(base + o_rf);
@@ -155,6 +162,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->refit.max_blocks = refit_blocks;
     e = cudaMemset(h->arena, 0, off);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->host_header, B * 32 * sizeof(float));
     if (e != cudaSuccess) {
         cudaFree(h->arena);
         delete h;
@@ -173,6 +181,7 @@ int sfmb200_destroy(sfmb200_t* h) {
     if (!h) return SFMB200_OK;
     cudaStreamSynchronize(h->stream);
     if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->host_header) cudaFreeHost(h->host_header);
     if (h->prof_ev) {
         for (int i = 0; i < PROF_RING; i++)
             for (int k = 0; k < 8; k++) cudaEventDestroy(h->prof_ev[i][k]);
@@ -428,10 +437,28 @@ int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t s
     return run_stages(h, H, seed, thr);
 }
 
-__global__ void gather_selected_pose_kernel(DeviceState s, float* out) {
-    int b = blockIdx.x;
-    int t = threadIdx.x;
-    if (t < 16) out[(size_t)b * 16 + t] = s.P[(size_t)b * 64 + 16 * s.P_ind[b] + t];
+// Results of the whole path packed for the host: one small header per pair and a
+// compact [4][n] copy of the points, so run_host needs two DMA transfers instead
+// of six (each small D2H copy costs ~5-10 us of latency on the critical path).
+__global__ void pack_results_kernel(DeviceState s, float* header, float* points, int want_points) {
+    const int b = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        const int t = threadIdx.x;
+        float v = 0.0f;
+        if (t < 9) v = s.E[(size_t)b * 9 + t];
+        else if (t < 25) v = s.P[(size_t)b * 64 + 16 * s.P_ind[b] + (t - 9)];
+        else if (t == 25) v = __int_as_float(s.P_ind[b]);
+        else if (t == 26) v = __int_as_float(s.best_count[b]);
+        else if (t == 27) v = __int_as_float(s.best_idx[b]);
+        header[(size_t)b * 32 + t] = v;
+    }
+    if (!want_points) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    const float* in = s.points + (size_t)b * 4 * s.n_stride;
+    float* out = points + (size_t)b * 4 * s.n;
+#pragma unroll
+    for (int r = 0; r < 4; r++) out[(size_t)r * s.n + i] = in[(size_t)r * s.n_stride + i];
 }
 
 int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t seed, float thr, float* h_E, float* h_P,
@@ -441,26 +468,22 @@ int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t see
     if (rc) return rc;
     if ((rc = run_stages(h, H, seed, thr))) return rc;
     DeviceState& s = h->s;
-    size_t B = s.B;
-    if (h_E) CK(cudaMemcpyAsync(h_E, s.E, B * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (h_P) {
-        // selected pose per pair, staged through the (now free) pixel buffer
-        gather_selected_pose_kernel<<<(unsigned)B, 16, 0, h->stream>>>(s, s.px);
-        CKL();
-        h->launches++;
-        CK(cudaMemcpyAsync(h_P, s.px, B * 16 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    }
-    if (h_pose_index) CK(cudaMemcpyAsync(h_pose_index, s.P_ind, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (h_inliers) CK(cudaMemcpyAsync(h_inliers, s.best_count, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (h_points) {
-        if (s.n == s.n_stride) {
-            CK(cudaMemcpyAsync(h_points, s.points, B * 4 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-        } else {
-            CK(cudaMemcpy2DAsync(h_points, (size_t)s.n * sizeof(float), s.points, (size_t)s.n_stride * sizeof(float),
-                                 (size_t)s.n * sizeof(float), B * 4, cudaMemcpyDeviceToHost, h->stream));
-        }
-    }
+    const size_t B = s.B;
+    dim3 grid(h_points ? (s.n + 255) / 256 : 1, (unsigned)B);
+    pack_results_kernel<<<grid, 256, 0, h->stream>>>(s, h->pack_header, h->pack_points, h_points ? 1 : 0);
+    CKL();
+    h->launches++;
+    CK(cudaMemcpyAsync(h->host_header, h->pack_header, B * 32 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_points)
+        CK(cudaMemcpyAsync(h_points, h->pack_points, B * 4 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    for (size_t b = 0; b < B; b++) {
+        const float* hd = h->host_header + b * 32;
+        if (h_E) memcpy(h_E + b * 9, hd, 9 * sizeof(float));
+        if (h_P) memcpy(h_P + b * 16, hd + 9, 16 * sizeof(float));
+        if (h_pose_index) memcpy(h_pose_index + b, hd + 25, sizeof(int32_t));
+        if (h_inliers) memcpy(h_inliers + b, hd + 26, sizeof(int32_t));
+    }
     return SFMB200_OK;
 }
 

@@ -2,6 +2,7 @@
 // triangulation and egress.  Reference: SfM/sfm.cu:80-92, 238-344, 374-383 and
 // SfM/kernels.h:261-279, 357-450, 471-495.
 #include "internal.cuh"
+#include "sampson.cuh"
 #include "smallmat.cuh"
 
 namespace sfmb200 {
@@ -241,17 +242,6 @@ __device__ __forceinline__ void dehomogenise(const float* v, float& X, float& Y,
     X = v[0] * iw; Y = v[1] * iw; Z = v[2] * iw;
 }
 
-__device__ __forceinline__ float sampson_d_geom(const float* e, float x1, float y1, float x2, float y2, float nthr) {
-    float l0 = fmaf(e[0], x2, fmaf(e[1], y2, e[2]));
-    float l1 = fmaf(e[3], x2, fmaf(e[4], y2, e[5]));
-    float l2 = fmaf(e[6], x2, fmaf(e[7], y2, e[8]));
-    float num = fmaf(x1, l0, fmaf(y1, l1, l2));
-    float m0 = fmaf(e[0], x1, fmaf(e[3], y1, e[6]));
-    float m1 = fmaf(e[1], x1, fmaf(e[4], y1, e[7]));
-    float den = fmaf(l0, l0, fmaf(l1, l1, fmaf(m0, m0, m1 * m1)));
-    return fmaf(den, nthr, num * num);
-}
-
 // ---------------------------------------------------------------------------
 // choosePose (sfm.cu:254-307).
 // compat = 1: cheirality of correspondence 0 only; every candidate is inverted
@@ -353,7 +343,7 @@ __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, fl
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = threadIdx.x; i < s.n; i += blockDim.x) {
         float4 p = corr[i];
-        if (sampson_d_geom(sE, p.x, p.y, p.z, p.w, -thr) >= 0.0f) continue;
+        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr) >= 0.0f) continue;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             float A[16], v[4];
@@ -406,7 +396,7 @@ __global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inl
     if (i >= s.n) return;
     float4 p = __ldg(s.corr + (size_t)b * s.n_stride + i);
     float X = 0.0f, Y = 0.0f, Z = 0.0f;
-    bool keep = !inliers_only || sampson_d_geom(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f;
+    bool keep = !inliers_only || sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f;
     if (keep) {
         float A[16], v[4];
         dlt_matrix(p.x, p.y, p.z, p.w, sM, A);
@@ -473,7 +463,7 @@ __global__ void inlier_mask_kernel(DeviceState s, int pair, float thr, unsigned 
 #pragma unroll
     for (int k = 0; k < 9; k++) e[k] = s.E[(size_t)pair * 9 + k];
     float4 p = s.corr[(size_t)pair * s.n_stride + i];
-    mask[i] = sampson_d_geom(e, p.x, p.y, p.z, p.w, -thr) < 0.0f ? 1 : 0;
+    mask[i] = sampson_d(e, p.x, p.y, p.z, p.w, -thr) < 0.0f ? 1 : 0;
 }
 void launch_inlier_mask(const DeviceState& s, int pair, float thr, unsigned char* d_mask, cudaStream_t st) {
     inlier_mask_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, thr, d_mask);

@@ -22,22 +22,12 @@
 //                        and publishes the next candidate.
 // Everything is deterministic: fixed grid, fixed-order reductions, no float atomics.
 #include "internal.cuh"
+#include "sampson.cuh"
 #include "smallmat.cuh"
 
 namespace sfmb200 {
 
 constexpr int REFIT_THREADS = 256;
-
-__device__ __forceinline__ float sampson_d_refit(const float* e, float x1, float y1, float x2, float y2, float nthr) {
-    float l0 = fmaf(e[0], x2, fmaf(e[1], y2, e[2]));
-    float l1 = fmaf(e[3], x2, fmaf(e[4], y2, e[5]));
-    float l2 = fmaf(e[6], x2, fmaf(e[7], y2, e[8]));
-    float num = fmaf(x1, l0, fmaf(y1, l1, l2));
-    float m0 = fmaf(e[0], x1, fmaf(e[3], y1, e[6]));
-    float m1 = fmaf(e[1], x1, fmaf(e[4], y1, e[7]));
-    float den = fmaf(l0, l0, fmaf(l1, l1, fmaf(m0, m0, m1 * m1)));
-    return fmaf(den, nthr, num * num);
-}
 
 // Fixed-order block reduction of NV values per thread; result valid in thread 0.
 template <int NV>
@@ -82,8 +72,8 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_eval_kernel(DeviceState s
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = blockIdx.x * REFIT_THREADS + threadIdx.x; i < s.n; i += gridDim.x * REFIT_THREADS) {
         float4 p = corr[i];
-        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f) m[NMOM] += 1.0f;
-        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
+        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f) m[NMOM] += 1.0f;
+        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
             m[0] += 1.0f;
             m[1] += p.x; m[2] += p.y; m[3] += p.z; m[4] += p.w;
             m[5] += fmaf(p.x, p.x, p.y * p.y);
@@ -148,7 +138,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_solve_kernel(DeviceState 
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = blockIdx.x * REFIT_THREADS + threadIdx.x; i < s.n; i += gridDim.x * REFIT_THREADS) {
         float4 p = corr[i];
-        if (sampson_d_refit(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
+        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
             float x1 = sT[0] * (p.x - sT[1]), y1 = sT[0] * (p.y - sT[2]);
             float x2 = sT[3] * (p.z - sT[4]), y2 = sT[3] * (p.w - sT[5]);
             float a[9] = {x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, 1.0f};

@@ -2,9 +2,9 @@
 //
 // Everything here is __host__ __device__ so the same code backs the device
 // kernels (hypgen / pose / triangulate) and the host-callable svd.h facade
-// (reference surface: SfM/svd.h:33-501).  The algorithms are our own:
-// exact-angle cyclic Jacobi on the Gram matrix followed by a Givens QR,
-// with the reference's output contract for svd() (SfM/svd.h:311-335):
+// (reference surface: SfM/svd.h:33-501).  The algorithms are our own (one-sided
+// Jacobi + Givens QR for the 3x3 SVD; Jacobi / inverse iteration for the 4x4
+// null vector), with the reference's output contract for svd() (SfM/svd.h:311-335):
 //   a = u * s * v^T, v NOT transposed, s (nearly) diagonal with
 //   |s00| >= |s11| >= |s22|, u and v proper rotations (s22 may be negative).
 #pragma once

@@ -1,0 +1,131 @@
+"""GPU tier: the kernels.h-equivalent linear-algebra entry points
+(include/sfmb200_la.h) against numpy, with the reference's own test literals
+(SfM/sfm.cu:389-510) and its call-site shapes (3x3 * 3xN, 8x9 and 4x4 batched
+SVD in cuSOLVER's column-major convention, 4x4 inverse)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def dp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def test_mmul_family(lib, T):
+    rng = np.random.default_rng(0)
+    A, B = rng.normal(size=(3, 3)).astype(np.float32), rng.normal(size=(3, 1000)).astype(np.float32)
+    dA, dB = T.from_numpy(A).cuda(), T.from_numpy(B).cuda()
+    dC = T.empty((3, 1000), device="cuda")
+    lib.call("sfmb200_la_mmul", dp(dA), dp(dB), dp(dC), 3, 3, 1000, None)        # fillXU: K^-1 * U (sfm.cu:88)
+    assert np.allclose(dC.cpu().numpy(), A @ B, atol=1e-6)
+    # batched E_h * X with a shared right operand (calculateInliers, sfm.cu:174)
+    E = rng.normal(size=(5, 3, 3)).astype(np.float32)
+    dE = T.from_numpy(E).cuda()
+    dO = T.empty((5, 3, 1000), device="cuda")
+    lib.call("sfmb200_la_mmul_batched", dp(dE), dp(dB), dp(dO), 3, 3, 1000, 9, 0, 3000, 5, None)
+    assert np.allclose(dO.cpu().numpy(), E @ B, atol=1e-5)
+    # X^T * E_h with X stored 3 x N (sfm.cu:178)
+    dO2 = T.empty((5, 1000, 3), device="cuda")
+    lib.call("sfmb200_la_mmul_transpose_batched", dp(dB), dp(dE), dp(dO2), 1000, 3, 3, 0, 9, 3000, 5, None)
+    assert np.allclose(dO2.cpu().numpy(), np.einsum("kn,bkj->bnj", B, E), atol=1e-5)
+    # literal of testBatchedmultTranspose (sfm.cu:467-489)
+    A2 = np.array([1, 2, 3, 1, 4, 5, 6, 1, 7, 8, 9, 1, 0, 1, 2, 1, 3, 4, 5, 1, 6, 7, 8, 1], np.float32)
+    B2 = np.arange(1, 10, dtype=np.float32)
+    dA2, dB2, dC2 = T.from_numpy(A2).cuda(), T.from_numpy(B2).cuda(), T.empty(24, device="cuda")
+    lib.call("sfmb200_la_mmul_transpose_batched", dp(dA2), dp(dB2), dp(dC2), 4, 3, 3, 12, 0, 12, 2, None)
+    want = np.stack([A2[:12].reshape(3, 4).T @ B2.reshape(3, 3), A2[12:].reshape(3, 4).T @ B2.reshape(3, 3)])
+    assert np.array_equal(dC2.cpu().numpy().reshape(2, 4, 3), want)
+
+
+def test_invert_and_singular(lib, T, pkg):
+    rng = np.random.default_rng(1)
+    M = rng.normal(size=(7, 4, 4)).astype(np.float32) + 3 * np.eye(4, dtype=np.float32)
+    dM, dI = T.from_numpy(M).cuda(), T.empty((7, 4, 4), device="cuda")
+    lib.call("sfmb200_la_invert", dp(dM), dp(dI), 4, 7, None)
+    assert np.allclose(dI.cpu().numpy() @ M, np.eye(4), atol=1e-4)
+    lib.call("sfmb200_la_invert", dp(dM), dp(dM), 4, 7, None)                    # in place, like choosePose (sfm.cu:286)
+    assert np.allclose(dM.cpu().numpy(), dI.cpu().numpy())
+    a = np.array([1, 2, 0, 0, 2, 0, 1, 2, 1], np.float32)                        # testInverse literal (sfm.cu:444-445)
+    da, db = T.from_numpy(a).cuda(), T.empty(9, device="cuda")
+    lib.call("sfmb200_la_invert", dp(da), dp(db), 3, 1, None)
+    assert np.allclose(db.cpu().numpy().reshape(3, 3), np.linalg.inv(a.reshape(3, 3)), atol=1e-6)
+    dz = T.zeros(16, device="cuda")
+    with pytest.raises(pkg.SfmError) as e:
+        lib.call("sfmb200_la_invert", dp(dz), dp(dz), 4, 1, None)
+    assert e.value.code == -5                                                     # the reference exit()s here
+
+
+@pytest.mark.parametrize("m,n", [(4, 4), (8, 9), (3, 3), (9, 8)])
+def test_svd_batched_cusolver_convention(lib, T, m, n):
+    rng = np.random.default_rng(2)
+    batch = 50
+    A = rng.normal(size=(batch, m, n)).astype(np.float32)
+    Acm = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))                       # column-major storage, lda = m
+    dA = T.from_numpy(Acm).cuda()
+    mn = min(m, n)
+    dS, dU, dV = T.empty((batch, mn), device="cuda"), T.empty((batch, m, m), device="cuda"), T.empty((batch, n, n), device="cuda")
+    lib.call("sfmb200_la_svd_batched", dp(dA), dp(dS), dp(dU), dp(dV), m, n, batch, None)
+    S = dS.cpu().numpy()
+    U = np.transpose(dU.cpu().numpy(), (0, 2, 1))                                # column-major -> math
+    V = np.transpose(dV.cpu().numpy(), (0, 2, 1))
+    sv = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    assert np.allclose(S, sv, atol=2e-5 * sv.max())
+    assert np.all(S[:, :-1] >= S[:, 1:] - 1e-6)                                   # sorted like gesvdj with sort_svd = 1
+    for b in range(batch):
+        Sm = np.zeros((m, n))
+        Sm[:mn, :mn] = np.diag(S[b])
+        assert np.abs(U[b] @ Sm @ V[b].T - A[b]).max() < 5e-5
+        assert np.abs(U[b].T @ U[b] - np.eye(m)).max() < 1e-4 and np.abs(V[b].T @ V[b] - np.eye(n)).max() < 1e-4
+    if (m, n) == (8, 9):
+        # the reference's use: null vector = 9th column of V = floats 72..80 of the column-major block (kernels.h:457)
+        dE = T.empty((batch, 9), device="cuda")
+        lib.call("sfmb200_la_row_extraction", dp(dV), dp(dE), batch, None)
+        e = dE.cpu().numpy()
+        assert np.abs(np.einsum("bij,bj->bi", A, e)).max() < 1e-4
+        assert np.array_equal(e, dV.cpu().numpy().reshape(batch, 81)[:, 72:81])
+
+
+def test_elementwise_vecnorm_threshold_argmax(lib, T):
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=5000).astype(np.float32), rng.normal(size=5000).astype(np.float32)
+    b[::7] = 0
+    for op, f in ((0, lambda x, y: x * y), (2, lambda x, y: x + y)):
+        da, db = T.from_numpy(a.copy()).cuda(), T.from_numpy(b).cuda()
+        lib.call("sfmb200_la_elementwise", op, dp(da), dp(db), 5000, None)
+        assert np.array_equal(da.cpu().numpy(), f(a, b))
+    da, db = T.from_numpy(a.copy()).cuda(), T.from_numpy(b).cuda()
+    lib.call("sfmb200_la_elementwise", 1, dp(da), dp(db), 5000, None)            # div with the b == 0 -> 0 guard (kernels.h:311)
+    want = np.where(b == 0, 0, a / np.where(b == 0, 1, b)).astype(np.float32)
+    assert np.allclose(da.cpu().numpy(), want, rtol=1e-6)
+    # testVecnorm literal (sfm.cu:503-510): columns of [1 2 3; 4 5 6; 7 8 9], p = 2 -> 8.124, 9.644, 11.225
+    t = T.arange(1, 10, dtype=T.float32, device="cuda")
+    r = T.empty(3, device="cuda")
+    lib.call("sfmb200_la_vecnorm", dp(t), dp(r), 3, 3, C.c_float(2), C.c_float(1), None)
+    assert np.allclose(r.cpu().numpy(), [8.1240384, 9.6436508, 11.224972], rtol=1e-6)
+    lib.call("sfmb200_la_vecnorm", dp(t), dp(r), 3, 3, C.c_float(2), C.c_float(2), None)   # exp == final_pow: sum of squares
+    assert np.allclose(r.cpu().numpy(), [66, 93, 126])
+    res = rng.uniform(0, 2e-6, size=(40, 333)).astype(np.float32)
+    dres, dcnt = T.from_numpy(res).cuda(), T.empty(40, dtype=T.int32, device="cuda")
+    lib.call("sfmb200_la_threshold_count", dp(dres), dp(dcnt), 333, 40, C.c_float(1e-6), None)
+    assert np.array_equal(dcnt.cpu().numpy(), (res < np.float32(1e-6)).sum(1))
+    v = T.tensor([1, 2, 3, 4, 5, 6, 4, 1, 3], dtype=T.int32, device="cuda")       # testThrust_max: 6 at position 5
+    idx = C.c_int32(-1)
+    lib.call("sfmb200_la_argmax_first", dp(v), 6, C.byref(idx), None)
+    assert idx.value == 5
+    v2 = T.tensor([-5, -2, -2, -9], dtype=T.int32, device="cuda")                 # negatives and ties: first maximum
+    lib.call("sfmb200_la_argmax_first", dp(v2), 4, C.byref(idx), None)
+    assert idx.value == 1
+    big = T.from_numpy(rng.integers(0, 1000, 100000).astype(np.int32)).cuda()
+    lib.call("sfmb200_la_argmax_first", dp(big), 100000, C.byref(idx), None)
+    assert idx.value == int(np.argmax(big.cpu().numpy()))
