@@ -256,7 +256,7 @@ __device__ __forceinline__ void dehomogenise(const float* v, float& X, float& Y,
 __device__ __forceinline__ bool cheirality_compat(const float4& c0, const float* M, float* Minv) {
     float A[16], v[4];
     dlt_matrix(c0.x, c0.y, c0.z, c0.w, M, A);
-    null4<5>(A, v);
+    if (!null4_inverse_iteration<8>(A, v)) null4<5>(A, v);     // same solve as triangulate_kernel
     float X, Y, Z;
     dehomogenise(v, X, Y, Z);
     inv4(M, Minv);

@@ -63,7 +63,11 @@ SFM_HD void jacobi_angle_fast(float app, float aqq, float apq, float& c, float& 
 SFM_HD void givens(float a, float b, float& c, float& s) {
     float r2 = fmaf(a, a, b * b);
     if (r2 < 1e-37f) { c = 1.0f; s = 0.0f; return; }
+#if defined(__CUDA_ARCH__)
+    float ir = rsqrtf(r2);
+#else
     float ir = 1.0f / sqrtf(r2);
+#endif
     c = a * ir;
     s = b * ir;
 }
@@ -123,8 +127,8 @@ SFM_HD void svd3(const float* a, float* u, float* s, float* v) {
                 float aqq = fmaf(B[6 + q], B[6 + q], fmaf(B[3 + q], B[3 + q], B[q] * B[q]));
                 float apq = fmaf(B[6 + p], B[6 + q], fmaf(B[3 + p], B[3 + q], B[p] * B[q]));
                 // skip when already orthogonal to working precision
-                bool small = fabsf(apq) <= 1e-9f * sqrtf(app * aqq);
-                jacobi_angle(app, aqq, small ? 0.0f : apq, c, sn, t);
+                bool small = apq * apq <= 1e-18f * (app * aqq);
+                jacobi_angle_fast(app, aqq, small ? 0.0f : apq, c, sn, t);   // MUFU angles on the device, exact on the host
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     float bp = B[3 * k + p], bq = B[3 * k + q];
