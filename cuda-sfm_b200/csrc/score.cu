@@ -303,7 +303,7 @@ static const ScoreVariant kVariants[] = {
     {2, 0, 256, 1}, {4, 1, 256, 1}, {4, 0, 256, 1}, {8, 0, 256, 2}, {8, 1, 256, 1},
     {4, 0, 128, 1}, {4, 1, 128, 1}, {8, 0, 128, 4}, {8, 1, 128, 2}, {2, 0, 128, 1},
     {8, 0, 256, 1}, {8, 0, 128, 3}, {8, 0, 128, 2}, {16, 0, 128, 1}, {16, 0, 128, 2}, {12, 0, 128, 2},
-    {12, 1, 256, 1}, {16, 1, 256, 1}, {16, 1, 128, 1}, {12, 1, 128, 2}, {8, 1, 256, 2}, {8, 1, 128, 4}, {6, 1, 256, 2},
+    {12, 1, 256, 1}, {16, 1, 256, 1}, {16, 1, 128, 1}, {12, 1, 128, 2}, {8, 1, 256, 2}, {8, 1, 128, 4}, {6, 1, 256, 2}, {8, 1, 192, 2}, {8, 1, 384, 1}, {8, 1, 320, 1},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -342,7 +342,10 @@ static int occupancy_one() {
         case 19: CALL(12, true, 128, 2); break;      \
         case 20: CALL(8, true, 256, 2); break;       \
         case 21: CALL(8, true, 128, 4); break;       \
-        default: CALL(6, true, 256, 2); break;       \
+        case 22: CALL(6, true, 256, 2); break;       \
+        case 23: CALL(8, true, 192, 2); break;       \
+        case 24: CALL(8, true, 384, 1); break;       \
+        default: CALL(8, true, 320, 1); break;       \
     }
 
 static int variant_occupancy(int v) {

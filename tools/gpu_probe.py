@@ -67,9 +67,9 @@ if __name__ == "__main__":
             stages(4096, 4096, -1, pairs=256, reps=3, label="config4 slice: 256 pairs", solver=solver)
         sys.exit(0)
     if which == "score":
-        for v in (4, 20, 21, 22):
+        for v in (4, 23, 24, 25):
             stages(10_000, 65_536, v, label="config2", solver=1)
-        for v in (4, 20, 21, 22):
+        for v in (4, 23, 24, 25):
             stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp", solver=1)
         sys.exit(0)
     probe()
