@@ -302,9 +302,12 @@ struct ScoreVariant { int hpt; int packed; int threads; int minb; };
 static const ScoreVariant kVariants[] = {
     {2, 0, 256, 1}, {4, 1, 256, 1}, {4, 0, 256, 1}, {8, 0, 256, 2}, {8, 1, 256, 1},
     {4, 0, 128, 1}, {4, 1, 128, 1}, {8, 0, 128, 4}, {8, 1, 128, 2}, {2, 0, 128, 1},
-    {8, 0, 256, 1}, {8, 0, 128, 3}, {8, 0, 128, 2}, {16, 0, 128, 1}, {16, 0, 128, 2}, {12, 0, 128, 2},
-    {12, 1, 256, 1}, {16, 1, 256, 1}, {16, 1, 128, 1}, {12, 1, 128, 2}, {8, 1, 256, 2}, {8, 1, 128, 4}, {6, 1, 256, 2}, {8, 1, 192, 2}, {8, 1, 384, 1}, {8, 1, 320, 1},
 };
+// Also measured on B200 and dropped (profiles/r01_variant_sweep.md): 12 / 16 hypotheses per
+// thread, scalar or packed (fewer resident warps than the reuse gain pays for); packed with a
+// 128-register cap for 16 warps/SM (less ILP: -8 %); 192 / 320 / 384-thread CTAs (warps not a
+// multiple of the 4 schedulers, or 12 warps/SM: -5 .. -30 %: operand reuse needs back-to-back
+// issue from the same warp, so fewer warps with more independent work each win).
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 template <int HPT, bool PACKED, int THREADS, int MINB>
@@ -329,23 +332,7 @@ static int occupancy_one() {
         case 6: CALL(4, true, 128, 1); break;        \
         case 7: CALL(8, false, 128, 4); break;       \
         case 8: CALL(8, true, 128, 2); break;        \
-        case 9: CALL(2, false, 128, 1); break;       \
-        case 10: CALL(8, false, 256, 1); break;      \
-        case 11: CALL(8, false, 128, 3); break;      \
-        case 12: CALL(8, false, 128, 2); break;      \
-        case 13: CALL(16, false, 128, 1); break;     \
-        case 14: CALL(16, false, 128, 2); break;     \
-        case 15: CALL(12, false, 128, 2); break;     \
-        case 16: CALL(12, true, 256, 1); break;      \
-        case 17: CALL(16, true, 256, 1); break;      \
-        case 18: CALL(16, true, 128, 1); break;      \
-        case 19: CALL(12, true, 128, 2); break;      \
-        case 20: CALL(8, true, 256, 2); break;       \
-        case 21: CALL(8, true, 128, 4); break;       \
-        case 22: CALL(6, true, 256, 2); break;       \
-        case 23: CALL(8, true, 192, 2); break;       \
-        case 24: CALL(8, true, 384, 1); break;       \
-        default: CALL(8, true, 320, 1); break;       \
+        default: CALL(2, false, 128, 1); break;      \
     }
 
 static int variant_occupancy(int v) {

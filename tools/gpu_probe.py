@@ -67,18 +67,18 @@ if __name__ == "__main__":
             stages(4096, 4096, -1, pairs=256, reps=3, label="config4 slice: 256 pairs", solver=solver)
         sys.exit(0)
     if which == "score":
-        for v in (4, 23, 24, 25):
+        for v in range(10):
             stages(10_000, 65_536, v, label="config2", solver=1)
-        for v in (4, 23, 24, 25):
+        for v in (3, 4, 8):
             stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp", solver=1)
         sys.exit(0)
     probe()
-    nv = 16
+    nv = 10
     for v in range(nv):
-        stages(10_000, 65_536, v, label="config2")
-    for v in (3, 4, 10, 11, 12, 13, 14, 15):
-        stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp")
-    for v in (3, 4, 10, 12, 13, 15):
-        stages(4096, 4096, v, pairs=256, reps=3, label="config4 slice: 256 pairs")
+        stages(10_000, 65_536, v, label="config2", solver=1)
+    for v in (3, 4, 8):
+        stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp", solver=1)
+    for v in (3, 4, 6, 8):
+        stages(4096, 4096, v, pairs=256, reps=3, label="config4 slice: 256 pairs", solver=1)
     stages(2000, 250, -1, label="config1-like: 2k corr, 250 hyp")
     stages(10_000, 65_536, -1, label="config2 auto")
