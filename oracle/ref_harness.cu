@@ -137,6 +137,7 @@ float ref_estimateE_injected(void* p, const int* h_idx, int H, int* out_best) {
     const int ransac_count = H;
     int* d_indices;
     cudaMalloc((void**)&d_indices, sizeof(int) * 8 * (H + 1));
+    cudaMemset(d_indices, 0, sizeof(int) * 8 * (H + 1));      // row H: the reference's off-by-one thread (kernels.h:242)
     cudaMemcpy(d_indices, h_idx, sizeof(int) * 8 * H, cudaMemcpyHostToDevice);
     float* d_A;
     cudaMalloc((void**)&d_A, 8 * 9 * (size_t)(ransac_count + 1) * sizeof(float));
