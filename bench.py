@@ -165,10 +165,10 @@ def run_ours(args):
     import torch.distributed as dist
 
     rank, world, local = dist_setup(args.gpus)
-    pkg, O = entry.load_package(), entry.load_oracle()
-    K, Kinv = O.reference_K()
+    pkg = entry.load_package()           # the checker (oracle/) is loaded by the baseline legs only
+    K, Kinv = pkg.synthetic.reference_K()
     # pairs sharded across ranks: each rank owns its own synthetic pair (weak scaling)
-    scene = O.synthetic_pair(N_CORR, 0.3, 1.0, seed=1234 + 10 * rank)
+    scene = pkg.synthetic.synthetic_pair(N_CORR, 0.3, 1.0, seed=1234 + 10 * rank)
     px = scene["px"]
     d_px = torch.from_numpy(px).cuda()
     h_px = torch.from_numpy(px).pin_memory()
@@ -275,6 +275,7 @@ def run_ours(args):
            "bytes_per_point": 32, "kernel_ms": tri_ms,
            "note": "10k points = 320 KB: launch-latency bound at this size; see profiles/ for the 1M-point run"}
     tri["frac"] = tri["achieved"] / hbm if tri["achieved"] else None
+    O = entry.load_oracle()              # cpu_baseline leg: the oracle port timed on the host cores
     x = O.normalise_points(px, Kinv)
     cpu = cpu_baseline(O, x)
     line = {

@@ -45,49 +45,46 @@ inline int ilog2(int x) {
 inline int ilog2ceil(int x) { return x == 1 ? 0 : ilog2(x - 1) + 1; }
 
 namespace Common {
-// CPU (chrono) and GPU (cudaEvent) stopwatch with the reference's method names.
+// Stopwatch pair with the reference's method names (SfM/common.h:48-132): a host
+// clock and a pair of CUDA events on the legacy default stream.  Misuse (start
+// twice, stop without start) throws std::runtime_error like the reference.
 class PerformanceTimer {
+    using clock = std::chrono::steady_clock;
+    enum Which { CPU = 0, GPU = 1 };
+    bool running_[2] = {false, false};
+    float last_ms_[2] = {0.f, 0.f};
+    clock::time_point cpu_begin_;
+    cudaEvent_t gpu_begin_ = nullptr, gpu_end_ = nullptr;
+
+    void arm(Which w, const char* what) {
+        if (running_[w]) throw std::runtime_error(std::string(what) + " timer already started");
+        running_[w] = true;
+    }
+    void disarm(Which w, const char* what) {
+        if (!running_[w]) throw std::runtime_error(std::string(what) + " timer not started");
+        running_[w] = false;
+    }
+
 public:
-    PerformanceTimer() {
-        cudaEventCreate(&event_start);
-        cudaEventCreate(&event_end);
-    }
-    ~PerformanceTimer() {
-        cudaEventDestroy(event_start);
-        cudaEventDestroy(event_end);
-    }
-    void startCpuTimer() {
-        if (cpu_started) throw std::runtime_error("CPU timer already started");
-        cpu_started = true;
-        t0 = std::chrono::high_resolution_clock::now();
-    }
-    void endCpuTimer() {
-        auto t1 = std::chrono::high_resolution_clock::now();
-        if (!cpu_started) throw std::runtime_error("CPU timer not started");
-        cpu_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
-        cpu_started = false;
-    }
-    void startGpuTimer() {
-        if (gpu_started) throw std::runtime_error("GPU timer already started");
-        gpu_started = true;
-        cudaEventRecord(event_start);
-    }
-    void endGpuTimer() {
-        cudaEventRecord(event_end);
-        cudaEventSynchronize(event_end);
-        if (!gpu_started) throw std::runtime_error("GPU timer not started");
-        cudaEventElapsedTime(&gpu_ms, event_start, event_end);
-        gpu_started = false;
-    }
-    float getCpuElapsedTimeForPreviousOperation() { return cpu_ms; }
-    float getGpuElapsedTimeForPreviousOperation() { return gpu_ms; }
+    PerformanceTimer() { cudaEventCreate(&gpu_begin_); cudaEventCreate(&gpu_end_); }
+    ~PerformanceTimer() { cudaEventDestroy(gpu_begin_); cudaEventDestroy(gpu_end_); }
     PerformanceTimer(const PerformanceTimer&) = delete;
     PerformanceTimer& operator=(const PerformanceTimer&) = delete;
 
-private:
-    cudaEvent_t event_start = nullptr, event_end = nullptr;
-    std::chrono::high_resolution_clock::time_point t0;
-    bool cpu_started = false, gpu_started = false;
-    float cpu_ms = 0.f, gpu_ms = 0.f;
+    void startCpuTimer() { arm(CPU, "CPU"); cpu_begin_ = clock::now(); }
+    void endCpuTimer() {
+        const auto stop = clock::now();
+        disarm(CPU, "CPU");
+        last_ms_[CPU] = std::chrono::duration<float, std::milli>(stop - cpu_begin_).count();
+    }
+    void startGpuTimer() { arm(GPU, "GPU"); cudaEventRecord(gpu_begin_); }
+    void endGpuTimer() {
+        cudaEventRecord(gpu_end_);
+        cudaEventSynchronize(gpu_end_);
+        disarm(GPU, "GPU");
+        cudaEventElapsedTime(&last_ms_[GPU], gpu_begin_, gpu_end_);
+    }
+    float getCpuElapsedTimeForPreviousOperation() { return last_ms_[CPU]; }
+    float getGpuElapsedTimeForPreviousOperation() { return last_ms_[GPU]; }
 };
 }  // namespace Common

@@ -9,6 +9,6 @@ There is no CPU fallback: loading fails loudly when the library is missing.
 """
 from .binding import Lib, SfmError, load_library, lib_path  # noqa: F401
 from .image_pair import ImagePair, BatchedPairs  # noqa: F401
-from . import sharding  # noqa: F401
+from . import sharding, synthetic  # noqa: F401
 
 __all__ = ["Lib", "SfmError", "load_library", "lib_path", "ImagePair", "BatchedPairs"]

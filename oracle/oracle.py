@@ -1,8 +1,9 @@
 """fp64 CPU restatement of the reference hot path (TEST INFRASTRUCTURE ONLY).
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
-reference legs may import this module.  The product path (cuda-sfm_b200/) never
-does: it fails loudly when the CUDA library is missing.
+Only tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference
+legs and the checker-side dev tools (tools/gpu_diag.py, tools/reference_baselines.py)
+may import this module.  The product path (cuda-sfm_b200/) never does: it fails
+loudly when the CUDA library is missing.
 
 Reference: Black-Phoenix/CUDA-SfM, files under SfM/.  Each function cites the
 file:line whose *stated* algorithm it restates.  Where the reference's code is
@@ -25,73 +26,20 @@ import numpy as np
 MASK64 = (1 << 64) - 1
 
 # --------------------------------------------------------------------------
-# Camera + synthetic scene (reference intrinsics: src/main.cpp:292-297)
+# Camera + synthetic scene: input generation lives with the host code
+# (cuda-sfm_b200/synthetic.py) so that the measured arm of bench.py never imports
+# this checker; re-exported here for the tests.
 # --------------------------------------------------------------------------
-F_REF = 2360.0
-W_REF, H_REF = 720, 576
+import importlib.util as _ilu
+import os as _os
 
-
-def reference_K(w: int = W_REF, h: int = H_REF):
-    """K and K^-1 exactly as src/main.cpp:292-297 builds them (fp32)."""
-    K = np.array([[F_REF, 0, w / 2.0], [0, F_REF, h / 2.0], [0, 0, 1]], dtype=np.float32)
-    Kinv = np.array(
-        [[1.0 / F_REF, 0, -(w / 2.0) / F_REF], [0, 1.0 / F_REF, -(h / 2.0) / F_REF], [0, 0, 1]],
-        dtype=np.float32,
-    )
-    return K, Kinv
-
-
-def _rot(axis, deg):
-    a = np.asarray(axis, float)
-    a = a / np.linalg.norm(a)
-    t = np.deg2rad(deg)
-    Kx = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
-    return np.eye(3) + np.sin(t) * Kx + (1 - np.cos(t)) * Kx @ Kx
-
-
-def synthetic_pair(n: int, outlier_frac: float = 0.3, noise_px: float = 1.0, seed: int = 1234):
-    """Two-view scene of BASELINE.json configs 2-5.
-
-    Camera 1 = [I|0]; camera 2: X2 = R X + t with R = 10 degrees about
-    (0.1, 1, 0.05) verging towards the scene (negative angle: with the positive
-    one the two 720x576 views do not overlap) and unit baseline along
-    (1, 0.05, 0.1).  Depth U[4, 8] baselines.  Gaussian pixel noise on both
-    views; outliers replace the image-2 point by a uniform pixel.
-
-    Returns dict: px (n,4) float32 pixel coords (u1,v1,u2,v2), R, t, is_outlier,
-    X (n,3) ground-truth 3-D points in camera-1 frame.
-    """
-    rng_scene = np.random.Generator(np.random.PCG64(seed))
-    rng_out = np.random.Generator(np.random.PCG64(seed + 1))
-    rng_noise = np.random.Generator(np.random.PCG64(seed + 2))
-    f, cx, cy = F_REF, W_REF / 2.0, H_REF / 2.0
-    R = _rot([0.1, 1.0, 0.05], -10.0)
-    t = np.array([1.0, 0.05, 0.1])
-    t = t / np.linalg.norm(t)
-    chunks, Xs, have = [], [], 0
-    while have < n:
-        m = max(4 * (n - have), 1024)
-        z = rng_scene.uniform(4.0, 8.0, m)
-        x = rng_scene.uniform(-1.2, 1.2, m) * z * (cx / f)
-        y = rng_scene.uniform(-1.2, 1.2, m) * z * (cy / f)
-        X = np.stack([x, y, z], 1)
-        X2 = X @ R.T + t
-        u1 = f * X[:, 0] / X[:, 2] + cx
-        v1 = f * X[:, 1] / X[:, 2] + cy
-        u2 = f * X2[:, 0] / X2[:, 2] + cx
-        v2 = f * X2[:, 1] / X2[:, 2] + cy
-        ok = (u1 >= 0) & (u1 < W_REF) & (v1 >= 0) & (v1 < H_REF) & (u2 >= 0) & (u2 < W_REF) & (v2 >= 0) & (v2 < H_REF) & (X2[:, 2] > 0)
-        chunks.append(np.stack([u1, v1, u2, v2], 1)[ok])
-        Xs.append(X[ok])
-        have += int(ok.sum())
-    px = np.concatenate(chunks)[:n]
-    X = np.concatenate(Xs)[:n]
-    px = px + rng_noise.normal(0.0, noise_px, px.shape)
-    is_out = rng_out.random(n) < outlier_frac
-    k = int(is_out.sum())
-    px[is_out, 2] = rng_out.uniform(0, W_REF, k)
-    px[is_out, 3] = rng_out.uniform(0, H_REF, k)
-    return {"px": px.astype(np.float32), "R": R, "t": t, "is_outlier": is_out, "X": X}
+_spec = _ilu.spec_from_file_location(
+    "sfm_synthetic", _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "cuda-sfm_b200", "synthetic.py"))
+_synthetic = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(_synthetic)
+F_REF, W_REF, H_REF = _synthetic.F_REF, _synthetic.W_REF, _synthetic.H_REF
+reference_K = _synthetic.reference_K
+synthetic_pair = _synthetic.synthetic_pair
 
 
 def normalise_points(px: np.ndarray, Kinv: np.ndarray) -> np.ndarray:

@@ -49,7 +49,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    pkg, O = entry.load_package(), entry.load_oracle()
+    pkg = entry.load_package()
+O = pkg.synthetic          # scenes + intrinsics only: no checker code in these tools
     K, Kinv = O.reference_K()
 
     def emit(**kw):

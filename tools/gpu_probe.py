@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry
 
-pkg, O = entry.load_package(), entry.load_oracle()
+pkg = entry.load_package()
+O = pkg.synthetic          # scenes + intrinsics only: no checker code in these tools
 lib = pkg.load_library()
 K, Kinv = O.reference_K()
 THR = 1e-6

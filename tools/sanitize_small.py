@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry
 
-pkg, O = entry.load_package(), entry.load_oracle()
+pkg = entry.load_package()
+O = pkg.synthetic          # scenes + intrinsics only: no checker code in these tools
 K, Kinv = O.reference_K()
 for n, H, pairs, variant in ((700, 300, 1, -1), (1100, 2500, 2, -1), (520, 1030, 1, 0), (2049, 700, 1, 6), (600, 2100, 1, 3)):
     px = np.stack([O.synthetic_pair(n, seed=3 + b)["px"] for b in range(pairs)])
