@@ -50,7 +50,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = entry.load_package()
-O = pkg.synthetic          # scenes + intrinsics only: no checker code in these tools
+    O = pkg.synthetic          # scenes + intrinsics only: no checker code in this tool
     K, Kinv = O.reference_K()
 
     def emit(**kw):
