@@ -256,7 +256,7 @@ __device__ __forceinline__ void dehomogenise(const float* v, float& X, float& Y,
 __device__ __forceinline__ bool cheirality_compat(const float4& c0, const float* M, float* Minv) {
     float A[16], v[4];
     dlt_matrix(c0.x, c0.y, c0.z, c0.w, M, A);
-    if (!null4_inverse_iteration<8>(A, v)) null4<5>(A, v);     // same solve as triangulate_kernel
+    if (!null4_inverse_iteration<5>(A, v)) null4<5>(A, v);     // same solve as triangulate_kernel
     float X, Y, Z;
     dehomogenise(v, X, Y, Z);
     inv4(M, Minv);
@@ -400,9 +400,9 @@ __global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inl
     if (keep) {
         float A[16], v[4];
         dlt_matrix(p.x, p.y, p.z, p.w, sM, A);
-        // inverse iteration (8 solves on one Cholesky factor); Jacobi only for the
+        // inverse iteration (cross-product start, 5 solves on one Cholesky factor); Jacobi only for the
         // rare point whose two smallest singular values nearly coincide
-        if (!null4_inverse_iteration<8>(A, v)) null4<5>(A, v);
+        if (!null4_inverse_iteration<5>(A, v)) null4<5>(A, v);
         dehomogenise(v, X, Y, Z);
     }
     float* out = s.points + (size_t)b * 4 * s.n_stride;

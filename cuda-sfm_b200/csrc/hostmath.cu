@@ -25,7 +25,7 @@ void sfmb200_host_solve_hypothesis_projector(const float pts[32], float E[9]) {
 
 void sfmb200_host_null4(const float A[16], float x[4]) { null4<5>(A, x); }
 
-int sfmb200_host_null4_fast(const float A[16], float x[4]) { return null4_inverse_iteration<8>(A, x) ? 0 : 1; }
+int sfmb200_host_null4_fast(const float A[16], float x[4]) { return null4_inverse_iteration<5>(A, x) ? 0 : 1; }
 
 int sfmb200_host_inv4(const float m[16], float out[16]) { return inv4(m, out) ? 0 : -1; }
 

@@ -328,7 +328,24 @@ SFM_HD bool null4_inverse_iteration(const float* A, float* x) {
     float d3 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, g[3][3] + eps)));
     d3 = fmaxf(d3, eps);
     float i3 = 1.0f / sqrtf(d3);
-    float v0 = 0.5f, v1 = 0.5f, v2 = 0.5f, v3 = 0.5f;
+    // Start from the exact null vector of the first three rows (A has rows
+    // (-1,0,x1,0), (0,-1,y1,0) in DLT use, but any A works): generalised cross
+    // product of rows 0..2.  For an inlier this is already the answer to within
+    // the noise, so the iteration only has to remove an O(1e-2) component.
+    float v0, v1, v2, v3;
+    {
+        const float *r0 = A, *r1 = A + 4, *r2 = A + 8;
+        float m01 = r0[0] * r1[1] - r0[1] * r1[0], m02 = r0[0] * r1[2] - r0[2] * r1[0], m03 = r0[0] * r1[3] - r0[3] * r1[0];
+        float m12 = r0[1] * r1[2] - r0[2] * r1[1], m13 = r0[1] * r1[3] - r0[3] * r1[1], m23 = r0[2] * r1[3] - r0[3] * r1[2];
+        v0 = -(r2[1] * m23 - r2[2] * m13 + r2[3] * m12);
+        v1 = (r2[0] * m23 - r2[2] * m03 + r2[3] * m02);
+        v2 = -(r2[0] * m13 - r2[1] * m03 + r2[3] * m01);
+        v3 = (r2[0] * m12 - r2[1] * m02 + r2[2] * m01);
+        float n2 = fmaf(v3, v3, fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
+        bool ok = n2 > 1e-30f;
+        float n = ok ? 1.0f / sqrtf(n2) : 0.0f;
+        v0 = ok ? v0 * n : 0.5f; v1 = ok ? v1 * n : 0.5f; v2 = ok ? v2 * n : 0.5f; v3 = ok ? v3 * n : 0.5f;
+    }
     float diff2 = 1.0f;
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
