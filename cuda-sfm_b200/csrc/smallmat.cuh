@@ -59,6 +59,16 @@ SFM_HD void jacobi_angle_fast(float app, float aqq, float apq, float& c, float& 
 #endif
 }
 
+// 1/sqrt(x): MUFU.RSQ (2 ulp) on the device, exact on the host.  Only for places
+// where the result feeds a self-correcting iteration or a normalisation.
+SFM_HD float sfm_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
 // Givens pair (c, s) with c*a + s*b = r >= 0 and -s*a + c*b = 0.
 SFM_HD void givens(float a, float b, float& c, float& s) {
     float r2 = fmaf(a, a, b * b);
@@ -315,19 +325,19 @@ SFM_HD bool null4_inverse_iteration(const float* A, float* x) {
     const float eps = 1e-7f * (g[0][0] + g[1][1] + g[2][2] + g[3][3]);
     // Cholesky, inverse diagonal kept
     float d0 = g[0][0] + eps;
-    float i0 = 1.0f / sqrtf(d0);
+    float i0 = sfm_rsqrt(d0);
     float l10 = g[0][1] * i0, l20 = g[0][2] * i0, l30 = g[0][3] * i0;
     float d1 = fmaf(-l10, l10, g[1][1] + eps);
     d1 = fmaxf(d1, eps);
-    float i1 = 1.0f / sqrtf(d1);
+    float i1 = sfm_rsqrt(d1);
     float l21 = fmaf(-l20, l10, g[1][2]) * i1, l31 = fmaf(-l30, l10, g[1][3]) * i1;
     float d2 = fmaf(-l21, l21, fmaf(-l20, l20, g[2][2] + eps));
     d2 = fmaxf(d2, eps);
-    float i2 = 1.0f / sqrtf(d2);
+    float i2 = sfm_rsqrt(d2);
     float l32 = fmaf(-l31, l21, fmaf(-l30, l20, g[2][3])) * i2;
     float d3 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, g[3][3] + eps)));
     d3 = fmaxf(d3, eps);
-    float i3 = 1.0f / sqrtf(d3);
+    float i3 = sfm_rsqrt(d3);
     // Start from the exact null vector of the first three rows (A has rows
     // (-1,0,x1,0), (0,-1,y1,0) in DLT use, but any A works): generalised cross
     // product of rows 0..2.  For an inlier this is already the answer to within
@@ -343,7 +353,7 @@ SFM_HD bool null4_inverse_iteration(const float* A, float* x) {
         v3 = (r2[0] * m12 - r2[1] * m02 + r2[2] * m01);
         float n2 = fmaf(v3, v3, fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
         bool ok = n2 > 1e-30f;
-        float n = ok ? 1.0f / sqrtf(n2) : 0.0f;
+        float n = ok ? sfm_rsqrt(n2) : 0.0f;
         v0 = ok ? v0 * n : 0.5f; v1 = ok ? v1 * n : 0.5f; v2 = ok ? v2 * n : 0.5f; v3 = ok ? v3 * n : 0.5f;
     }
     float diff2 = 1.0f;
@@ -357,7 +367,7 @@ SFM_HD bool null4_inverse_iteration(const float* A, float* x) {
         float z2 = fmaf(-l32, z3, y2) * i2;
         float z1 = fmaf(-l31, z3, fmaf(-l21, z2, y1)) * i1;
         float z0 = fmaf(-l30, z3, fmaf(-l20, z2, fmaf(-l10, z1, y0))) * i0;
-        float n = 1.0f / sqrtf(fmaf(z3, z3, fmaf(z2, z2, fmaf(z1, z1, z0 * z0))));
+        float n = sfm_rsqrt(fmaf(z3, z3, fmaf(z2, z2, fmaf(z1, z1, z0 * z0))));
         z0 *= n; z1 *= n; z2 *= n; z3 *= n;
         float e0 = z0 - v0, e1 = z1 - v1, e2 = z2 - v2, e3 = z3 - v3;
         diff2 = fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0)));
