@@ -43,6 +43,7 @@ SIGNATURES = {
     "sfmb200_estimate_e_slice": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float]),
     "sfmb200_best_buffer": (C.c_int, [_vp, C.POINTER(_vp)]),
     "sfmb200_adopt_best": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64]),
+    "sfmb200_find_homography": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_float, _vp, _vp]),
     "sfmb200_refine_e": (C.c_int, [_vp, C.c_int]),
     "sfmb200_get_refit_iterations": (C.c_int, [_vp, _vp]),
     "sfmb200_pose_candidates": (C.c_int, [_vp]),

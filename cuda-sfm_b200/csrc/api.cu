@@ -3,6 +3,7 @@
 // pre-allocated arena (the reference does ~21 cudaMalloc + ~19 cudaFree + >=4
 // device syncs per estimateE call, SfM/sfm.cu:94-236).
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -40,6 +41,7 @@ struct sfmb200_handle {
     int score_variant;
     int tri_inliers_only;
     int hyp_solver;
+    int model;             // what s.E holds: 0 essential matrix, 1 homography (find_homography)
     // state of the last estimate
     int H;            // hypotheses in the local slice
     int h_begin;
@@ -330,6 +332,44 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     h->have_candidates = true;
     h->have_E = true;
     h->have_pose = false;
+    h->model = 0;
+    return SFMB200_OK;
+}
+
+int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh, float* h_H, int32_t* h_matches) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->have_points) return fail(SFMB200_ERR_STATE, "find_homography before set_points%s");
+    if (loops < 1 || loops > h->s.h_max) return fail(SFMB200_ERR_ARG, "loops out of range / above max_hypotheses%s");
+    if (!(thresh > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
+    const float thr2 = thresh * thresh;
+    h->H = loops;
+    h->h_begin = 0;
+    h->thr = thr2;
+    h->plan = make_score_plan_homography(h->s.B, h->s.n, loops);
+    launch_hypgen(h->s, nullptr, (long long)loops * 8, loops, 0, seed, 2, h->stream);
+    CKL();
+    launch_score_homography(h->s, h->plan, loops, 0, thr2, h->stream);
+    CKL();
+    launch_select(h->s, 0, h->stream);
+    CKL();
+    h->launches += 3;
+    h->have_candidates = true;
+    h->have_E = false;        // s.E holds a homography now: the pose stages must not consume it
+    h->have_pose = false;
+    h->model = 1;
+    if (h_H) CK(cudaMemcpyAsync(h_H, h->s.E, (size_t)h->s.B * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_matches) CK(cudaMemcpyAsync(h_matches, h->s.best_count, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h_H || h_matches) CK(cudaStreamSynchronize(h->stream));
+    if (h_H) {
+        // CudaSift returns h8 = 1 (matching.cu:907-948 solves for 8 parameters); do the same when h8 is not ~0
+        for (int b = 0; b < h->s.B; b++) {
+            float* Hm = h_H + 9 * b;
+            if (fabsf(Hm[8]) > 1e-12f) {
+                float inv = 1.0f / Hm[8];
+                for (int i = 0; i < 9; i++) Hm[i] *= inv;
+            }
+        }
+    }
     return SFMB200_OK;
 }
 int sfmb200_estimate_e(sfmb200_t* h, const int32_t* d_idx, int H, uint64_t seed, float thr) {
@@ -508,6 +548,7 @@ int sfmb200_set_E(sfmb200_t* h, const float* h_E) {
     CK(cudaStreamSynchronize(h->stream));
     h->have_E = true;
     h->have_pose = false;
+    h->model = 0;
     if (!(h->thr > 0)) h->thr = 1e-6f;
     return SFMB200_OK;
 }
@@ -584,8 +625,8 @@ int sfmb200_get_X(sfmb200_t* h, int pair, int image, float* d_X) {
 int sfmb200_get_inlier_mask(sfmb200_t* h, int pair, uint8_t* d_mask) {
     int rc = check_pair(h, pair, d_mask);
     if (rc) return rc;
-    if (!h->have_E || !h->have_points) return fail(SFMB200_ERR_STATE, "no essential matrix yet%s");
-    launch_inlier_mask(h->s, pair, h->thr > 0 ? h->thr : 1e-6f, d_mask, h->stream);
+    if (!(h->have_E || h->model == 1) || !h->have_points) return fail(SFMB200_ERR_STATE, "no model yet%s");
+    launch_inlier_mask(h->s, pair, h->thr > 0 ? h->thr : 1e-6f, h->model, d_mask, h->stream);
     CKL();
     h->launches++;
     return SFMB200_OK;

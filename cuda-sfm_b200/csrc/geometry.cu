@@ -456,17 +456,20 @@ void launch_export_X(const DeviceState& s, int pair, int image, float* d_out, cu
     export_X_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, image, d_out);
 }
 
-__global__ void inlier_mask_kernel(DeviceState s, int pair, float thr, unsigned char* mask) {
+// model 0: Sampson test of the essential matrix in s.E; model 1: transfer-error test of the
+// homography in s.E (thr = squared threshold)
+__global__ void inlier_mask_kernel(DeviceState s, int pair, float thr, int model, unsigned char* mask) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
     float e[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) e[k] = s.E[(size_t)pair * 9 + k];
     float4 p = s.corr[(size_t)pair * s.n_stride + i];
-    mask[i] = sampson_d(e, p.x, p.y, p.z, p.w, -thr) < 0.0f ? 1 : 0;
+    float d = model == 0 ? sampson_d(e, p.x, p.y, p.z, p.w, -thr) : homography_d(e, p.x, p.y, p.z, p.w, -thr);
+    mask[i] = d < 0.0f ? 1 : 0;
 }
-void launch_inlier_mask(const DeviceState& s, int pair, float thr, unsigned char* d_mask, cudaStream_t st) {
-    inlier_mask_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, thr, d_mask);
+void launch_inlier_mask(const DeviceState& s, int pair, float thr, int model, unsigned char* d_mask, cudaStream_t st) {
+    inlier_mask_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, thr, model, d_mask);
 }
 
 }  // namespace sfmb200

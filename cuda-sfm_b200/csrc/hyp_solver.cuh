@@ -368,6 +368,116 @@ SFM_HD void solve_hypothesis_projector(const Corr* pts, float* E) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// 4-point homography hypothesis (replaces CudaSift's
+// ComputeHomographies, matching.cu:907-948, an 8x8 Gaussian elimination with
+// h8 = 1): Hartley-normalise, 8x9 DLT rows, null vector through the same 8x8
+// Cholesky projector as the essential-matrix solver, de-normalise
+// H = T2^-1 Hh T1, unit Frobenius norm.  Maps image-1 points to image-2 points.
+// ---------------------------------------------------------------------------
+SFM_HD void hartley4(const float* x, const float* y, float& s, float& cx, float& cy) {
+    cx = 0.25f * (x[0] + x[1] + x[2] + x[3]);
+    cy = 0.25f * (y[0] + y[1] + y[2] + y[3]);
+    float d = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float dx = x[i] - cx, dy = y[i] - cy;
+        d += sqrtf(fmaf(dx, dx, dy * dy));
+    }
+    s = 5.65685425f / d;   // sqrt(2) / (d / 4)
+}
+SFM_HD void solve_homography(const Corr* pts, float* Hm) {
+    float x1[4], y1[4], x2[4], y2[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { x1[i] = pts[i].x1; y1[i] = pts[i].y1; x2[i] = pts[i].x2; y2[i] = pts[i].y2; }
+    float s1, c1x, c1y, s2, c2x, c2y;
+    hartley4(x1, y1, s1, c1x, c1y);
+    hartley4(x2, y2, s2, c2x, c2y);
+    float A[8][9];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float x = s1 * (x1[i] - c1x), y = s1 * (y1[i] - c1y);
+        float u = s2 * (x2[i] - c2x), v = s2 * (y2[i] - c2y);
+        float* r0 = A[2 * i];
+        float* r1 = A[2 * i + 1];
+        r0[0] = -x; r0[1] = -y; r0[2] = -1.0f; r0[3] = 0.0f; r0[4] = 0.0f; r0[5] = 0.0f; r0[6] = u * x; r0[7] = u * y; r0[8] = u;
+        r1[0] = 0.0f; r1[1] = 0.0f; r1[2] = 0.0f; r1[3] = -x; r1[4] = -y; r1[5] = -1.0f; r1[6] = v * x; r1[7] = v * y; r1[8] = v;
+    }
+    float k[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            float acc = A[i][0] * A[j][0];
+#pragma unroll
+            for (int c = 1; c < 9; c++) acc = fmaf(A[i][c], A[j][c], acc);
+            k[i][j] = acc;
+        }
+    Chol8 ch;
+    chol8_factor(k, ch);
+    int best = 0;
+    float bestv = -1.0f;
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+        float col[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) col[r] = A[r][c];
+        float v = 1.0f - chol8_quad(ch, col);
+        if (v > bestv) { bestv = v; best = c; }
+    }
+    float e[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) e[c] = (c == best) ? 1.0f : 0.0f;
+#pragma unroll 1
+    for (int it = 0; it < 3; it++) {
+        float y[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            float res = A[r][0] * e[0];
+#pragma unroll
+            for (int c = 1; c < 9; c++) res = fmaf(A[r][c], e[c], res);
+            y[r] = res;
+        }
+        chol8_solve(ch, y);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 9; c++) e[c] = fmaf(-A[r][c], y[r], e[c]);
+        float n2 = e[0] * e[0];
+#pragma unroll
+        for (int c = 1; c < 9; c++) n2 = fmaf(e[c], e[c], n2);
+        float inv = 1.0f / sqrtf(n2);
+#pragma unroll
+        for (int c = 0; c < 9; c++) e[c] *= inv;
+    }
+    // H = T2^-1 Hh T1 with T = [s 0 -s cx; 0 s -s cy; 0 0 1], T^-1 = [1/s 0 cx; 0 1/s cy; 0 0 1]
+    float M[9];                       // M = Hh T1
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        M[3 * i + 0] = e[3 * i + 0] * s1;
+        M[3 * i + 1] = e[3 * i + 1] * s1;
+        M[3 * i + 2] = fmaf(-s1 * c1x, e[3 * i + 0], fmaf(-s1 * c1y, e[3 * i + 1], e[3 * i + 2]));
+    }
+    const float is2 = 1.0f / s2;
+    float n2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        Hm[0 + j] = fmaf(c2x, M[6 + j], is2 * M[0 + j]);
+        Hm[3 + j] = fmaf(c2y, M[6 + j], is2 * M[3 + j]);
+        Hm[6 + j] = M[6 + j];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) n2 = fmaf(Hm[i], Hm[i], n2);
+    float inv = 1.0f / sqrtf(n2);
+    bool finite = ch.ok;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { Hm[i] *= inv; finite = finite && (fabsf(Hm[i]) <= 3.0e38f); }
+    if (!finite) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) Hm[i] = 0.0f;
+    }
+}
+
 // Counter-based sample-index generator shared (bit-exactly) with the oracle
 // (oracle/oracle.py: sample_indices).  Hypothesis h of a pair draws 8 distinct
 // indices in [0, n): splitmix64 of (seed, h, draw counter), mapped with a

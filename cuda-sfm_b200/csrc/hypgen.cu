@@ -58,7 +58,8 @@ hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pa
     bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b,
                           (long long)h_offset + (live ? j : 0), pts);
     if (SOLVER == 0) solve_hypothesis<SYNC>(pts, E);
-    else solve_hypothesis_projector(pts, E);
+    else if (SOLVER == 1) solve_hypothesis_projector(pts, E);
+    else solve_homography(pts, E);                      // first 4 of the 8 sampled correspondences
     if (!live) return;
     float* out = s.Ecand + (size_t)b * 9 * s.h_stride + j;
 #pragma unroll
@@ -67,15 +68,18 @@ hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pa
 }
 
 // solver 0: 9x9 Jacobi eigensolve (255 registers, 2 CTAs of 128 threads per SM);
-// solver 1: 8x8 Cholesky projector (see hyp_solver.cuh), 4 CTAs of 128 threads per SM.
+// solver 1: 8x8 Cholesky projector (see hyp_solver.cuh), 4 CTAs of 128 threads per SM;
+// solver 2: 4-point homography through the same projector (find_homography).
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
                    unsigned long long seed, int solver, cudaStream_t st) {
     int need = H > s.tiles_max ? H : s.tiles_max;
     dim3 grid((need + 127) / 128, s.B);
     if (solver == 0)
         hypgen_kernel<128, 2, 0, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
-    else
+    else if (solver == 1)
         hypgen_kernel<128, 4, 0, 1><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+    else
+        hypgen_kernel<128, 4, 0, 2><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
 }
 
 // Multi-GPU single-pair case: after the (count, index) all-reduce every rank
@@ -94,7 +98,8 @@ __global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_i
     float E[9];
     bool ok = load_sample(corr, s.n, rows, seed + 0x632BE59BD9B4E019ull * (unsigned long long)b, (long long)hg, pts);
     if (solver == 0) solve_hypothesis<0>(pts, E);      // same code path as hypgen_kernel: bit-identical E
-    else solve_hypothesis_projector(pts, E);
+    else if (solver == 1) solve_hypothesis_projector(pts, E);
+    else solve_homography(pts, E);
 #pragma unroll
     for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = ok ? E[k] : 0.0f;
     s.best_idx[b] = (int)hg;

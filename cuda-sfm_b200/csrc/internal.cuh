@@ -70,6 +70,8 @@ void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pai
 ScorePlan make_score_plan(int B, int n, int H, int variant_override);
 int score_num_variants();
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
+void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st);
+ScorePlan make_score_plan_homography(int B, int n, int H);
 void launch_select(const DeviceState& s, int h_offset, cudaStream_t st);
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride,
                        unsigned long long seed, int solver, cudaStream_t st);
@@ -80,7 +82,7 @@ void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaS
 void launch_vbo(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, cudaStream_t st);
 void launch_export_ecand(const DeviceState& s, int pair, int H, float* d_out_Hx9, cudaStream_t st);
 void launch_export_X(const DeviceState& s, int pair, int image, float* d_out_3xN, cudaStream_t st);
-void launch_inlier_mask(const DeviceState& s, int pair, float thr, unsigned char* d_mask, cudaStream_t st);
+void launch_inlier_mask(const DeviceState& s, int pair, float thr, int model, unsigned char* d_mask, cudaStream_t st);
 
 // FP32 pipe micro-benchmark (bench/roofline denominator): returns lane-FMAs issued.
 double launch_fma_probe(int mode, int iters, cudaStream_t st, float* d_sink);

@@ -33,4 +33,38 @@ __device__ __forceinline__ float2 sampson_d2(const float2* e, float2 x1, float2 
     return __ffma2_rn(den, nthr, __fmul2_rn(num, num));
 }
 
+// Homography model (CudaSift's TestHomographies, matching.cu:953-996):
+// one-sided transfer error of x1 -> x2 under H, division-free exactly like the original:
+//   d = (x2*W - X)^2 + (y2*W - Y)^2 - thr^2 * W^2,  (X, Y, W) = H (x1, y1, 1);  inlier <=> d < 0.
+// nthr is -(thr^2).
+__device__ __forceinline__ float homography_d(const float* e, float x1, float y1, float x2, float y2, float nthr) {
+    float X = fmaf(e[0], x1, fmaf(e[1], y1, e[2]));
+    float Y = fmaf(e[3], x1, fmaf(e[4], y1, e[5]));
+    float W = fmaf(e[6], x1, fmaf(e[7], y1, e[8]));
+    float ex = fmaf(x2, W, -X);
+    float ey = fmaf(y2, W, -Y);
+    float err2 = fmaf(ex, ex, ey * ey);
+    return fmaf(W * W, nthr, err2);
+}
+__device__ __forceinline__ float2 homography_d2(const float2* e, float2 x1, float2 y1, float2 x2, float2 y2, float2 nthr) {
+    float2 X = __ffma2_rn(e[0], x1, __ffma2_rn(e[1], y1, e[2]));
+    float2 Y = __ffma2_rn(e[3], x1, __ffma2_rn(e[4], y1, e[5]));
+    float2 W = __ffma2_rn(e[6], x1, __ffma2_rn(e[7], y1, e[8]));
+    float2 nX = make_float2(-X.x, -X.y), nY = make_float2(-Y.x, -Y.y);
+    float2 ex = __ffma2_rn(x2, W, nX);
+    float2 ey = __ffma2_rn(y2, W, nY);
+    float2 err2 = __ffma2_rn(ex, ex, __fmul2_rn(ey, ey));
+    return __ffma2_rn(__fmul2_rn(W, W), nthr, err2);
+}
+
+// MODEL 0: essential matrix / Sampson; MODEL 1: homography / transfer error.
+template <int MODEL>
+__device__ __forceinline__ float model_d(const float* e, float x1, float y1, float x2, float y2, float nthr) {
+    return MODEL == 0 ? sampson_d(e, x1, y1, x2, y2, nthr) : homography_d(e, x1, y1, x2, y2, nthr);
+}
+template <int MODEL>
+__device__ __forceinline__ float2 model_d2(const float2* e, float2 x1, float2 y1, float2 x2, float2 y2, float2 nthr) {
+    return MODEL == 0 ? sampson_d2(e, x1, y1, x2, y2, nthr) : homography_d2(e, x1, y1, x2, y2, nthr);
+}
+
 }  // namespace sfmb200

@@ -127,7 +127,7 @@ struct ChunkDesc {
     int seg_pts;       // points of the whole segment (valid when seg_last)
 };
 
-template <int HPT, bool PACKED, int THREADS, int MINB>
+template <int HPT, bool PACKED, int THREADS, int MINB, int MODEL>
 __global__ void __launch_bounds__(THREADS, MINB)
 score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, int n_units, float thr) {
     constexpr int HPC = HPT * THREADS;
@@ -214,7 +214,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
                 float2 x2 = make_float2(q.x, q.y), y2 = make_float2(q.z, q.w);
 #pragma unroll
                 for (int j = 0; j < HPT / 2; j++) {
-                    float2 dd = sampson_d2(e2[j], x1, y1, x2, y2, nthr2);
+                    float2 dd = model_d2<MODEL>(e2[j], x1, y1, x2, y2, nthr2);
                     cnt[2 * j] += __float_as_uint(dd.x) >> 31;
                     cnt[2 * j + 1] += __float_as_uint(dd.y) >> 31;
                 }
@@ -225,7 +225,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
                 float4 p = pb[i];
 #pragma unroll
                 for (int j = 0; j < HPT; j++) {
-                    float dd = sampson_d(e[j], p.x, p.y, p.z, p.w, nthr);
+                    float dd = model_d<MODEL>(e[j], p.x, p.y, p.z, p.w, nthr);
                     cnt[j] += __float_as_uint(dd) >> 31;
                 }
             }
@@ -313,12 +313,12 @@ constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 template <int HPT, bool PACKED, int THREADS, int MINB>
 static void launch_one(const DeviceState& s, int ctas, int H, int h_offset, int T, long long units, int n_units, float thr,
                        cudaStream_t st) {
-    score_kernel<HPT, PACKED, THREADS, MINB><<<ctas, THREADS, 0, st>>>(s, H, h_offset, T, units, n_units, thr);
+    score_kernel<HPT, PACKED, THREADS, MINB, 0><<<ctas, THREADS, 0, st>>>(s, H, h_offset, T, units, n_units, thr);
 }
 template <int HPT, bool PACKED, int THREADS, int MINB>
 static int occupancy_one() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<HPT, PACKED, THREADS, MINB>, THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_kernel<HPT, PACKED, THREADS, MINB, 0>, THREADS, 0);
     return n > 0 ? n : 1;
 }
 #define SFM_FOR_VARIANT(v, CALL)                     \
@@ -373,6 +373,23 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     if (ctas < 1) ctas = 1;
     p.ctas = (int)ctas;
     return p;
+}
+
+// Homography model: the same kernel with the transfer-error test; three tile sizes are enough
+// (thr here is the SQUARED pixel / coordinate threshold).
+ScorePlan make_score_plan_homography(int B, int n, int H) {
+    return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9));     // tiles of 2048 / 512 / 256 hypotheses
+}
+void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st) {
+    const int v = plan.variant;
+    const bool big = kVariants[v].hpt * kVariants[v].threads >= 2048, mid = kVariants[v].hpt * kVariants[v].threads >= 512;
+    if (big) {
+        score_kernel<8, true, 256, 1, 1><<<plan.ctas, 256, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr2);
+    } else if (mid) {
+        score_kernel<4, true, 128, 1, 1><<<plan.ctas, 128, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr2);
+    } else {
+        score_kernel<2, false, 128, 1, 1><<<plan.ctas, 128, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr2);
+    }
 }
 
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {

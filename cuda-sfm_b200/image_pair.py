@@ -126,6 +126,14 @@ class BatchedPairs:
     def adopt_best(self, H_total: int, seed: int = 0, d_idx=None):
         self.lib.call("sfmb200_adopt_best", self._h, _dptr(d_idx), H_total, C.c_uint64(seed))
 
+    def find_homography(self, loops: int, seed: int = 0, thresh: float = 5.0):
+        """CudaSift FindHomography semantics on this handle's correspondences; returns (H [pairs,3,3], matches [pairs])."""
+        Hm = np.empty((self.pairs, 3, 3), np.float32)
+        cnt = np.empty(self.pairs, np.int32)
+        self.lib.call("sfmb200_find_homography", self._h, loops, C.c_uint64(seed), C.c_float(thresh), _hptr(Hm), _hptr(cnt))
+        self.H = loops
+        return Hm, cnt
+
     def refine_e(self, iterations: int = 4) -> np.ndarray:
         """LO-RANSAC refit on the inlier set; returns accepted refits per pair."""
         self.lib.call("sfmb200_refine_e", self._h, iterations)

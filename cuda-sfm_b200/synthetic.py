@@ -71,3 +71,35 @@ def synthetic_pair(n: int, outlier_frac: float = 0.3, noise_px: float = 1.0, see
     px[is_out, 2] = rng_out.uniform(0, W_REF, k)
     px[is_out, 3] = rng_out.uniform(0, H_REF, k)
     return {"px": px.astype(np.float32), "R": R, "t": t, "is_outlier": is_out, "X": X}
+
+
+def planar_pair(n: int, outlier_frac: float = 0.3, noise_px: float = 0.5, seed: int = 7):
+    """Correspondences of a planar scene (points on a slanted plane seen by the same two
+    cameras as synthetic_pair): image 2 = H(image 1) + noise, plus uniform outliers.
+    Returns dict: px (n,4) float32, H (3,3) pixel-space ground-truth homography (h8 = 1), is_outlier."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f, cx, cy = F_REF, W_REF / 2.0, H_REF / 2.0
+    K = np.array([[f, 0, cx], [0, f, cy], [0, 0, 1.0]])
+    R = _rot([0.1, 1.0, 0.05], -10.0)
+    t = np.array([1.0, 0.05, 0.1])
+    t = t / np.linalg.norm(t)
+    nrm = np.array([0.15, -0.1, 1.0])
+    nrm = nrm / np.linalg.norm(nrm)
+    d = 6.0                                               # plane n.X = d in camera-1 frame
+    Hm = K @ (R + np.outer(t, nrm) / d) @ np.linalg.inv(K)
+    Hm = Hm / Hm[2, 2]
+    pts = []
+    while sum(len(p) for p in pts) < n:
+        u = rng.uniform(0, W_REF, 4 * n)
+        v = rng.uniform(0, H_REF, 4 * n)
+        q = Hm @ np.stack([u, v, np.ones_like(u)])
+        u2, v2 = q[0] / q[2], q[1] / q[2]
+        ok = (u2 >= 0) & (u2 < W_REF) & (v2 >= 0) & (v2 < H_REF)
+        pts.append(np.stack([u, v, u2, v2], 1)[ok])
+    px = np.concatenate(pts)[:n]
+    px[:, 2:] += rng.normal(0.0, noise_px, (n, 2))
+    is_out = rng.random(n) < outlier_frac
+    k = int(is_out.sum())
+    px[is_out, 2] = rng.uniform(0, W_REF, k)
+    px[is_out, 3] = rng.uniform(0, H_REF, k)
+    return {"px": px.astype(np.float32), "H": Hm, "is_outlier": is_out}

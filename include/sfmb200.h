@@ -103,6 +103,16 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
 int sfmb200_best_buffer(sfmb200_t* h, uint64_t** d_best);
 int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed);
 
+/* ---- homography RANSAC: CudaSift's FindHomography (CudaSift/cudaSift.h:43,
+ * matching.cu:1000-1087; the outlier pre-filter the reference's main.cpp:283-290 has commented out) on the
+ * same hypothesis / scoring skeleton.  `loops` 4-point hypotheses per pair (device-drawn from `seed`), one-sided
+ * transfer error of image-1 -> image-2 points under H below `thresh` (same division-free test as
+ * TestHomographies, matching.cu:953-996), first maximum wins.  Coordinates and threshold are in whatever
+ * units ingest produced: create the handle with K = Kinv = identity for CudaSift's pixel-space semantics.
+ * h_H: host [pairs][9] row-major with h8 = 1 like CudaSift; h_matches: inlier counts.  Afterwards
+ * get_inlier_mask / get_inlier_counts / get_best refer to the homography. */
+int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh, float* h_H, int32_t* h_matches);
+
 /* ---- local optimisation (not in the reference; its README.md:65-69 lists it as future work,
  * SURVEY.md 8f rank 2): up to `iterations` rounds of { normalised 8-point fit on ALL inliers of
  * the current E through the 9x9 Jacobi eigensolve, rank-2 projection, re-score }, each accepted

@@ -40,6 +40,7 @@ _spec.loader.exec_module(_synthetic)
 F_REF, W_REF, H_REF = _synthetic.F_REF, _synthetic.W_REF, _synthetic.H_REF
 reference_K = _synthetic.reference_K
 synthetic_pair = _synthetic.synthetic_pair
+planar_pair = _synthetic.planar_pair
 
 
 def normalise_points(px: np.ndarray, Kinv: np.ndarray) -> np.ndarray:
@@ -238,6 +239,58 @@ def refit_on_inliers(x: np.ndarray, E0: np.ndarray, thr: float = 1e-6, iteration
         if c > count:
             E, count, accepted = model, c, accepted + 1
     return E, count, accepted
+
+
+# --------------------------------------------------------------------------
+# Homography RANSAC (CudaSift FindHomography: ComputeHomographies matching.cu:907-948,
+# TestHomographies 953-996, selection 1063-1071) - SURVEY.md 8f rank 3
+# --------------------------------------------------------------------------
+def homography_hypotheses(x: np.ndarray, idx4: np.ndarray) -> np.ndarray:
+    """H candidates (L,3,3) in fp64 mapping image-1 to image-2 points, from 4
+    correspondences each (idx4: (L,4)); exact 4-point DLT null vector, unit
+    Frobenius norm (CudaSift solves the same system with h8 = 1)."""
+    p = x[idx4].astype(np.float64)                       # (L,4,4)
+    X, Y, U, V = p[..., 0], p[..., 1], p[..., 2], p[..., 3]
+    Z, O1 = np.zeros_like(X), np.ones_like(X)
+    r0 = np.stack([-X, -Y, -O1, Z, Z, Z, U * X, U * Y, U], -1)
+    r1 = np.stack([Z, Z, Z, -X, -Y, -O1, V * X, V * Y, V], -1)
+    A = np.concatenate([r0, r1], 1)                      # (L,8,9)
+    _, _, Vt = np.linalg.svd(A)
+    Hm = Vt[:, -1, :]
+    return (Hm / np.linalg.norm(Hm, axis=1, keepdims=True)).reshape(-1, 3, 3)
+
+
+def homography_mask_f32(Hm: np.ndarray, x: np.ndarray, thresh: float) -> np.ndarray:
+    """Inliers under the transfer-error test with the kernels' fp32 fma tree
+    (csrc/sampson.cuh: homography_d), emulated like sampson_mask_f32."""
+    f32, f64 = np.float32, np.float64
+    e = Hm.reshape(9).astype(f32)
+    x1, y1, x2, y2 = (x[:, i].astype(f32) for i in range(4))
+
+    def fma(a, b, c):
+        return (a.astype(f64) * np.asarray(b, f64) + np.asarray(c, f64)).astype(f32)
+
+    X = fma(x1, e[0], fma(y1, e[1], np.full_like(x1, e[2])))
+    Y = fma(x1, e[3], fma(y1, e[4], np.full_like(x1, e[5])))
+    W = fma(x1, e[6], fma(y1, e[7], np.full_like(x1, e[8])))
+    ex = fma(x2, W, -X)
+    ey = fma(y2, W, -Y)
+    err2 = fma(ex, ex, (ey * ey).astype(f32))
+    nthr = -(f32(thresh) * f32(thresh))
+    d = fma((W * W).astype(f32), nthr, err2)
+    return d < 0
+
+
+def homography_counts(Hm: np.ndarray, x: np.ndarray, thresh: float, band: float = 1e-4):
+    """fp64 counts of the same test + borderline counts (|d| <= band * thr^2 W^2)."""
+    Hm = Hm.reshape(-1, 3, 3).astype(np.float64)
+    x1 = np.stack([x[:, 0], x[:, 1], np.ones(len(x))], 0).astype(np.float64)
+    q = Hm @ x1                                           # (L,3,n)
+    ex = x[:, 2][None] * q[:, 2] - q[:, 0]
+    ey = x[:, 3][None] * q[:, 2] - q[:, 1]
+    t = thresh * thresh * q[:, 2] ** 2
+    d = ex * ex + ey * ey - t
+    return (d < 0).sum(1), (np.abs(d) <= band * t + 1e-300).sum(1)
 
 
 def argmax_first(counts: np.ndarray) -> int:

@@ -183,3 +183,19 @@ def test_refit_on_inliers_improves_a_noisy_minimal_hypothesis(O):
     tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
     Etrue = (tx @ R).T[None]
     assert O.e_distance(E1[None], Etrue)[0] < O.e_distance(E[b][None], Etrue)[0]
+
+
+def test_homography_oracle_recovers_planar_ground_truth(O):
+    sc = O.planar_pair(2000, outlier_frac=0.3, noise_px=0.3, seed=3)
+    x = sc["px"]
+    idx = O.sample_indices(4, 500, len(x))[:, :4]
+    Hc = O.homography_hypotheses(x, idx)
+    cnt, _ = O.homography_counts(Hc, x, 2.0)
+    b = int(np.argmax(cnt))
+    Hn = Hc[b] / Hc[b][2, 2]
+    assert np.abs(Hn - sc["H"]).max() < 0.05 * np.abs(sc["H"]).max()
+    assert cnt[b] > 0.85 * (~sc["is_outlier"]).sum()
+    # fp32 emulation of the kernel's test agrees with the fp64 count up to borderline points
+    m = O.homography_mask_f32(Hc[b], x, 2.0)
+    c64, amb = O.homography_counts(Hc[b][None], x, 2.0)
+    assert abs(int(m.sum()) - int(c64[0])) <= int(amb[0]) + 1
