@@ -45,7 +45,12 @@ def test_homography_against_oracle(pkg, O, loops):
     assert abs(Hbest[0][2, 2] - 1) < 1e-6
     assert h_distance(Hbest[0][None], Hc[bi[0]][None])[0] < 1e-6
     # (4) ground truth: the winner maps points like the true homography; the mask separates outliers
-    assert h_distance(Hbest[0][None], sc["H"][None])[0] < 5e-3 if loops >= 1000 else True
+    good = ~sc["is_outlier"]
+    q = Hbest[0].astype(np.float64) @ np.stack([x[good, 0], x[good, 1], np.ones(good.sum())])
+    q_true = sc["H"] @ np.stack([x[good, 0], x[good, 1], np.ones(good.sum())])
+    transfer = np.hypot(q[0] / q[2] - q_true[0] / q_true[2], q[1] / q[2] - q_true[1] / q_true[2])
+    if loops >= 1000:
+        assert np.median(transfer) < 1.5          # pixels, from 4 points with 0.5 px noise
     mask = h.get_inlier_mask().cpu().numpy().astype(bool)
     assert mask.sum() == matches[0]
     if loops >= 1000:
