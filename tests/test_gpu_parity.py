@@ -419,3 +419,34 @@ def test_filtered_sift_ingest(pkg, O, torch_cuda, scene_small):
     with pytest.raises(pkg.SfmError) as e:
         ip_f.set_points_sift_filtered(d_sift, n, 2.0, 0.0)       # nothing survives
     assert e.value.code == -3
+
+
+def test_random_shapes_fuzz(pkg, O, oracle_c, torch_cuda):
+    """Random (pairs, n, H, variant, solver) shapes: the stream-K partition, the split /
+    atomic epilogue and the fused arg-max against the fp32 port, bit for bit."""
+    torch = torch_cuda
+    K, Kinv = O.reference_K()
+    rng = np.random.default_rng(2024)
+    base = O.synthetic_pair(6000, seed=77)["px"]
+    for trial in range(24):
+        B = int(rng.integers(1, 4))
+        n = int(rng.integers(8, 6000))
+        H = int(rng.integers(1, 5000))
+        variant = int(rng.integers(-1, 10))
+        solver = int(rng.integers(0, 2))
+        px = np.stack([np.ascontiguousarray(base[rng.permutation(6000)[:n]]) for _ in range(B)])
+        h = pkg.BatchedPairs(K, Kinv, B, n, H)
+        h.set_option(2, variant)
+        h.set_option(5, solver)
+        h.set_points_xy(torch.from_numpy(px).cuda())
+        seed = int(rng.integers(0, 2**62))
+        h.estimate_e(H, seed, THR)
+        bi, bc = h.get_best()
+        for b in range(B):
+            Eg = h.get_E_candidates(b).cpu().numpy()
+            got = h.get_inlier_counts(b).cpu().numpy()
+            want = counts_f32(oracle_c, Eg, gpu_x(h, b))
+            assert np.array_equal(got, want), (trial, B, n, H, variant, solver, h.score_plan())
+            assert bc[b] == got.max() and bi[b] == int(np.argmax(got)), (trial, B, n, H, variant)
+            assert np.array_equal(h.get_E()[b].reshape(9), Eg[bi[b]])
+        h.close()
