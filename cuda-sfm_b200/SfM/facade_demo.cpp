@@ -97,6 +97,28 @@ int main(int argc, char** argv) {
     // the reference's seven print-only self tests, asserting here
     bool t[7] = {sfm.testBatchedmult(), sfm.testSVD(), sfm.testInverse(), sfm.testThrust_max(),
                  sfm.testBatchedmultTranspose(), sfm.testRow_extraction_kernel(), sfm.testVecnorm()};
+    // kernels::regular_svd (row-major 8x9 batch, like estimateE's call at sfm.cu:124): null vector in V's 9th column
+    bool regular_ok = true;
+    {
+        const int B = 64;
+        std::vector<float> A(B * 72);
+        for (int i = 0; i < B * 72; i++) A[i] = (float)((i * 2654435761u >> 8) & 0xFFFF) / 65536.0f - 0.5f;
+        float* d_A = kernels::cuda_alloc_copy(A.data(), B * 72);
+        float *d_ut, *d_vt, *d_s;
+        cudaMalloc((void**)&d_ut, B * 64 * sizeof(float));
+        cudaMalloc((void**)&d_vt, B * 81 * sizeof(float));
+        cudaMalloc((void**)&d_s, B * 8 * sizeof(float));
+        kernels::regular_svd(d_A, d_ut, d_s, d_vt, 8, 9, B, (int*)nullptr, 0, 0);
+        std::vector<float> V(B * 81);
+        cudaMemcpy(V.data(), d_vt, B * 81 * sizeof(float), cudaMemcpyDeviceToHost);
+        for (int b = 0; b < B; b++)
+            for (int r = 0; r < 8; r++) {
+                float acc = 0;
+                for (int c = 0; c < 9; c++) acc += A[b * 72 + r * 9 + c] * V[b * 81 + 72 + c];
+                regular_ok = regular_ok && fabsf(acc) < 1e-4f;
+            }
+        cudaFree(d_A); cudaFree(d_ut); cudaFree(d_vt); cudaFree(d_s);
+    }
     // svd.h surface on the host
     float a[9] = {1, 2, 3, 4, 5, 6, 7, 8, 10}, u[9], s[9], v[9], us[9], rec[9];
     svd(a, u, s, v);
@@ -105,8 +127,8 @@ int main(int argc, char** argv) {
     float err = 0;
     for (int i = 0; i < 9; i++) err = fmaxf(err, fabsf(rec[i] - a[i]));
     printf("{\"n\": %d, \"as_built_inliers\": %d, \"H\": %d, \"best\": %d, \"inliers\": %d, \"pose_index\": %d, "
-           "\"self_tests\": [%d,%d,%d,%d,%d,%d,%d], \"svd_recon_err\": %g, \"det\": %g}\n",
-           n, inl_asbuilt, H, best, inliers, pind, t[0], t[1], t[2], t[3], t[4], t[5], t[6], err, det(a));
+           "\"self_tests\": [%d,%d,%d,%d,%d,%d,%d], \"regular_svd\": %d, \"svd_recon_err\": %g, \"det\": %g}\n",
+           n, inl_asbuilt, H, best, inliers, pind, t[0], t[1], t[2], t[3], t[4], t[5], t[6], (int)regular_ok, err, det(a));
     cudaFree(dptrVertPositions); cudaFree(dptrVertVelocities); cudaFree(siftData1.d_data);
     return 0;
 }

@@ -106,12 +106,7 @@ void regular_svd(float* src, float* UT, float* S, float* VT, int m, int n, const
                  Params) {
     float* colmajor = nullptr;
     cudaMalloc((void**)&colmajor, sizeof(float) * m * n * batchSize);
-    // row-major m x n == column-major n x m: one batched "A^T * I" through mmul_transpose would do, but a
-    // strided 2-D copy per matrix keeps this wrapper dependency-free.
-    for (int b = 0; b < batchSize; b++)
-        for (int r = 0; r < m; r++)
-            cudaMemcpy2DAsync(colmajor + (size_t)b * m * n + r, sizeof(float) * m, src + (size_t)b * m * n + (size_t)r * n,
-                              sizeof(float), sizeof(float), n, cudaMemcpyDeviceToDevice, 0);
+    la_check(sfmb200_la_transpose_batched(src, colmajor, m, n, batchSize, nullptr), "regular_svd");   // one launch, not one per matrix
     la_check(sfmb200_la_svd_batched(colmajor, S, UT, VT, m, n, batchSize, nullptr), "regular_svd");
     cudaDeviceSynchronize();
     cudaFree(colmajor);

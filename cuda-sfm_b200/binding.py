@@ -81,6 +81,7 @@ SIGNATURES = {
     "sfmb200_la_mmul_transpose_batched": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sfmb200_la_invert": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "sfmb200_la_svd_batched": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "sfmb200_la_transpose_batched": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sfmb200_la_vecnorm": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp]),
     "sfmb200_la_elementwise": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp]),
     "sfmb200_la_threshold_count": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, _vp]),

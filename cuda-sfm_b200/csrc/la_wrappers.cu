@@ -211,6 +211,18 @@ __global__ void argmax_first_kernel(const int* v, int n, unsigned long long* out
     }
 }
 
+// out[b][c][r] = in[b][r][c]: row-major rows x cols -> column-major (what cuSOLVER wants).  The
+// reference does this with one <<<1,(10,10)>>> launch PER MATRIX (kernels.h:214-218).
+__global__ void transpose_batched_kernel(const float* in, float* out, int rows, int cols, long long total) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int per = rows * cols;
+        long long b = t / per;
+        int e = (int)(t - b * per);
+        int c = e / rows, r = e - c * rows;          // output element (c, r) of matrix b
+        out[t] = in[b * per + (long long)r * cols + c];
+    }
+}
+
 int check() { return cudaGetLastError() == cudaSuccess ? 0 : -2; }
 
 }  // namespace
@@ -256,6 +268,13 @@ int sfmb200_la_invert(const float* src, float* dst, int n, int batch, void* stre
 int sfmb200_la_svd_batched(const float* A, float* S, float* U, float* V, int m, int n, int batch, void* stream) {
     if (!A || !S || !U || !V || m < 1 || n < 1 || m > LA_MAX || n > LA_MAX || batch < 1) return -1;
     svd_batched_kernel<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(A, S, U, V, m, n, batch);
+    return check();
+}
+int sfmb200_la_transpose_batched(const float* in, float* out, int rows, int cols, int batch, void* stream) {
+    if (!in || !out || rows < 1 || cols < 1 || batch < 1) return -1;
+    long long total = (long long)rows * cols * batch;
+    int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    transpose_batched_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, total);
     return check();
 }
 int sfmb200_la_vecnorm(const float* A, float* res, int row, int col, float ex, float final_pow, void* stream) {

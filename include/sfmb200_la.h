@@ -24,6 +24,9 @@ int sfmb200_la_invert(const float* src, float* dst, int n, int batch, void* stre
 /* svd_square / regular_svd (kernels.h:175-234) = cusolverDnSgesvdjBatched: column-major A (m x n),
  * S min(m,n) descending, U m x m and V n x n column-major; m, n <= 9. */
 int sfmb200_la_svd_batched(const float* A, float* S, float* U, float* V, int m, int n, int batch, void* stream);
+/* transpose (kernels.h:196-209, launched once per matrix by regular_svd, 214-218): batched
+ * row-major rows x cols -> column-major, one launch for the whole batch. */
+int sfmb200_la_transpose_batched(const float* in, float* out, int rows, int cols, int batch, void* stream);
 /* vecnorm (kernels.h:325-341) */
 int sfmb200_la_vecnorm(const float* A, float* res, int row, int col, float exp, float final_pow, void* stream);
 /* element_wise_mult / _div / _sum (kernels.h:297-323): op 0 / 1 / 2, in place on A. */

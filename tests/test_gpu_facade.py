@@ -27,6 +27,7 @@ def test_facade_demo_matches_python_mirror(pkg, O, tmp_path):
     assert r.returncode == 0, r.stderr
     info = json.loads(r.stdout.strip().splitlines()[-1])
     assert info["self_tests"] == [1] * 7, info          # the reference's test literals (sfm.cu:389-510)
+    assert info["regular_svd"] == 1                      # kernels::regular_svd: null vector in V's 9th column
     assert info["svd_recon_err"] < 1e-5 and abs(info["det"] - (-3.0)) < 1e-4
     assert 0 <= info["as_built_inliers"] <= n
     raw = np.fromfile(fout, dtype=np.uint8)

@@ -96,6 +96,14 @@ def test_svd_batched_cusolver_convention(lib, T, m, n):
         assert np.array_equal(e, dV.cpu().numpy().reshape(batch, 81)[:, 72:81])
 
 
+def test_transpose_batched(lib, T):
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(1000, 8, 9)).astype(np.float32)
+    dA, dO = T.from_numpy(A).cuda(), T.empty((1000, 9, 8), device="cuda")
+    lib.call("sfmb200_la_transpose_batched", dp(dA), dp(dO), 8, 9, 1000, None)
+    assert np.array_equal(dO.cpu().numpy(), np.transpose(A, (0, 2, 1)))
+
+
 def test_elementwise_vecnorm_threshold_argmax(lib, T):
     rng = np.random.default_rng(3)
     a, b = rng.normal(size=5000).astype(np.float32), rng.normal(size=5000).astype(np.float32)
