@@ -29,6 +29,10 @@
 // on ties = thrust::max_element semantics.  No separate arg-max kernel.
 //
 // Roofline: FP32 pipe; algorithmic work 34 FLOP per evaluation.
+#include <math.h>
+
+#include <mutex>
+
 #include "internal.cuh"
 #include "sampson.cuh"
 
@@ -118,6 +122,78 @@ struct ChunkWalk {
         return true;
     }
 };
+
+// End of a segment (a contiguous point range of one (pair, tile) handled by one CTA): publish
+// the counts and take part in the fused arg-max.  A CTA that saw every point of the tile writes
+// counts directly and reduces from registers.  Otherwise partial counts are atomically added and
+// a per-tile counter of points processed (it persists across launches of the same estimate)
+// tells which CTA completed the tile; that CTA reads the totals and reduces them.  One atomicMax
+// per tile on the packed key (count << 32) | (0xFFFFFFFF - global index).  Must be called by
+// every thread of the CTA.
+// `full`: this CTA saw every point of the tile.  Otherwise the tile's ticket counter advances by
+// `inc` and the CTA that brings it to `total` completes the tile (TMA path: points processed out
+// of n; constant-bank path: CTA arrivals out of the number the host scheduled for the tile).
+template <int HPT, int THREADS>
+__device__ __forceinline__ void segment_epilogue(const DeviceState& s, int b, int t, int H, int h_offset,
+                                                 const unsigned int* cnt, bool full, int inc, int total,
+                                                 unsigned long long* red, int* s_last) {
+    constexpr int HPC = HPT * THREADS;
+    const int tid = threadIdx.x;
+    int* counts = s.counts + (size_t)b * s.h_stride;
+    unsigned long long key = 0ull;
+    bool do_argmax;
+    if (full) {                          // this CTA saw every point of the tile
+#pragma unroll
+        for (int j = 0; j < HPT; j++) {
+            int h = t * HPC + j * THREADS + tid;
+            if (h < H) {
+                counts[h] = (int)cnt[j];
+                unsigned long long kk = ((unsigned long long)cnt[j] << 32) |
+                                        (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + h));
+                key = kk > key ? kk : key;
+            }
+        }
+        do_argmax = true;
+    } else {                             // partial: add, the CTA completing the tile reduces it
+#pragma unroll
+        for (int j = 0; j < HPT; j++) {
+            int h = t * HPC + j * THREADS + tid;
+            if (h < H && cnt[j] != 0u) atomicAdd(&counts[h], (int)cnt[j]);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int before = atomicAdd(&s.tile_done[(size_t)b * s.tiles_max + t], inc);
+            *s_last = (before + inc == total);
+        }
+        __syncthreads();
+        do_argmax = *s_last != 0;
+        if (do_argmax) {
+            __threadfence();
+#pragma unroll
+            for (int j = 0; j < HPT; j++) {
+                int h = t * HPC + j * THREADS + tid;
+                if (h < H) {
+                    unsigned int total = (unsigned int)__ldcg(&counts[h]);
+                    unsigned long long kk = ((unsigned long long)total << 32) |
+                                            (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + h));
+                    key = kk > key ? kk : key;
+                }
+            }
+        }
+    }
+    if (do_argmax) {                     // uniform across the CTA
+        key = warp_max_u64(key);
+        if ((tid & 31) == 0) red[tid >> 5] = key;
+        __syncthreads();
+        if (tid < 32) {
+            unsigned long long v = tid < THREADS / 32 ? red[tid] : 0ull;
+            v = warp_max_u64(v);
+            if (tid == 0 && v != 0ull) atomicMax(&s.best[b], v);
+        }
+        __syncthreads();                 // red[] is reused by the next segment
+    }
+}
 
 // Chunk descriptor handed from the producer thread to the consumers through
 // shared memory (published by the mbarrier the chunk's TMA completes on).
@@ -234,61 +310,131 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
         if (d.cnt_flags >= 0) continue;   // bit 31 clear: segment continues
 
         // ---- end of a segment: counts + fused arg-max for (pair b, tile t) ----
-        int* counts = s.counts + (size_t)d.b * s.h_stride;
-        unsigned long long key = 0ull;
-        bool do_argmax;
-        if (d.seg_pts == s.n) {             // this CTA saw every point of the tile
+        segment_epilogue<HPT, THREADS>(s, d.b, d.t, H, h_offset, cnt, d.seg_pts == s.n, d.seg_pts, s.n, red, &s_last);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Constant-bank path.  ncu shows what bounds the kernels above (profiles/
+// r01_ncu_score_variants.md): every FFMA reads three general registers and the
+// register-bank conflicts surface as dispatch stalls (scalar) or the packed pipe
+// saturates at ~80 %.  The point coordinates are the same for every thread, so
+// they do not have to be general registers at all: staged in __constant__
+// memory they are fetched by uniform loads (LDCU) into UNIFORM registers and
+// each FFMA reads two general registers + one uniform one.  No shared memory,
+// no reuse-cache dependence, 1.8e12 evals/s for any hypotheses-per-thread.
+// The price: 64 KB of constant bank = 4,000 points per launch, so a pair is
+// scored in ceil(n / 4000) launches whose partial counts meet in counts[] and in
+// the per-tile points-processed counter; used when one launch has enough work
+// to amortise the 64 KB device-to-device refill (single pairs with many
+// hypotheses: configs 2, 3, 5), while batches of small pairs keep the TMA path.
+// ---------------------------------------------------------------------------
+constexpr int CONST_PTS = 4000;
+__constant__ float4 c_pts[CONST_PTS];
+
+// Work split of one launch: grid (tiles, splits); CTA (t, y) scores tile t against points
+// [y * chunk, y * chunk + np) of the batch, np = chunk except for the last split.  The loop
+// counter runs from 0 to a bound that is a plain select between two kernel parameters and the
+// base is c_pts + blockIdx.y * chunk: with anything more elaborate (min, shifts, a work-stealing
+// walk) nvcc 12.9 moves the index to vector registers and the loads become LDC into general
+// registers - exactly the operand traffic this kernel exists to avoid.
+template <int HPT, int THREADS, int MINB, int MODEL>
+__global__ void __launch_bounds__(THREADS, MINB)
+score_const_kernel(DeviceState s, int b, int chunk, int last_np, int arrivals, int H, int h_offset, float thr) {
+    constexpr int HPC = HPT * THREADS;
+    __shared__ unsigned long long red[THREADS / 32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x;
+    const float4* base = c_pts + blockIdx.y * chunk;
+    const int np = (blockIdx.y == gridDim.y - 1) ? last_np : chunk;
+    const float nthr = -thr;
+    const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
+    float e[HPT][9];
+    unsigned int cnt[HPT];
 #pragma unroll
-            for (int j = 0; j < HPT; j++) {
-                int h = d.t * HPC + j * THREADS + tid;
-                if (h < H) {
-                    counts[h] = (int)cnt[j];
-                    unsigned long long kk = ((unsigned long long)cnt[j] << 32) |
-                                            (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + h));
-                    key = kk > key ? kk : key;
-                }
-            }
-            do_argmax = true;
-        } else {                             // partial: add, the CTA completing the tile reduces it
+    for (int j = 0; j < HPT; j++) {
+        int h = t * HPC + j * THREADS + tid;
+        bool valid = h < H;
 #pragma unroll
-            for (int j = 0; j < HPT; j++) {
-                int h = d.t * HPC + j * THREADS + tid;
-                if (h < H && cnt[j] != 0u) atomicAdd(&counts[h], (int)cnt[j]);
-            }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                int before = atomicAdd(&s.tile_done[(size_t)d.b * s.tiles_max + d.t], d.seg_pts);
-                s_last = (before + d.seg_pts == s.n);
-            }
-            __syncthreads();
-            do_argmax = s_last != 0;
-            if (do_argmax) {
-                __threadfence();
+        for (int k = 0; k < 9; k++) e[j][k] = valid ? __ldg(Eb + (size_t)k * s.h_stride + h) : 0.0f;
+        cnt[j] = 0u;
+    }
+#pragma unroll 4
+    for (int i = 0; i < np; i++) {
+        const float4 p = base[i];                       // uniform address -> LDCU -> uniform registers
 #pragma unroll
-                for (int j = 0; j < HPT; j++) {
-                    int h = d.t * HPC + j * THREADS + tid;
-                    if (h < H) {
-                        unsigned int total = (unsigned int)__ldcg(&counts[h]);
-                        unsigned long long kk = ((unsigned long long)total << 32) |
-                                                (unsigned long long)(0xFFFFFFFFu - (unsigned)(h_offset + h));
-                        key = kk > key ? kk : key;
-                    }
-                }
-            }
-        }
-        if (do_argmax) {                     // uniform across the CTA
-            key = warp_max_u64(key);
-            if ((tid & 31) == 0) red[tid >> 5] = key;
-            __syncthreads();
-            if (tid < 32) {
-                unsigned long long v = tid < THREADS / 32 ? red[tid] : 0ull;
-                v = warp_max_u64(v);
-                if (tid == 0 && v != 0ull) atomicMax(&s.best[d.b], v);
-            }
-            __syncthreads();                 // red[] is reused by the next segment
+        for (int j = 0; j < HPT; j++) {
+            float dd = model_d<MODEL>(e[j], p.x, p.y, p.z, p.w, nthr);
+            cnt[j] += __float_as_uint(dd) >> 31;
         }
     }
+    // Tile completion is counted in CTA arrivals, not points: feeding the loop bound `np` into the
+    // per-thread epilogue code would pull it (and with it the whole point loop) off the uniform datapath.
+    segment_epilogue<HPT, THREADS>(s, b, t, H, h_offset, cnt, arrivals == 1, 1, arrivals, red, &s_last);
+}
+
+// Number of point splits per tile for one launch: the grid tiles x splits should fill whole
+// waves of `slots` resident CTAs (all CTAs of a launch take the same time), with at least
+// `min_chunk` points per CTA to amortise loading its essential matrices.
+static int const_splits(int tiles, int batch, long long slots, int min_chunk = 64) {
+    int max_s = batch / min_chunk;
+    if (max_s < 1) max_s = 1;
+    if (max_s > 512) max_s = 512;
+    int best_s = 1;
+    double best_eff = -1.0;
+    for (int sp = 1; sp <= max_s; sp++) {
+        double waves = (double)tiles * sp / (double)slots;
+        double eff = waves / ceil(waves);
+        // prefer fewer splits on near-ties (fewer atomics, better amortisation)
+        if (eff > best_eff + 0.02) { best_eff = eff; best_s = sp; }
+        if (eff > 0.985 && waves >= 2.0) break;
+    }
+    return best_s;
+}
+
+constexpr int CONST_HPT = 8, CONST_THREADS = 128, CONST_MINB = 4;
+
+// The __constant__ bank is one per device and process, not per handle or stream: refills are
+// serialised with a mutex and every refill waits for the last kernel that read the previous
+// contents, whichever stream it ran on.
+struct ConstBankGuard {
+    std::mutex mu;
+    cudaEvent_t last_use[64] = {};
+};
+static ConstBankGuard g_const;
+
+template <int MODEL>
+static void launch_score_const(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    std::lock_guard<std::mutex> lock(g_const.mu);
+    if (!g_const.last_use[dev]) cudaEventCreateWithFlags(&g_const.last_use[dev], cudaEventDisableTiming);
+    const int batches = (s.n + CONST_PTS - 1) / CONST_PTS;
+    const int per = ((s.n + batches - 1) / batches + 15) / 16 * 16;      // even batches
+    // pass 1: the split of every batch, and with it the CTA arrivals each tile will see in total
+    int arrivals = 0;
+    for (int off = 0; off < s.n; off += per) {
+        const int cnt = s.n - off < per ? s.n - off : per;
+        const int splits = const_splits(plan.tiles, cnt, plan.ctas);        // plan.ctas = resident CTA slots
+        const int chunk = (cnt + splits - 1) / splits;
+        arrivals += (cnt + chunk - 1) / chunk;
+    }
+    for (int b = 0; b < s.B; b++)
+        for (int off = 0; off < s.n; off += per) {
+            const int cnt = s.n - off < per ? s.n - off : per;
+            const int splits = const_splits(plan.tiles, cnt, plan.ctas);
+            const int chunk = (cnt + splits - 1) / splits;
+            const int real_splits = (cnt + chunk - 1) / chunk;
+            const int last_np = cnt - (real_splits - 1) * chunk;
+            cudaStreamWaitEvent(st, g_const.last_use[dev], 0);
+            cudaMemcpyToSymbolAsync(c_pts, s.corr + (size_t)b * s.n_stride + off, (size_t)cnt * sizeof(float4), 0,
+                                    cudaMemcpyDeviceToDevice, st);
+            score_const_kernel<CONST_HPT, CONST_THREADS, CONST_MINB, MODEL>
+                <<<dim3(plan.tiles, real_splits), CONST_THREADS, 0, st>>>(s, b, chunk, last_np, arrivals, H, h_offset, thr);
+            cudaEventRecord(g_const.last_use[dev], st);
+        }
 }
 
 // Kernel family.  Register-bank bandwidth is what bounds the FP32 pipe here: an
@@ -302,7 +448,9 @@ struct ScoreVariant { int hpt; int packed; int threads; int minb; };
 static const ScoreVariant kVariants[] = {
     {2, 0, 256, 1}, {4, 1, 256, 1}, {4, 0, 256, 1}, {8, 0, 256, 2}, {8, 1, 256, 1},
     {4, 0, 128, 1}, {4, 1, 128, 1}, {8, 0, 128, 4}, {8, 1, 128, 2}, {2, 0, 128, 1},
+    {CONST_HPT, 0, CONST_THREADS, CONST_MINB},      // 10: constant-bank path (score_const_kernel)
 };
+constexpr int kConstVariant = 10;
 // Also measured on B200 and dropped (profiles/r01_variant_sweep.md): 12 / 16 hypotheses per
 // thread, scalar or packed (fewer resident warps than the reuse gain pays for); packed with a
 // 128-register cap for 16 warps/SM (less ILP: -8 %); 192 / 320 / 384-thread CTAs (warps not a
@@ -337,6 +485,11 @@ static int occupancy_one() {
 
 static int variant_occupancy(int v) {
     static int cache[kNumVariants] = {0};
+    if (cache[v] == 0 && v == kConstVariant) {
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_const_kernel<CONST_HPT, CONST_THREADS, CONST_MINB, 0>, CONST_THREADS, 0);
+        cache[v] = n > 0 ? n : 1;
+    }
     if (cache[v] == 0) {
 #define SFM_OCC(h, p, t, m) cache[v] = occupancy_one<h, p, t, m>()
         SFM_FOR_VARIANT(v, SFM_OCC)
@@ -352,10 +505,13 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     if (variant_override >= 0 && variant_override < kNumVariants) {
         p.variant = variant_override;
     } else {
-        // Measured on B200 (profiles/r01_variant_sweep.md): packed FFMA2 with 8
-        // hypotheses per thread and one 256-thread CTA per SM is the fastest at
-        // every large shape; smaller tiles only when H cannot fill a 2048 tile.
-        p.variant = H >= 1536 ? 4 : (H >= 768 ? 1 : (H >= 384 ? 6 : 9));
+        // Measured on B200 (profiles/): when one launch over <= 4,000 points has enough
+        // work to amortise the constant-bank refill, the constant-bank kernel wins
+        // (1.8e12 evals/s); otherwise packed FFMA2 with 8 hypotheses per thread and one
+        // 256-thread CTA per SM, and smaller tiles when H cannot fill a 2048 tile.
+        const long long per_launch = (long long)H * (n < CONST_PTS ? n : CONST_PTS);
+        if (per_launch >= 30000000LL) p.variant = kConstVariant;
+        else p.variant = H >= 1536 ? 4 : (H >= 768 ? 1 : (H >= 384 ? 6 : 9));
     }
     const ScoreVariant& v = kVariants[p.variant];
     p.hyp_per_cta = v.hpt * v.threads;
@@ -369,7 +525,7 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     p.n_units = (n + SCORE_GRAIN - 1) / SCORE_GRAIN;
     p.total_units = (long long)B * p.tiles * p.n_units;
     long long ctas = (long long)sms * variant_occupancy(p.variant);   // persistent: all CTAs co-resident
-    if (ctas > p.total_units) ctas = p.total_units;
+    if (p.variant != kConstVariant && ctas > p.total_units) ctas = p.total_units;   // const path: ctas = resident slots
     if (ctas < 1) ctas = 1;
     p.ctas = (int)ctas;
     return p;
@@ -378,10 +534,16 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
 // Homography model: the same kernel with the transfer-error test; three tile sizes are enough
 // (thr here is the SQUARED pixel / coordinate threshold).
 ScorePlan make_score_plan_homography(int B, int n, int H) {
+    const long long per_launch = (long long)H * (n < CONST_PTS ? n : CONST_PTS);
+    if (per_launch >= 30000000LL) return make_score_plan(B, n, H, kConstVariant);
     return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9));     // tiles of 2048 / 512 / 256 hypotheses
 }
 void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st) {
     const int v = plan.variant;
+    if (v == kConstVariant) {
+        launch_score_const<1>(s, plan, H, h_offset, thr2, st);
+        return;
+    }
     const bool big = kVariants[v].hpt * kVariants[v].threads >= 2048, mid = kVariants[v].hpt * kVariants[v].threads >= 512;
     if (big) {
         score_kernel<8, true, 256, 1, 1><<<plan.ctas, 256, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr2);
@@ -393,6 +555,10 @@ void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h
 }
 
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {
+    if (plan.variant == kConstVariant) {
+        launch_score_const<0>(s, plan, H, h_offset, thr, st);
+        return;
+    }
 #define SFM_LAUNCH(h, p, t, m) launch_one<h, p, t, m>(s, plan.ctas, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr, st)
     SFM_FOR_VARIANT(plan.variant, SFM_LAUNCH)
 #undef SFM_LAUNCH

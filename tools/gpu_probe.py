@@ -68,10 +68,14 @@ if __name__ == "__main__":
             stages(4096, 4096, -1, pairs=256, reps=3, label="config4 slice: 256 pairs", solver=solver)
         sys.exit(0)
     if which == "score":
-        for v in range(10):
+        for v in (4, 10, -1):
             stages(10_000, 65_536, v, label="config2", solver=1)
-        for v in (3, 4, 8):
+        for v in (4, 10, -1):
             stages(1 << 20, 16_384, v, reps=3, label="1M points x 16k hyp", solver=1)
+        for v in (4, 10, -1):
+            stages(4096, 4096, v, pairs=256, reps=3, label="config4 slice: 256 pairs", solver=1)
+        for v in (9, 10, -1):
+            stages(2000, 250, v, label="config1-like: 2k corr, 250 hyp", solver=1)
         sys.exit(0)
     probe()
     nv = 10

@@ -15,7 +15,7 @@ import __graft_entry__ as entry
 pkg = entry.load_package()
 O = pkg.synthetic          # scenes + intrinsics only: no checker code in these tools
 K, Kinv = O.reference_K()
-for n, H, pairs, variant in ((700, 300, 1, -1), (1100, 2500, 2, -1), (520, 1030, 1, 0), (2049, 700, 1, 6), (600, 2100, 1, 3)):
+for n, H, pairs, variant in ((700, 300, 1, -1), (1100, 2500, 2, -1), (520, 1030, 1, 0), (2049, 700, 1, 6), (600, 2100, 1, 3), (5000, 1500, 1, 10), (300, 40, 2, 10)):
     px = np.stack([O.synthetic_pair(n, seed=3 + b)["px"] for b in range(pairs)])
     h = pkg.BatchedPairs(K, Kinv, pairs, n, H)
     h.set_option(2, variant)
