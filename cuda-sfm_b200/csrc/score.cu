@@ -451,6 +451,7 @@ static const ScoreVariant kVariants[] = {
     {CONST_HPT, 0, CONST_THREADS, CONST_MINB},      // 10: constant-bank path (score_const_kernel)
 };
 constexpr int kConstVariant = 10;
+constexpr long long kConstMinEvalsPerLaunch = 1000000000LL;
 // Also measured on B200 and dropped (profiles/r01_variant_sweep.md): 12 / 16 hypotheses per
 // thread, scalar or packed (fewer resident warps than the reuse gain pays for); packed with a
 // 128-register cap for 16 warps/SM (less ILP: -8 %); 192 / 320 / 384-thread CTAs (warps not a
@@ -509,8 +510,9 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
         // work to amortise the constant-bank refill, the constant-bank kernel wins
         // (1.8e12 evals/s); otherwise packed FFMA2 with 8 hypotheses per thread and one
         // 256-thread CTA per SM, and smaller tiles when H cannot fill a 2048 tile.
+        // (each launch pays ~10-20 us of refill + launch + wave tail: measured break-even ~1e9 evals)
         const long long per_launch = (long long)H * (n < CONST_PTS ? n : CONST_PTS);
-        if (per_launch >= 30000000LL) p.variant = kConstVariant;
+        if (B == 1 && per_launch >= kConstMinEvalsPerLaunch) p.variant = kConstVariant;
         else p.variant = H >= 1536 ? 4 : (H >= 768 ? 1 : (H >= 384 ? 6 : 9));
     }
     const ScoreVariant& v = kVariants[p.variant];
@@ -535,7 +537,7 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
 // (thr here is the SQUARED pixel / coordinate threshold).
 ScorePlan make_score_plan_homography(int B, int n, int H) {
     const long long per_launch = (long long)H * (n < CONST_PTS ? n : CONST_PTS);
-    if (per_launch >= 30000000LL) return make_score_plan(B, n, H, kConstVariant);
+    if (B == 1 && per_launch >= kConstMinEvalsPerLaunch) return make_score_plan(B, n, H, kConstVariant);
     return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9));     // tiles of 2048 / 512 / 256 hypotheses
 }
 void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st) {

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("which", nargs="+", choices=["c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the configs (tests)")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--variant", type=int, default=-1, help="scoring kernel variant (-1 = auto)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -64,6 +65,7 @@ def main():
         d_px = torch.from_numpy(sc["px"]).cuda()
         lo, hi = pkg.sharding.shard_range(H, rank, world)
         h = pkg.BatchedPairs(K, Kinv, 1, n, hi - lo)
+        h.set_option(2, args.variant)
         h.set_points_xy(d_px)
 
         def step():
@@ -80,7 +82,7 @@ def main():
             assert all(torch.equal(Es[0], e) for e in Es), "ranks disagree on the selected E"
         t = min(ms)
         emit(config="c3", n_gpus=world, n=n, H=H, sharding="hypotheses", ms=t, ms_all=ms, evals_per_s=n * H / (t * 1e-3),
-             best_index=int(idx[0]), inliers=int(cnt[0]), collective="one all_reduce(MAX) of 8 bytes")
+             best_index=int(idx[0]), inliers=int(cnt[0]), collective="one all_reduce(MAX) of 8 bytes", plan=h.score_plan())
         h.close()
 
     if "c4" in args.which:
