@@ -324,10 +324,15 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
 // each FFMA reads two general registers + one uniform one.  No shared memory,
 // no reuse-cache dependence, 1.8e12 evals/s for any hypotheses-per-thread.
 // The price: 64 KB of constant bank = 4,000 points per launch, so a pair is
-// scored in ceil(n / 4000) launches whose partial counts meet in counts[] and in
-// the per-tile points-processed counter; used when one launch has enough work
-// to amortise the 64 KB device-to-device refill (single pairs with many
-// hypotheses: configs 2, 3, 5), while batches of small pairs keep the TMA path.
+// scored in ceil(n / 4000) launches whose partial counts meet in counts[] (one
+// atomic per hypothesis per CTA) and in the per-tile arrival counter.
+// MEASURED OUTCOME (B200, profiles/r01_const_bank.md): a stand-alone prototype
+// with 1.2M hypotheses per launch reaches 1.80e12 evals/s (+8 % over the TMA /
+// FFMA2 kernel), but in the product the refill + launch + wave tail per 4,000
+// points and above all the H atomics per launch eat the gain: config 2 0.429 ms
+// vs 0.404, config 3 665 ms vs 654.  It is therefore selectable
+// (SFMB200_OPT_SCORE_VARIANT = 10, tested for parity) but never chosen
+// automatically; the TMA-staged kernels remain the product path.
 // ---------------------------------------------------------------------------
 constexpr int CONST_PTS = 4000;
 __constant__ float4 c_pts[CONST_PTS];
@@ -451,7 +456,6 @@ static const ScoreVariant kVariants[] = {
     {CONST_HPT, 0, CONST_THREADS, CONST_MINB},      // 10: constant-bank path (score_const_kernel)
 };
 constexpr int kConstVariant = 10;
-constexpr long long kConstMinEvalsPerLaunch = 1000000000LL;
 // Also measured on B200 and dropped (profiles/r01_variant_sweep.md): 12 / 16 hypotheses per
 // thread, scalar or packed (fewer resident warps than the reuse gain pays for); packed with a
 // 128-register cap for 16 warps/SM (less ILP: -8 %); 192 / 320 / 384-thread CTAs (warps not a
@@ -506,14 +510,11 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     if (variant_override >= 0 && variant_override < kNumVariants) {
         p.variant = variant_override;
     } else {
-        // Measured on B200 (profiles/): when one launch over <= 4,000 points has enough
-        // work to amortise the constant-bank refill, the constant-bank kernel wins
-        // (1.8e12 evals/s); otherwise packed FFMA2 with 8 hypotheses per thread and one
-        // 256-thread CTA per SM, and smaller tiles when H cannot fill a 2048 tile.
-        // (each launch pays ~10-20 us of refill + launch + wave tail: measured break-even ~1e9 evals)
-        const long long per_launch = (long long)H * (n < CONST_PTS ? n : CONST_PTS);
-        if (B == 1 && per_launch >= kConstMinEvalsPerLaunch) p.variant = kConstVariant;
-        else p.variant = H >= 1536 ? 4 : (H >= 768 ? 1 : (H >= 384 ? 6 : 9));
+        // Measured on B200 (profiles/): packed FFMA2 with 8 hypotheses per thread and one
+        // 256-thread CTA per SM is the fastest at every large shape; smaller tiles only
+        // when H cannot fill a 2048 tile.  The constant-bank kernel (variant 10) is never
+        // chosen automatically: see the note above score_const_kernel.
+        p.variant = H >= 1536 ? 4 : (H >= 768 ? 1 : (H >= 384 ? 6 : 9));
     }
     const ScoreVariant& v = kVariants[p.variant];
     p.hyp_per_cta = v.hpt * v.threads;
@@ -536,8 +537,6 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
 // Homography model: the same kernel with the transfer-error test; three tile sizes are enough
 // (thr here is the SQUARED pixel / coordinate threshold).
 ScorePlan make_score_plan_homography(int B, int n, int H) {
-    const long long per_launch = (long long)H * (n < CONST_PTS ? n : CONST_PTS);
-    if (B == 1 && per_launch >= kConstMinEvalsPerLaunch) return make_score_plan(B, n, H, kConstVariant);
     return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9));     // tiles of 2048 / 512 / 256 hypotheses
 }
 void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st) {
