@@ -53,6 +53,7 @@ struct sfmb200_handle {
     float* pack_header;    // device [B][32]: E 9, selected P 16, pose index, inliers, best index (run_host results)
     float* pack_points;    // device [B][4][n] compact copy of the triangulated points
     float* host_header;    // pinned mirror of pack_header
+    int* adapt;            // device [4]: adaptive termination flag, hypotheses used, pairs unsatisfied, spare
     void* arena;
     // optional per-stage timing (SFMB200_OPT_PROFILE): ring of event sets, one set
     // per run_device / run_host call, 8 boundary marks -> 7 stage durations
@@ -125,6 +126,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_fs = carve(((size_t)max_points / 256 + 2) * sizeof(int));
     size_t o_ph = carve(B * 32 * sizeof(float));
     size_t o_pp = carve(B * 4 * (size_t)max_points * sizeof(float));
+    size_t o_ad = carve(4 * sizeof(int));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
     size_t o_rT = carve(B * 8 * sizeof(float));
@@ -155,6 +157,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->filter_scratch = (int*)(base + o_fs);
     h->pack_header = (float*)(base + o_ph);
     h->pack_points = (float*)(base + o_pp);
+    h->adapt = (int*)(base + o_ad);
     h->refit.cand = (float*)(base + o_rc);
     h->refit.T = (float*)(base + o_rT);
     h->refit.flags = (int*)(base + o_rf);
@@ -374,6 +377,66 @@ int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh
 }
 int sfmb200_estimate_e(sfmb200_t* h, const int32_t* d_idx, int H, uint64_t seed, float thr) {
     return sfmb200_estimate_e_slice(h, d_idx, H, 0, H, seed, thr);
+}
+
+// Rounds cover [0, first), [first, first*growth), ... up to H_max; everything is enqueued at
+// once and the rounds after the termination test passes return immediately on the device
+// (hypgen.cu: adaptive_decide_kernel), so there is no host round trip between rounds.
+// The result equals sfmb200_estimate_e(h, d_idx, used, seed, thr) bit for bit when d_idx is NULL
+// (counter-based sampler) or when d_idx rows are the same prefix.
+int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, int first_round, int growth,
+                                uint64_t seed, float thr, float confidence, int32_t* h_used) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->have_points) return fail(SFMB200_ERR_STATE, "estimate_e before set_points%s");
+    if (H_max < 1 || first_round < 1 || growth < 2) return fail(SFMB200_ERR_ARG, "H_max >= 1, first_round >= 1, growth >= 2 required%s");
+    if (!(thr > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
+    if (!(confidence > 0.0f && confidence < 1.0f)) return fail(SFMB200_ERR_ARG, "confidence must be in (0, 1)%s");
+    // every round must fit the candidate arena
+    {
+        long long lo = 0, hi = first_round;
+        while (lo < H_max) {
+            if (hi > H_max) hi = H_max;
+            if (hi - lo > h->s.h_max) return fail(SFMB200_ERR_ARG, "a round exceeds max_hypotheses of the handle%s");
+            lo = hi;
+            hi *= growth;
+        }
+    }
+    const double log1mp = log1p(-(double)confidence);
+    CK(cudaMemsetAsync(h->adapt, 0, 4 * sizeof(int), h->stream));
+    DeviceState s = h->s;
+    s.skip = h->adapt;
+    long long lo = 0, hi = first_round;
+    int rounds = 0;
+    while (lo < H_max) {
+        if (hi > H_max) hi = H_max;
+        const int Hr = (int)(hi - lo);
+        h->plan = make_score_plan(s.B, s.n, Hr, h->score_variant);
+        launch_hypgen(s, d_idx, (long long)H_max * 8, Hr, (int)lo, seed, h->hyp_solver, h->stream, rounds > 0);
+        CKL();
+        launch_score(s, h->plan, Hr, (int)lo, thr, h->stream);
+        CKL();
+        launch_adaptive_decide(s, h->adapt, (int)hi, log1mp, hi >= H_max, h->stream);
+        CKL();
+        h->launches += 3;
+        rounds++;
+        h->H = Hr;
+        h->h_begin = (int)lo;
+        lo = hi;
+        hi *= growth;
+    }
+    launch_regen_best(h->s, d_idx, (long long)H_max * 8, seed, h->hyp_solver, h->stream);
+    CKL();
+    h->launches++;
+    h->thr = thr;
+    h->have_candidates = false;   // the candidate arena holds whichever round ran last, not [0, used)
+    h->have_E = true;
+    h->have_pose = false;
+    h->model = 0;
+    if (h_used) {
+        CK(cudaMemcpyAsync(h_used, h->adapt + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return SFMB200_OK;
 }
 
 int sfmb200_best_buffer(sfmb200_t* h, uint64_t** d_best) {

@@ -43,12 +43,13 @@ __device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int
 template <int THREADS, int MINB, int SYNC, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB)
 hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride, int H, int h_offset,
-              unsigned long long seed) {
+              unsigned long long seed, int keep_best) {
+    if (s.skip != nullptr && *s.skip != 0) return;      // adaptive termination reached in an earlier round
     const int b = blockIdx.y;
     const int j = blockIdx.x * THREADS + threadIdx.x;   // local hypothesis slot
     // Reset the per-launch accumulators of this pair (scoring adds into them).
     if (j < s.tiles_max) s.tile_done[(size_t)b * s.tiles_max + j] = 0;
-    if (j == 0) s.best[b] = 0ull;
+    if (j == 0 && !keep_best) s.best[b] = 0ull;
     const bool live = j < H;
     if (SYNC == 0 && !live) return;                     // with barriers every thread must stay
     const float4* corr = s.corr + (size_t)b * s.n_stride;
@@ -71,15 +72,15 @@ hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pa
 // solver 1: 8x8 Cholesky projector (see hyp_solver.cuh), 4 CTAs of 128 threads per SM;
 // solver 2: 4-point homography through the same projector (find_homography).
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
-                   unsigned long long seed, int solver, cudaStream_t st) {
+                   unsigned long long seed, int solver, cudaStream_t st, int keep_best) {
     int need = H > s.tiles_max ? H : s.tiles_max;
     dim3 grid((need + 127) / 128, s.B);
     if (solver == 0)
-        hypgen_kernel<128, 2, 0, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+        hypgen_kernel<128, 2, 0, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
     else if (solver == 1)
-        hypgen_kernel<128, 4, 0, 1><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+        hypgen_kernel<128, 4, 0, 1><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
     else
-        hypgen_kernel<128, 4, 0, 2><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed);
+        hypgen_kernel<128, 4, 0, 2><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
 }
 
 // Multi-GPU single-pair case: after the (count, index) all-reduce every rank
@@ -104,6 +105,38 @@ __global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_i
     for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = ok ? E[k] : 0.0f;
     s.best_idx[b] = (int)hg;
     s.best_count[b] = cnt;
+}
+
+// Adaptive termination (the reference lists "limit on RANSAC iterations" as
+// future work, README.md:65-69).  After the round that brings the hypotheses tried to
+// `done_after`, every pair's best inlier ratio w gives the standard bound
+//   needed = log(1 - confidence) / log(1 - w^8);
+// when done_after >= needed for ALL pairs of the batch (or this is the last round) the flag is
+// raised, the remaining rounds' kernels return immediately and adapt[1] records the
+// hypotheses actually used.  One block; the host never synchronises between rounds.
+__global__ void adaptive_decide_kernel(DeviceState s, int* adapt, int done_after, double log1mp, int last) {
+    if (adapt[0] != 0) return;
+    __shared__ int unsatisfied;
+    if (threadIdx.x == 0) unsatisfied = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int b = threadIdx.x; b < s.B; b += blockDim.x) {
+        double w = (double)(int)(s.best[b] >> 32) / (double)s.n;
+        double w2 = w * w, w4 = w2 * w2, w8 = w4 * w4;
+        bool ok = w8 >= 1.0 || (w8 > 0.0 && (double)done_after >= log1mp / log1p(-w8));
+        mine += ok ? 0 : 1;
+    }
+    if (mine) atomicAdd(&unsatisfied, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && (unsatisfied == 0 || last)) {
+        adapt[1] = done_after;
+        adapt[2] = unsatisfied;
+        __threadfence();
+        adapt[0] = 1;
+    }
+}
+void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int done_after, double log1mp, int last, cudaStream_t st) {
+    adaptive_decide_kernel<<<1, 128, 0, st>>>(s, d_adapt, done_after, log1mp, last);
 }
 
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, unsigned long long seed,

@@ -46,6 +46,8 @@ struct DeviceState {
     int* P_ind;         // [B]
     float* points;      // [B][4][n_stride] SoA (x,y,z,1), the reference's d_final_points layout
     int* tri_count;     // [B] points triangulated in front of both cameras (diagnostic)
+    const int* skip;    // adaptive termination: when non-null and *skip != 0 the hypgen / score kernels of
+                        // the remaining rounds return at once (set by adaptive_decide_kernel); else nullptr
 };
 
 // Scratch of the local-optimisation (refit) stage, per pair.
@@ -66,7 +68,8 @@ void launch_ingest_sift_filtered(const DeviceState& s, const void* d_sift, int n
 void launch_ingest_xy(const DeviceState& s, const float* d_px, int n, cudaStream_t st);
 void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cudaStream_t st);
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
-                   unsigned long long seed, int solver, cudaStream_t st);
+                   unsigned long long seed, int solver, cudaStream_t st, int keep_best = 0);
+void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int done_after, double log1mp, int last, cudaStream_t st);
 ScorePlan make_score_plan(int B, int n, int H, int variant_override);
 int score_num_variants();
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);

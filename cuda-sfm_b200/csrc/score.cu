@@ -216,6 +216,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
     __shared__ unsigned long long red[THREADS / 32];
     __shared__ int s_last;
 
+    if (s.skip != nullptr && *s.skip != 0) return;      // adaptive termination reached in an earlier round
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -349,6 +350,7 @@ score_const_kernel(DeviceState s, int b, int chunk, int last_np, int arrivals, i
     constexpr int HPC = HPT * THREADS;
     __shared__ unsigned long long red[THREADS / 32];
     __shared__ int s_last;
+    if (s.skip != nullptr && *s.skip != 0) return;      // adaptive termination reached in an earlier round
     const int tid = threadIdx.x;
     const int t = blockIdx.x;
     const float4* base = c_pts + blockIdx.y * chunk;

@@ -116,6 +116,15 @@ class BatchedPairs:
             self.lib.call("sfmb200_estimate_e_slice", self._h, _dptr(d_idx), H_total, h_begin, H, C.c_uint64(seed), C.c_float(thr))
         self.H = H
 
+    def estimate_e_adaptive(self, H_max: int, seed: int = 0, thr: float = 1e-6, confidence: float = 0.99,
+                            first_round: int = 1024, growth: int = 4, d_idx=None) -> int:
+        """RANSAC with adaptive termination, rounds skipped on the device; returns the hypotheses tried."""
+        used = C.c_int32(0)
+        self.lib.call("sfmb200_estimate_e_adaptive", self._h, _dptr(d_idx), H_max, first_round, growth, C.c_uint64(seed),
+                      C.c_float(thr), C.c_float(confidence), C.byref(used))
+        self.H = used.value
+        return used.value
+
     def best_buffer(self):
         """torch int64 view [pairs] of the packed winners (for dist.all_reduce MAX)."""
         torch = _torch()

@@ -96,6 +96,18 @@ int sfmb200_set_points_normalised(sfmb200_t* h, const float* d_x, int n);
 int sfmb200_estimate_e(sfmb200_t* h, const int32_t* d_idx, int H, uint64_t seed, float thr);
 int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, int h_begin, int H, uint64_t seed,
                              float thr);
+/* RANSAC with adaptive termination ("limit on RANSAC iterations" is
+ * listed as future work in the reference's README.md:65-69).  Hypotheses are tried in
+ * rounds [0, first_round), [first_round, first_round*growth), ... up to H_max; after each
+ * round the usual bound  needed = log(1 - confidence) / log(1 - w^8),  w = best inlier ratio,
+ * is evaluated on the device for every pair, and once the hypotheses tried reach it for all
+ * pairs the remaining rounds are skipped on the device (no host synchronisation between
+ * rounds).  *h_used (optional; forces one stream synchronisation) = hypotheses tried.
+ * The selected E, index and count are exactly those of sfmb200_estimate_e over the first
+ * `used` hypotheses.  d_idx: NULL or int32 [pairs][H_max][8].  Afterwards the per-hypothesis
+ * getters (get_inlier_counts, get_E_candidates) are not available. */
+int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, int first_round, int growth,
+                                uint64_t seed, float thr, float confidence, int32_t* h_used);
 /* Device pointer to the per-pair packed winners, uint64 [pairs]:
  * (count << 32) | (0xFFFFFFFF - global hypothesis index).  Multi-GPU: all-reduce
  * this buffer with MAX over ranks (8 bytes per pair), then call

@@ -21,6 +21,8 @@ math".
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 MASK64 = (1 << 64) - 1
@@ -297,6 +299,28 @@ def argmax_first(counts: np.ndarray) -> int:
     """thrust::max_element semantics (sfm.cu:135-136): first maximum.  The
     reference then subtracts one (sfm.cu:137, SURVEY Q13: a bug); we do not."""
     return int(np.argmax(counts))
+
+
+def adaptive_rounds(H_max: int, first_round: int, growth: int) -> list[int]:
+    """Round boundaries of the adaptive RANSAC: hypotheses tried after each round."""
+    out, hi = [], first_round
+    while True:
+        out.append(min(hi, H_max))
+        if hi >= H_max:
+            return out
+        hi *= growth
+
+
+def adaptive_used(best_after_round, n: int, confidence: float, bounds: list[int]) -> int:
+    """Adaptive termination (new functionality; the reference lists "limit on RANSAC
+    iterations" as future work, README.md:65-69): the textbook bound
+    needed = log(1 - p) / log(1 - w^8), w = best inlier ratio so far.  best_after_round[r] =
+    best inlier count (per pair: min over pairs decides) over hypotheses [0, bounds[r])."""
+    for r, done in enumerate(bounds):
+        w8 = (np.min(best_after_round[r]) / n) ** 8
+        if w8 >= 1.0 or (w8 > 0.0 and done >= math.log1p(-confidence) / math.log1p(-w8)):
+            return done
+    return bounds[-1]
 
 
 # --------------------------------------------------------------------------

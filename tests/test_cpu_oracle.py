@@ -199,3 +199,20 @@ def test_homography_oracle_recovers_planar_ground_truth(O):
     m = O.homography_mask_f32(Hc[b], x, 2.0)
     c64, amb = O.homography_counts(Hc[b][None], x, 2.0)
     assert abs(int(m.sum()) - int(c64[0])) <= int(amb[0]) + 1
+
+
+def test_adaptive_termination_rule(O):
+    """Restatement of the RANSAC stopping bound used to check sfmb200_estimate_e_adaptive."""
+    assert O.adaptive_rounds(1000, 64, 2) == [64, 128, 256, 512, 1000]
+    assert O.adaptive_rounds(64, 64, 4) == [64]
+    assert O.adaptive_rounds(65, 64, 4) == [64, 65]
+    b = O.adaptive_rounds(4096, 256, 2)
+    # w = 0.5: needed = ln(0.01) / ln(1 - 2^-8) = 1176.6 -> first boundary >= that is 2048
+    assert O.adaptive_used([np.array([50])] * len(b), 100, 0.99, b) == 2048
+    # perfect data stops after the first round; no inliers never stops early
+    assert O.adaptive_used([np.array([100])] * len(b), 100, 0.99, b) == 256
+    assert O.adaptive_used([np.array([0])] * len(b), 100, 0.99, b) == 4096
+    # a batch waits for its worst pair; improving counts stop earlier
+    assert O.adaptive_used([np.array([100, 50])] * len(b), 100, 0.99, b) == 2048
+    rising = [np.array([30]), np.array([50]), np.array([80]), np.array([80]), np.array([80])]
+    assert O.adaptive_used(rising, 100, 0.99, b) == 1024   # w=0.8: needed 25.1, reached when the count reaches 80
