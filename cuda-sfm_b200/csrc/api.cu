@@ -34,6 +34,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 struct sfmb200_handle {
     DeviceState s;
     RefitState refit;
+    BAState ba;
     cudaStream_t stream;
     bool own_stream;
     int device;
@@ -127,6 +128,15 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_ph = carve(B * 32 * sizeof(float));
     size_t o_pp = carve(B * 4 * (size_t)max_points * sizeof(float));
     size_t o_ad = carve(4 * sizeof(int));
+    const int ba_blocks = 64;
+    size_t o_bp = carve(B * 2 * 3 * (size_t)s.n_stride * sizeof(float));
+    size_t o_ba = carve(B * (size_t)s.n_stride);
+    size_t o_bc2 = carve(B * 24 * sizeof(float));
+    size_t o_bd = carve(B * 6 * sizeof(double));
+    size_t o_bi2 = carve(B * 8 * sizeof(int));
+    size_t o_bf = carve(B * 8 * sizeof(float));
+    size_t o_bpart = carve(B * ba_blocks * 34 * sizeof(double));
+    size_t o_bs = carve(B * 8 * sizeof(float));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
     size_t o_rT = carve(B * 8 * sizeof(float));
@@ -158,6 +168,15 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->pack_header = (float*)(base + o_ph);
     h->pack_points = (float*)(base + o_pp);
     h->adapt = (int*)(base + o_ad);
+    h->ba.pts = (float*)(base + o_bp);
+    h->ba.active = (unsigned char*)(base + o_ba);
+    h->ba.cam = (float*)(base + o_bc2);
+    h->ba.dc = (double*)(base + o_bd);
+    h->ba.ctl_i = (int*)(base + o_bi2);
+    h->ba.ctl_f = (float*)(base + o_bf);
+    h->ba.part = (double*)(base + o_bpart);
+    h->ba.stats = (float*)(base + o_bs);
+    h->ba.max_blocks = ba_blocks;
     h->refit.cand = (float*)(base + o_rc);
     h->refit.T = (float*)(base + o_rT);
     h->refit.flags = (int*)(base + o_rf);
@@ -465,6 +484,29 @@ int sfmb200_refine_e(sfmb200_t* h, int iterations) {
     h->have_pose = false;
     return SFMB200_OK;
 }
+// Bundle adjustment of the selected pose and the triangulated inliers with inlier re-selection
+// (bundle.cu).  Each outer round: inliers of the current E -> LM iterations -> refined camera,
+// E derived from it, cloud re-triangulated, inliers recounted.  h_stats (optional, host
+// [pairs][8]): active points, cost at entry, cost at exit, accepted steps, lambda, gauge scale,
+// inliers of the refined E, spare - of the LAST round.
+int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float* h_stats) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (outer_rounds < 1 || outer_rounds > 64 || iterations < 1 || iterations > 256)
+        return fail(SFMB200_ERR_ARG, "outer_rounds in [1, 64] and iterations in [1, 256] required%s");
+    if (!h->have_points || !h->have_E || !h->have_pose || h->model != 0)
+        return fail(SFMB200_ERR_STATE, "bundle_adjust needs an essential matrix and a chosen pose%s");
+    const float thr = h->thr > 0 ? h->thr : 1e-6f;
+    for (int r = 0; r < outer_rounds; r++) {
+        h->launches += launch_bundle_adjust(h->s, h->ba, thr, iterations, 1e-3f, h->tri_inliers_only, h->ba.stats, h->stream);
+        CKL();
+    }
+    if (h_stats) {
+        CK(cudaMemcpyAsync(h_stats, h->ba.stats, (size_t)h->s.B * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return SFMB200_OK;
+}
+
 int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_iters) {
     if (!h || !h_iters) return fail(SFMB200_ERR_ARG, "null argument%s");
     CK(cudaMemcpyAsync(h_iters, h->refit.iters_done, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

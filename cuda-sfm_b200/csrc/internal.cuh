@@ -62,6 +62,21 @@ struct RefitState {
 };
 int launch_refit(const DeviceState& s, const RefitState& r, float thr, int iterations, cudaStream_t st);
 
+// Scratch of the two-view bundle adjustment (bundle.cu), per pair.
+struct BAState {
+    float* pts;             // [B][2][3][n_stride] double-buffered 3-D points (SoA)
+    unsigned char* active;  // [B][n_stride] 1 = takes part in the adjustment
+    float* cam;             // [B][2][12] double-buffered camera 2: R row-major (9), t (3)
+    double* dc;             // [B][6] camera step of the current iteration
+    int* ctl_i;             // [B][8] see bundle.cu
+    float* ctl_f;           // [B][8]
+    double* part;           // [B][max_blocks][34] per-CTA partial sums
+    float* stats;           // [B][8] device copy of the statistics of the last round
+    int max_blocks;
+};
+int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int iterations, float lambda0,
+                         int tri_inliers_only, float* d_stats, cudaStream_t st);
+
 void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStream_t st);
 void launch_ingest_sift_filtered(const DeviceState& s, const void* d_sift, int n, float min_score, float max_ambiguity,
                                  int* d_scratch, int* d_kept_index, cudaStream_t st);

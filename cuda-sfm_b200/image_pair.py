@@ -150,6 +150,14 @@ class BatchedPairs:
         self.lib.call("sfmb200_get_refit_iterations", self._h, _hptr(out))
         return out
 
+    BA_STATS = ("active", "cost_entry", "cost", "accepted", "lambda", "gauge_scale", "inliers", "spare")
+
+    def bundle_adjust(self, outer_rounds: int = 3, iterations: int = 10) -> np.ndarray:
+        """Two-view bundle adjustment with inlier re-selection; returns the [pairs, 8] statistics of the last round (BA_STATS)."""
+        st = np.empty((self.pairs, 8), np.float32)
+        self.lib.call("sfmb200_bundle_adjust", self._h, outer_rounds, iterations, _hptr(st))
+        return st
+
     def pose_candidates(self):
         self.lib.call("sfmb200_pose_candidates", self._h)
 

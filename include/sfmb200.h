@@ -130,6 +130,22 @@ int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh
  * the current E through the 9x9 Jacobi eigensolve, rank-2 projection, re-score }, each accepted
  * only if it has more inliers.  Updates E and the inlier count in place; call after estimate_e. */
 int sfmb200_refine_e(sfmb200_t* h, int iterations);
+
+/* Two-view bundle adjustment with inlier re-selection ("bundle
+ * adjustment" is future work in the reference's README.md:65-69).  Needs a chosen pose.
+ * Refines the selected camera-2 matrix P[pose_index] (x1 ~ X, x2 ~ P X: the convention of
+ * linear_triangulation, sfm.cu:309-336) and the 3-D points of the inliers by Levenberg-
+ * Marquardt on the reprojection error in normalised coordinates; camera 1 stays [I|0], the
+ * gauge is |t| = 1.  Each of the `outer_rounds` rounds: inliers of the current E (same test
+ * and threshold as the estimate) that triangulate in front of both cameras -> `iterations`
+ * LM steps (point blocks eliminated by a Schur complement, 6x6 camera system) -> the refined
+ * camera replaces P[pose_index], E is replaced by the essential matrix of that camera, the
+ * whole cloud is re-triangulated (adjusted points for the active correspondences) and the
+ * inlier count of the new E replaces the best count.  Everything is enqueued on the handle's
+ * stream.  h_stats: NULL or host float [pairs][8] of the LAST round (forces a synchronise):
+ * active points, cost at entry, cost at exit (sum of squared residuals), accepted steps,
+ * lambda, gauge scale, inliers of the refined E, spare. */
+int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float* h_stats);
 int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_accepted /* [pairs] */);
 
 /* ---- poses: computePosecandidates (sfm.cu:238-252), choosePose (254-307) ---- */

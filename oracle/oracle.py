@@ -449,6 +449,139 @@ def choose_pose(x: np.ndarray, P: np.ndarray, compat: bool = True, mask: np.ndar
     return int(np.argmax(votes)), P.copy()
 
 
+# --------------------------------------------------------------------------
+# Two-view bundle adjustment (new functionality: "bundle adjustment" is the
+# reference's listed future work, README.md:65-69).
+# Restated in fp64 with the same parameterisation, damping schedule and
+# accept rule as cuda-sfm_b200/csrc/bundle.cu.
+# --------------------------------------------------------------------------
+def ba_active(x: np.ndarray, M: np.ndarray, X: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """Points that take part: inliers of the selected E (mask) whose triangulated
+    point is finite and in front of both cameras (x1 ~ X, x2 ~ M X)."""
+    Xc = X[:3].T
+    Y = Xc @ M[:3, :3].T + M[:3, 3]
+    return mask.astype(bool) & np.isfinite(Xc).all(1) & (Xc[:, 2] > 0) & (Y[:, 2] > 0)
+
+
+def ba_cost(x: np.ndarray, R: np.ndarray, t: np.ndarray, Xc: np.ndarray) -> float:
+    """Sum of squared reprojection errors in normalised coordinates, both views."""
+    Y = Xc @ R.T + t
+    r1 = Xc[:, :2] / Xc[:, 2:3] - x[:, 0:2]
+    r2 = Y[:, :2] / Y[:, 2:3] - x[:, 2:4]
+    return float((r1 * r1).sum() + (r2 * r2).sum())
+
+
+def _rodrigues(w: np.ndarray) -> np.ndarray:
+    th = float(np.linalg.norm(w))
+    Kx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + Kx
+    return np.eye(3) + (math.sin(th) / th) * Kx + ((1 - math.cos(th)) / (th * th)) * (Kx @ Kx)
+
+
+def bundle_adjust(x: np.ndarray, M: np.ndarray, X: np.ndarray, active: np.ndarray, iterations: int = 10,
+                  lambda0: float = 1e-3):
+    """Levenberg-Marquardt over (R, t) of camera 2 and the active 3-D points; camera 1 = [I|0].
+    Left-multiplicative rotation update R <- exp([dw]x) R; Marquardt damping lambda*diag on the
+    point blocks and on the reduced 6x6 camera system (Schur complement); a step is accepted iff
+    the cost decreases strictly (lambda /= 3, floor 1e-9), else rejected (lambda *= 4, cap 1e6).
+    Finally the gauge is fixed to |t| = 1 (points scaled alike).  Returns dict(M, X, cost0, cost,
+    accepted, n_active)."""
+    x = np.asarray(x, np.float64)
+    R, t = M[:3, :3].astype(np.float64).copy(), M[:3, 3].astype(np.float64).copy()
+    Xall = X[:3].T.astype(np.float64).copy()
+    act = np.flatnonzero(active)
+    xa = x[act]
+    Xc = Xall[act].copy()
+    lam, accepted = lambda0, 0
+    cost0 = cost = ba_cost(xa, R, t, Xc) if len(act) else 0.0
+    if len(act) >= 8:
+        for _ in range(iterations):
+            n = len(Xc)
+            iz = 1.0 / Xc[:, 2]
+            u, v = Xc[:, 0] * iz, Xc[:, 1] * iz
+            r1 = np.stack([u - xa[:, 0], v - xa[:, 1]], 1)
+            Jp1 = np.zeros((n, 2, 3))
+            Jp1[:, 0, 0] = iz; Jp1[:, 0, 2] = -u * iz
+            Jp1[:, 1, 1] = iz; Jp1[:, 1, 2] = -v * iz
+            Q = Xc @ R.T
+            Y = Q + t
+            iz2 = 1.0 / Y[:, 2]
+            u2, v2 = Y[:, 0] * iz2, Y[:, 1] * iz2
+            r2 = np.stack([u2 - xa[:, 2], v2 - xa[:, 3]], 1)
+            Jpi = np.zeros((n, 2, 3))
+            Jpi[:, 0, 0] = iz2; Jpi[:, 0, 2] = -u2 * iz2
+            Jpi[:, 1, 1] = iz2; Jpi[:, 1, 2] = -v2 * iz2
+            Jp2 = Jpi @ R
+            nQx = np.zeros((n, 3, 3))                      # -[Q]x
+            nQx[:, 0, 1] = Q[:, 2]; nQx[:, 0, 2] = -Q[:, 1]
+            nQx[:, 1, 0] = -Q[:, 2]; nQx[:, 1, 2] = Q[:, 0]
+            nQx[:, 2, 0] = Q[:, 1]; nQx[:, 2, 1] = -Q[:, 0]
+            Jc = np.concatenate([Jpi @ nQx, Jpi], axis=2)  # (n,2,6)
+            V = Jp1.transpose(0, 2, 1) @ Jp1 + Jp2.transpose(0, 2, 1) @ Jp2
+            gp = (Jp1.transpose(0, 2, 1) @ r1[:, :, None] + Jp2.transpose(0, 2, 1) @ r2[:, :, None])[:, :, 0]
+            Vd = V + lam * np.einsum("nii->ni", V)[:, :, None] * np.eye(3)
+            Vinv = np.linalg.inv(Vd)
+            W = Jc.transpose(0, 2, 1) @ Jp2                # (n,6,3)
+            U = Jc.transpose(0, 2, 1) @ Jc
+            gc = (Jc.transpose(0, 2, 1) @ r2[:, :, None])[:, :, 0]
+            Yw = W @ Vinv
+            A = (U - Yw @ W.transpose(0, 2, 1)).sum(0)
+            D = np.einsum("nii->i", U)
+            g = (gc - (Yw @ gp[:, :, None])[:, :, 0]).sum(0)
+            try:
+                dc = np.linalg.solve(A + lam * np.diag(D), -g)
+            except np.linalg.LinAlgError:
+                lam = min(lam * 4, 1e6)
+                continue
+            dp = -(Vinv @ (gp + (W.transpose(0, 2, 1) @ dc))[:, :, None])[:, :, 0]
+            Rn, tn, Xn = _rodrigues(dc[:3]) @ R, t + dc[3:], Xc + dp
+            Yn = Xn @ Rn.T + tn
+            ok = bool(np.all(Xn[:, 2] > 0) and np.all(Yn[:, 2] > 0))
+            cn = ba_cost(xa, Rn, tn, Xn) if ok else np.inf
+            if cn < cost:
+                R, t, Xc, cost = Rn, tn, Xn, cn
+                lam = max(lam / 3, 1e-9)
+                accepted += 1
+            else:
+                lam = min(lam * 4, 1e6)
+    sc = 1.0 / np.linalg.norm(t) if np.linalg.norm(t) > 0 else 1.0
+    Mo = np.eye(4)
+    Mo[:3, :3], Mo[:3, 3] = R, t * sc
+    Xo = triangulate(x, Mo)     # whole cloud under the refined camera; adjusted points for the active set
+    Xo[:3, act] = (Xc * sc).T
+    return dict(M=Mo, X=Xo, cost0=cost0, cost=cost, accepted=accepted, n_active=len(act))
+
+
+def essential_from_pose(M: np.ndarray) -> np.ndarray:
+    """E with x1^T E x2 = 0 for x1 ~ X, x2 ~ R X + t: E = ([t]x R)^T."""
+    R, t = M[:3, :3], M[:3, 3]
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    return (tx @ R).T
+
+
+def bundle_adjust_rounds(x: np.ndarray, M: np.ndarray, E: np.ndarray, thr: float = 1e-6, outer_rounds: int = 3,
+                         iterations: int = 10):
+    """Outer loop of sfmb200_bundle_adjust: inliers of the current E -> LM -> E from the
+    refined camera -> recount.  Returns dict(M, E, X, inliers, rounds=[per-round results])."""
+    M, E = np.asarray(M, np.float64), np.asarray(E, np.float64)
+    rounds = []
+    X = None
+    for _ in range(outer_rounds):
+        mask = sampson_mask_f32(E, x, thr)
+        X0 = triangulate(x, M)
+        act = ba_active(x, M, X0, mask)
+        if act.sum() < 8:
+            X = X0
+            rounds.append(dict(M=M, X=X0, cost0=0.0, cost=0.0, accepted=0, n_active=int(act.sum())))
+            continue
+        r = bundle_adjust(x, M, X0, act, iterations)
+        M, X = r["M"], r["X"]
+        E = essential_from_pose(M)
+        rounds.append(r)
+    return dict(M=M, E=E, X=X, inliers=int(sampson_mask_f32(E, x, thr).sum()), rounds=rounds)
+
+
 def to_vbo(points_soa: np.ndarray) -> np.ndarray:
     """kernCopyPositionsToVBO (kernels.h:471-483): 4xN SoA -> Nx4 AoS (x,y,z,1)."""
     out = points_soa.T.copy()
