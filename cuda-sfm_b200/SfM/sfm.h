@@ -122,6 +122,31 @@ public:
         check(sfmb200_set_points_sift_filtered(h_, data, num_points, minScore, maxAmbiguity, d_kept_index, &kept), "fillXU");
         return kept;
     }
+    // ---- beyond the reference (its README.md:52,65-69 future work) ----
+    // RANSAC that stops once log(1-confidence)/log(1-w^8) hypotheses were tried; returns the number tried
+    int estimateEAdaptive(int maxH, uint64_t seed, float threshold, float confidence = 0.99f, int firstRound = 1024, int growth = 4) {
+        int32_t used = 0;
+        check(sfmb200_estimate_e_adaptive(h_, nullptr, maxH, firstRound, growth, seed, threshold, confidence, &used), "estimateEAdaptive");
+        return used;
+    }
+    // LO-RANSAC refit of E on its inlier set; returns the accepted refits
+    int refineE(int iterations = 4) {
+        int32_t acc = 0;
+        check(sfmb200_refine_e(h_, iterations), "refineE");
+        check(sfmb200_get_refit_iterations(h_, &acc), "refineE");
+        return acc;
+    }
+    // CudaSift FindHomography semantics (matching.cu:907-1087) on this pair; returns the matches, H row-major 3x3
+    int findHomography(float H[9], int loops = 10000, float thresh = 5.0f, uint64_t seed = 0) {
+        int32_t matches = 0;
+        check(sfmb200_find_homography(h_, loops, seed, thresh, H, &matches), "findHomography");
+        return matches;
+    }
+    // bundle adjustment of the chosen pose and the inlier points, with inlier re-selection; stats: see sfmb200.h
+    void bundleAdjust(int outerRounds = 3, int iterations = 10, float stats[8] = nullptr) {
+        check(sfmb200_bundle_adjust(h_, outerRounds, iterations, stats), "bundleAdjust");
+        check(sfmb200_synchronize(h_), "bundleAdjust");
+    }
     void setCompat(bool reference_semantics) { check(sfmb200_set_option(h_, SFMB200_OPT_COMPAT, reference_semantics), "setCompat"); }
     void getE(float E[9]) { check(sfmb200_get_E(h_, E), "getE"); }
     void getPoses(float P[64]) { check(sfmb200_get_poses(h_, P), "getPoses"); }

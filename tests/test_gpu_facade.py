@@ -52,3 +52,17 @@ def test_facade_demo_matches_python_mirror(pkg, O, tmp_path):
     assert np.array_equal(P, ip.get_poses()[0].reshape(64))
     assert np.array_equal(vbo, O.to_vbo(ip.get_points_host()).astype(np.float32))
     assert np.all(col == 1)
+    # the additive 8f chain of the facade == the same chain through the Python mirror
+    h = ip
+    h.set_option(1, 0)
+    used = h.estimate_e_adaptive(8192, seed, 1e-6, 0.99, 256, 2)
+    refits = h.refine_e(4)
+    inl_refit = int(h.get_best()[1][0])
+    h.pose_candidates(); h.choose_pose(); h.triangulate()
+    st = h.bundle_adjust(3, 10)[0]
+    assert (info["adaptive_used"], info["refits"], info["inliers_refit"]) == (used, int(refits[0]), inl_refit)
+    assert info["inliers_ba"] == int(h.get_best()[1][0]) == int(st[6]) and info["inliers_ba"] >= inl_refit
+    assert info["ba_active"] == st[0] and np.float32(info["ba_cost"]) == st[2] and info["ba_cost"] <= info["ba_cost_entry"]
+    assert np.array_equal(np.asarray(info["E_ba"], np.float32), h.get_E()[0].reshape(9))
+    assert 0 <= info["h_matches"] <= n
+    h.close()
