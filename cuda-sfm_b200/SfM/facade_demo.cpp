@@ -147,8 +147,8 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 9; i++) err = fmaxf(err, fabsf(rec[i] - a[i]));
     printf("{\"n\": %d, \"as_built_inliers\": %d, \"H\": %d, \"best\": %d, \"inliers\": %d, \"pose_index\": %d, "
            "\"self_tests\": [%d,%d,%d,%d,%d,%d,%d], \"regular_svd\": %d, \"svd_recon_err\": %g, \"det\": %g, "
-           "\"adaptive_used\": %d, \"refits\": %d, \"inliers_refit\": %d, \"inliers_ba\": %d, \"ba_active\": %g, "
-           "\"ba_cost_entry\": %g, \"ba_cost\": %g, \"E_ba\": [%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g], \"h_matches\": %d}\n",
+           "\"adaptive_used\": %d, \"refits\": %d, \"inliers_refit\": %d, \"inliers_ba\": %d, \"ba_active\": %.9g, "
+           "\"ba_cost_entry\": %.9g, \"ba_cost\": %.9g, \"E_ba\": [%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g], \"h_matches\": %d}\n",
            n, inl_asbuilt, H, best, inliers, pind, t[0], t[1], t[2], t[3], t[4], t[5], t[6], (int)regular_ok, err, det(a),
            used, refits, inl_refit, inl_ba, ba[0], ba[1], ba[2], E_ba[0], E_ba[1], E_ba[2], E_ba[3], E_ba[4], E_ba[5], E_ba[6],
            E_ba[7], E_ba[8], hmatches);

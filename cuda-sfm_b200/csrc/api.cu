@@ -128,7 +128,8 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_ph = carve(B * 32 * sizeof(float));
     size_t o_pp = carve(B * 4 * (size_t)max_points * sizeof(float));
     size_t o_ad = carve(4 * sizeof(int));
-    const int ba_blocks = 64;
+    int ba_blocks = (592 + pairs - 1) / pairs;      // LM kernels: ~4 CTAs per SM over the whole batch
+    ba_blocks = ba_blocks < 2 ? 2 : (ba_blocks > 296 ? 296 : ba_blocks);
     size_t o_bp = carve(B * 2 * 3 * (size_t)s.n_stride * sizeof(float));
     size_t o_ba = carve(B * (size_t)s.n_stride);
     size_t o_bc2 = carve(B * 24 * sizeof(float));

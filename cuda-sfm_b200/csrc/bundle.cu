@@ -222,14 +222,14 @@ __global__ void __launch_bounds__(BA_THREADS) ba_accumulate_kernel(DeviceState s
         }
         acc[33] += cost;
     }
-    // fixed-order reduction: lanes -> warps -> CTA partial (fp64 from here on)
+    // fixed-order reduction: lanes (fp32 shuffles) -> warps -> CTA partial (fp64 from here on)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < BA_NSUM; k++) {
-        double v = (double)acc[k];
+        float v = acc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
-        if (lane == 0) red[warp * BA_NSUM + k] = v;
+        if (lane == 0) red[warp * BA_NSUM + k] = (double)v;
     }
     __syncthreads();
     double* part = ba.part + ((size_t)b * ba.max_blocks + blockIdx.x) * BA_NSUM;
@@ -244,10 +244,21 @@ __global__ void __launch_bounds__(BA_THREADS) ba_accumulate_kernel(DeviceState s
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // last CTA: BA_GROUPS groups of 34 threads each add a fixed stripe of the per-CTA partials, then 34 threads add the groups
+    constexpr int BA_GROUPS = BA_THREADS / BA_NSUM;
+    {
+        const int k = threadIdx.x % BA_NSUM, g = threadIdx.x / BA_NSUM;
+        if (g < BA_GROUPS) {
+            const double* all = ba.part + (size_t)b * ba.max_blocks * BA_NSUM;
+            double v = 0.0;
+            for (unsigned q = g; q < gridDim.x; q += BA_GROUPS) v += __ldcg(all + (size_t)q * BA_NSUM + k);
+            red[g * BA_NSUM + k] = v;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x < BA_NSUM) {
-        const double* all = ba.part + (size_t)b * ba.max_blocks * BA_NSUM;
         double v = 0.0;
-        for (unsigned k = 0; k < gridDim.x; k++) v += __ldcg(all + (size_t)k * BA_NSUM + threadIdx.x);
+        for (int g = 0; g < BA_GROUPS; g++) v += red[g * BA_NSUM + threadIdx.x];
         tot[threadIdx.x] = v;
     }
     __syncthreads();
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_update_kernel(DeviceState s, BA
     if (ci[3] < 8) return;
     __shared__ float sCam[12], sNew[12];
     __shared__ float sDc[6];
-    __shared__ double red[(BA_THREADS / 32) * 2];
+    __shared__ double red[64];
     __shared__ int s_last;
     const int cur = ci[0];
     const float lam = cf[0];
@@ -314,8 +325,9 @@ __global__ void __launch_bounds__(BA_THREADS) ba_update_kernel(DeviceState s, BA
     const unsigned char* active = ba.active + (size_t)b * s.n_stride;
     float cost = 0.0f, bad = 0.0f;
     for (int i = blockIdx.x * BA_THREADS + threadIdx.x; i < s.n; i += gridDim.x * BA_THREADS) {
+        if (!active[i]) continue;            // inactive points are never read back from the BA buffers
         float X[3] = {pts[i], pts[(size_t)s.n_stride + i], pts[(size_t)2 * s.n_stride + i]};
-        if (active[i]) {
+        {
             const float4 p = s.corr[(size_t)b * s.n_stride + i];
             float Vinv[6], W[18], gp[3], Jc[12], r2[2], c0;
             if (ba_linearise<false>(sCam, sCam + 9, p, X, lam, Vinv, W, gp, Jc, r2, c0)) {
@@ -366,12 +378,20 @@ __global__ void __launch_bounds__(BA_THREADS) ba_update_kernel(DeviceState s, BA
         s_last = (atomicAdd(&ci[2], 1) == (int)gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
+    if (!s_last) return;
     __threadfence();
+    if (threadIdx.x < 32) {                  // 32 fixed stripes of the per-CTA partials, then one thread adds the stripes
+        const double* all = ba.part + (size_t)b * ba.max_blocks * BA_NSUM;
+        double c = 0.0, bd = 0.0;
+        for (unsigned k = threadIdx.x; k < gridDim.x; k += 32) { c += __ldcg(all + (size_t)k * BA_NSUM); bd += __ldcg(all + (size_t)k * BA_NSUM + 1); }
+        red[2 * threadIdx.x] = c;
+        red[2 * threadIdx.x + 1] = bd;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     ci[2] = 0;
-    const double* all = ba.part + (size_t)b * ba.max_blocks * BA_NSUM;
     double c = 0.0, bd = 0.0;
-    for (unsigned k = 0; k < gridDim.x; k++) { c += __ldcg(all + (size_t)k * BA_NSUM); bd += __ldcg(all + (size_t)k * BA_NSUM + 1); }
+    for (int k = 0; k < 32; k++) { c += red[2 * k]; bd += red[2 * k + 1]; }
     const bool accept = ci[5] != 0 && bd == 0.0 && (float)c < cf[1];
     if (accept) {
         ci[0] = 1 - cur;
@@ -476,6 +496,8 @@ __global__ void ba_publish_kernel(DeviceState s, BAState ba, float* stats_out) {
 int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int iterations, float lambda0,
                          int tri_inliers_only, float* d_stats, cudaStream_t st) {
     int launches = 0;
+    // init / scatter: one thread per correspondence; LM kernels: at most max_blocks CTAs per pair (about four
+    // CTAs per SM over the whole batch, several correspondences per thread) so the per-CTA reductions stay cheap
     const int nb_all = (s.n + BA_THREADS - 1) / BA_THREADS;
     const int nb = nb_all < ba.max_blocks ? nb_all : ba.max_blocks;
     launch_triangulate(s, 1, thr, st);      // only inliers of the current E can become active
