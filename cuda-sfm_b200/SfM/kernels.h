@@ -131,6 +131,36 @@ inline void threshold_count(float* A, int* count_res, int batch_size, int ransac
 inline void row_extraction_kernel(float* d_vt, float* d_E, int number_points) {
     la_check(sfmb200_la_row_extraction(d_vt, d_E, number_points, nullptr), "row_extraction_kernel");
 }
+// host-callable forms of the reference's remaining hot-path kernels, same names and argument lists
+// (kernels.h:196-209, 236-295, 357-450, 471-495); call them as functions, without <<< >>>
+inline void transpose(float* odata, float* idata, int width, int height) {      // one height x width matrix
+    la_check(sfmb200_la_transpose_batched(idata, odata, height, width, 1, nullptr), "transpose");
+}
+inline void kernels(float* d1, float* d2, float* A, int* indices, const int ransac_iterations, int num_points) {
+    la_check(sfmb200_la_design_matrix(d1, d2, A, indices, ransac_iterations, num_points, nullptr), "kernels");
+}
+inline void copy_point(SiftPoint* data, int numPoints, float* U1, float* U2) {
+    la_check(sfmb200_la_copy_point(data, numPoints, U1, U2, nullptr), "copy_point");
+}
+inline void normalizeE(float* E, int ransac_iterations) { la_check(sfmb200_la_normalize_E(E, ransac_iterations, nullptr), "normalizeE"); }
+inline void candidate_kernels(float* d_P, const float* u, const float* v) {
+    la_check(sfmb200_la_candidate_poses(d_P, u, v, nullptr), "candidate_kernels");
+}
+inline void compute_linear_triangulation_A(float* A, const float* pt1, const float* pt2, const int count, const int num_points,
+                                           const float* m1, const float* m2, int P_ind, bool candidate_m2) {
+    la_check(sfmb200_la_triangulation_A(A, pt1, pt2, count, num_points, m1, m2, P_ind, candidate_m2, nullptr),
+             "compute_linear_triangulation_A");
+}
+inline void normalize_pt_kernal(float* v, float* converted_pt, int number_points) {
+    la_check(sfmb200_la_normalize_pt(v, converted_pt, number_points, nullptr), "normalize_pt_kernal");
+}
+inline void kernCopyPositionsToVBO(int N, float* pos, float* vbo, float s_scale) {
+    la_check(sfmb200_la_copy_to_vbo(N, pos, vbo, s_scale, nullptr), "kernCopyPositionsToVBO");
+}
+inline void kernCopyVelocitiesToVBO(int N, float* vbo, float s_scale) {
+    (void)s_scale;
+    la_check(sfmb200_la_copy_to_vbo(N, nullptr, vbo, 1.0f, nullptr), "kernCopyVelocitiesToVBO");
+}
 inline int max_element_index(const int* d_v, int n) {      // thrust::max_element(dv, dv + n) - dv
     int32_t idx = 0;
     la_check(sfmb200_la_argmax_first(d_v, n, &idx, nullptr), "max_element");

@@ -89,6 +89,13 @@ SIGNATURES = {
     "sfmb200_la_threshold_count": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, _vp]),
     "sfmb200_la_row_extraction": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "sfmb200_la_argmax_first": (C.c_int, [_vp, C.c_int, _i, _vp]),
+    "sfmb200_la_copy_point": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "sfmb200_la_design_matrix": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "sfmb200_la_normalize_E": (C.c_int, [_vp, C.c_int, _vp]),
+    "sfmb200_la_candidate_poses": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "sfmb200_la_triangulation_A": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "sfmb200_la_normalize_pt": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "sfmb200_la_copy_to_vbo": (C.c_int, [C.c_int, _vp, _vp, C.c_float, _vp]),
 }
 
 

@@ -225,6 +225,113 @@ __global__ void transpose_batched_kernel(const float* in, float* out, int rows, 
 
 int check() { return cudaGetLastError() == cudaSuccess ? 0 : -2; }
 
+
+// ---- the reference's hot-path kernels by name (SfM/kernels.h:236-295, 357-450, 471-495) as stand-alone
+// entry points.  The product path fuses all of these away (hypgen.cu, geometry.cu); they exist so that code
+// written against kernels.h keeps working, and as per-stage checkers. ----
+
+// copy_point (kernels.h:261-279): SiftPoint AoS (144 floats; xpos 0, ypos 1, match_xpos 9, match_ypos 10)
+// -> two 3xN SoA pixel arrays with a row of ones.
+__global__ void copy_point_kernel(const float* sift, int n, float* U1, float* U2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = sift + (size_t)i * 144;
+    U1[i] = p[0]; U1[n + i] = p[1]; U1[2 * (size_t)n + i] = 1.0f;
+    U2[i] = p[9]; U2[n + i] = p[10]; U2[2 * (size_t)n + i] = 1.0f;
+}
+
+// kernels::kernels (kernels.h:236-259): 8x9 design matrix per hypothesis, row = kron(x1, x2) of the sampled
+// correspondence; x1, x2 are 3xN SoA.  One thread per (hypothesis, row); guard h < H (the reference's
+// `index > ransac_iterations` lets one thread past the end).
+__global__ void design_matrix_kernel(const float* d1, const float* d2, float* A, const int* indices, int H, int n) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= H * 8) return;
+    int j = indices[t];
+    float a[3] = {d1[j], d1[n + j], d1[2 * (size_t)n + j]};
+    float b[3] = {d2[j], d2[n + j], d2[2 * (size_t)n + j]};
+    float* row = A + (size_t)t * 9;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) row[3 * r + c] = a[r] * b[c];
+}
+
+// normalizeE (kernels.h:281-295): E <- U diag(1,1,0) V^T per 3x3.
+__global__ void normalize_E_kernel(float* E, int H) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    float e[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) e[k] = E[(size_t)h * 9 + k];
+    sfmb200::project_essential(e);
+#pragma unroll
+    for (int k = 0; k < 9; k++) E[(size_t)h * 9 + k] = e[k];
+}
+
+// candidate_kernels (kernels.h:357-385): P_i = [ (u W v^T)^T | -+u[:,2] ; 0 0 0 1 ], W for i < 2, W^T for i >= 2,
+// sign -1 for i in {0, 2}.
+__global__ void candidate_poses_kernel(float* P, const float* u, const float* v) {
+    int i = threadIdx.x;
+    if (i >= 4) return;
+    const float W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1}, Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    float uu[9], vv[9], wv[9], R[9];
+    for (int k = 0; k < 9; k++) { uu[k] = u[k]; vv[k] = v[k]; }
+    sfmb200::mul33_ABt(i < 2 ? W : Wt, vv, wv);
+    sfmb200::mul33(uu, wv, R);
+    const float sg = (i == 0 || i == 2) ? -1.0f : 1.0f;
+    float* o = P + 16 * i;
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) o[4 * r + c] = R[3 * c + r];
+        o[4 * r + 3] = sg * uu[3 * r + 2];
+    }
+    o[12] = 0.0f; o[13] = 0.0f; o[14] = 0.0f; o[15] = 1.0f;
+}
+
+// compute_linear_triangulation_A (kernels.h:387-431): per index the 4x4
+// [x1 m1[2]-m1[0]; y1 m1[2]-m1[1]; x2 M[2]-M[0]; y2 M[2]-M[1]]; candidate_m2: index = candidate (M = m2[index]),
+// correspondence 0 only; otherwise index = correspondence, M = m2[P_ind].  Points are 3 x num_points SoA.
+__global__ void triangulation_A_kernel(float* A, const float* pt1, const float* pt2, int count, int num_points,
+                                       const float* m1, const float* m2, int P_ind, int candidate_m2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int j = candidate_m2 ? 0 : i;
+    const float* M = m2 + 16 * (candidate_m2 ? i : P_ind);
+    const float x1 = pt1[j], y1 = pt1[num_points + j], x2 = pt2[j], y2 = pt2[num_points + j];
+    float* o = A + (size_t)i * 16;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        o[c] = x1 * m1[8 + c] - m1[c];
+        o[4 + c] = y1 * m1[8 + c] - m1[4 + c];
+        o[8 + c] = x2 * M[8 + c] - M[c];
+        o[12 + c] = y2 * M[8 + c] - M[4 + c];
+    }
+}
+
+// normalize_pt_kernal (kernels.h:433-450): row 3 of each 4x4 block of v (the null vector as gesvdj stores it)
+// de-homogenised into a 4xN SoA; (0,0,0,1) when w == 0 or |w| > 5.
+__global__ void normalize_pt_kernel(const float* v, float* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = v + (size_t)i * 16 + 12;
+    const float w = r[3];
+    const bool zero = (w == 0.0f) || fabsf(w) > 5.0f;
+    out[i] = zero ? 0.0f : r[0] / w;
+    out[n + i] = zero ? 0.0f : r[1] / w;
+    out[2 * (size_t)n + i] = zero ? 0.0f : r[2] / w;
+    out[3 * (size_t)n + i] = 1.0f;
+}
+
+// kernCopyPositionsToVBO / kernCopyVelocitiesToVBO (kernels.h:471-495): 4xN SoA -> Nx4 AoS (x,y,z,1)*scale; colours = 1.
+__global__ void vbo_positions_kernel(int n, const float* pos, float* vbo, float scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    reinterpret_cast<float4*>(vbo)[i] = make_float4(pos[i] * scale, pos[n + i] * scale, pos[2 * (size_t)n + i] * scale, 1.0f);
+}
+__global__ void vbo_ones_kernel(int n, float* vbo) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) reinterpret_cast<float4*>(vbo)[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+}
+
 }  // namespace
 
 extern "C" {
@@ -312,6 +419,46 @@ int sfmb200_la_argmax_first(const int32_t* d_v, int n, int32_t* h_index, void* s
     cudaFree(d_out);
     *h_index = (int32_t)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
     return rc;
+}
+
+int sfmb200_la_copy_point(const void* d_sift, int n, float* U1, float* U2, void* stream) {
+    if (!d_sift || !U1 || !U2 || n < 1) return -1;
+    copy_point_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)d_sift, n, U1, U2);
+    return check();
+}
+int sfmb200_la_design_matrix(const float* d1, const float* d2, float* A, const int32_t* indices, int H, int n, void* stream) {
+    if (!d1 || !d2 || !A || !indices || H < 1 || n < 1) return -1;
+    design_matrix_kernel<<<(H * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d1, d2, A, indices, H, n);
+    return check();
+}
+int sfmb200_la_normalize_E(float* E, int H, void* stream) {
+    if (!E || H < 1) return -1;
+    normalize_E_kernel<<<(H + 127) / 128, 128, 0, (cudaStream_t)stream>>>(E, H);
+    return check();
+}
+int sfmb200_la_candidate_poses(float* d_P, const float* d_u, const float* d_v, void* stream) {
+    if (!d_P || !d_u || !d_v) return -1;
+    candidate_poses_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_P, d_u, d_v);
+    return check();
+}
+int sfmb200_la_triangulation_A(float* A, const float* pt1, const float* pt2, int count, int num_points, const float* m1,
+                               const float* m2, int P_ind, int candidate_m2, void* stream) {
+    if (!A || !pt1 || !pt2 || !m1 || !m2 || count < 1 || num_points < 1 || P_ind < 0 || P_ind > 3) return -1;
+    if (candidate_m2 && count != 4) return -1;
+    triangulation_A_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, pt1, pt2, count, num_points, m1, m2,
+                                                                                   P_ind, candidate_m2);
+    return check();
+}
+int sfmb200_la_normalize_pt(const float* v, float* out, int n, void* stream) {
+    if (!v || !out || n < 1) return -1;
+    normalize_pt_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(v, out, n);
+    return check();
+}
+int sfmb200_la_copy_to_vbo(int n, const float* pos_4xN, float* vbo, float scale, void* stream) {
+    if (!vbo || n < 1) return -1;
+    if (pos_4xN) vbo_positions_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, pos_4xN, vbo, scale);
+    else vbo_ones_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, vbo);
+    return check();
 }
 
 }  // extern "C"

@@ -137,3 +137,86 @@ def test_elementwise_vecnorm_threshold_argmax(lib, T):
     big = T.from_numpy(rng.integers(0, 1000, 100000).astype(np.int32)).cuda()
     lib.call("sfmb200_la_argmax_first", dp(big), 100000, C.byref(idx), None)
     assert idx.value == int(np.argmax(big.cpu().numpy()))
+
+
+def test_reference_stage_kernels_by_name(lib, T, O):
+    """The reference's estimateE / pose / triangulation stages written with the kernels.h names
+    (copy_point, gpu_blas_mmul, kernels, transpose, regular_svd, row_extraction_kernel, normalizeE,
+    candidate_kernels, compute_linear_triangulation_A, svd_square, normalize_pt_kernal, kernCopy*ToVBO)
+    against the fp64 restatement, stage by stage (sfm.cu:80-129, 238-252, 309-336, 374-383)."""
+    n, H = 600, 40
+    K, Kinv = O.reference_K()
+    sc = O.synthetic_pair(n, seed=13)
+    x = O.normalise_points(sc["px"], Kinv)
+    sift = np.zeros((n, 144), np.float32)
+    sift[:, 0], sift[:, 1], sift[:, 9], sift[:, 10] = sc["px"].T
+    d_sift = T.from_numpy(sift).cuda()
+    U1, U2 = T.empty((3, n), device="cuda"), T.empty((3, n), device="cuda")
+    lib.call("sfmb200_la_copy_point", dp(d_sift), n, dp(U1), dp(U2), None)
+    assert np.array_equal(U1.cpu().numpy(), np.vstack([sc["px"][:, :2].T, np.ones(n, np.float32)]))
+    assert np.array_equal(U2.cpu().numpy(), np.vstack([sc["px"][:, 2:].T, np.ones(n, np.float32)]))
+    dK = T.from_numpy(np.asarray(Kinv, np.float32).reshape(3, 3)).cuda()
+    X1, X2 = T.empty((3, n), device="cuda"), T.empty((3, n), device="cuda")
+    lib.call("sfmb200_la_mmul", dp(dK), dp(U1), dp(X1), 3, 3, n, None)
+    lib.call("sfmb200_la_mmul", dp(dK), dp(U2), dp(X2), 3, 3, n, None)
+    assert np.allclose(X1.cpu().numpy()[:2].T, x[:, :2], atol=1e-6) and np.allclose(X2.cpu().numpy()[:2].T, x[:, 2:], atol=1e-6)
+    # design matrices -> null vectors -> E candidates
+    idx = O.sample_indices(3, H, n).astype(np.int32)
+    d_idx = T.from_numpy(idx).cuda()
+    A = T.empty((H, 8, 9), device="cuda")
+    lib.call("sfmb200_la_design_matrix", dp(X1), dp(X2), dp(A), dp(d_idx), H, n, None)
+    want_A = np.stack([O.design_matrix(x[idx[h]]) for h in range(H)])
+    assert np.allclose(A.cpu().numpy(), want_A, atol=1e-6)
+    At = T.empty((H, 9, 8), device="cuda")
+    lib.call("sfmb200_la_transpose_batched", dp(A), dp(At), 8, 9, H, None)
+    S, Uo, Vo = T.empty((H, 8), device="cuda"), T.empty((H, 64), device="cuda"), T.empty((H, 81), device="cuda")
+    lib.call("sfmb200_la_svd_batched", dp(At), dp(S), dp(Uo), dp(Vo), 8, 9, H, None)
+    E = T.empty((H, 9), device="cuda")
+    lib.call("sfmb200_la_row_extraction", dp(Vo), dp(E), H, None)
+    lib.call("sfmb200_la_normalize_E", dp(E), H, None)
+    Eo = O.hypotheses(x, idx)
+    dist = O.e_distance(E.cpu().numpy().reshape(H, 3, 3), Eo)
+    assert (dist < 1e-3).mean() > 0.9, dist
+    sv = np.linalg.svd(E.cpu().numpy().reshape(H, 3, 3).astype(np.float64), compute_uv=False)
+    assert np.allclose(sv, np.array([1, 1, 0])[None], atol=1e-5)
+    # pose candidates from a host SVD of the first candidate, like computePosecandidates (sfm.cu:239-250)
+    u, _, v = O.svd_rot(Eo[0])
+    if O.det_reference_typo(u @ v.T) < 0:
+        v = -v
+    du, dv = T.from_numpy(u.astype(np.float32)).cuda(), T.from_numpy(v.astype(np.float32)).cuda()
+    dP = T.empty((4, 4, 4), device="cuda")
+    lib.call("sfmb200_la_candidate_poses", dp(dP), dp(du), dp(dv), None)
+    P = dP.cpu().numpy().astype(np.float64)
+    Wm = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    for i in range(4):
+        R = (u @ (Wm if i < 2 else Wm.T) @ v.T).T
+        t = (-1 if i in (0, 2) else 1) * u[:, 2]
+        assert np.allclose(P[i, :3, :3], R, atol=1e-6) and np.allclose(P[i, :3, 3], t, atol=1e-6) and np.allclose(P[i, 3], [0, 0, 0, 1])
+    # triangulation: A per point with camera 2 = P[1], 4x4 SVD, de-homogenise, VBO
+    I4 = T.eye(4, device="cuda")
+    A4 = T.empty((n, 4, 4), device="cuda")
+    lib.call("sfmb200_la_triangulation_A", dp(A4), dp(X1), dp(X2), n, n, dp(I4), dp(dP), 1, 0, None)
+    assert np.allclose(A4.cpu().numpy(), O.dlt_rows(x, P[1]), atol=1e-6)
+    A4c = T.empty((4, 4, 4), device="cuda")
+    lib.call("sfmb200_la_triangulation_A", dp(A4c), dp(X1), dp(X2), 4, n, dp(I4), dp(dP), 0, 1, None)
+    assert np.allclose(A4c.cpu().numpy(), np.stack([O.dlt_rows(x[:1], P[i])[0] for i in range(4)]), atol=1e-6)
+    A4t = T.empty((n, 4, 4), device="cuda")
+    lib.call("sfmb200_la_transpose_batched", dp(A4), dp(A4t), 4, 4, n, None)
+    S4, U4, V4 = T.empty((n, 4), device="cuda"), T.empty((n, 16), device="cuda"), T.empty((n, 16), device="cuda")
+    lib.call("sfmb200_la_svd_batched", dp(A4t), dp(S4), dp(U4), dp(V4), 4, 4, n, None)
+    pts = T.empty((4, n), device="cuda")
+    lib.call("sfmb200_la_normalize_pt", dp(V4), dp(pts), n, None)
+    want = O.triangulate(x, P[1])
+    got = pts.cpu().numpy()
+    ok = (np.abs(want[2]) < 50) & (np.abs(want[2]) > 1e-3)
+    assert ok.mean() > 0.6 and np.all(got[3] == 1)
+    assert np.median(np.abs(got[:3, ok] - want[:3, ok]) / (np.abs(want[:3, ok]) + 1e-3)) < 1e-3
+    v0 = T.tensor([[0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 4, 6, 2], [0] * 12 + [1, 1, 1, 0], [0] * 12 + [6, 6, 6, 6]],
+                  dtype=T.float32, device="cuda")
+    o3 = T.empty((4, 3), device="cuda")
+    lib.call("sfmb200_la_normalize_pt", dp(v0), dp(o3), 3, None)
+    assert np.array_equal(o3.cpu().numpy(), np.array([[1, 0, 0], [2, 0, 0], [3, 0, 0], [1, 1, 1]], np.float32))   # w = 0 and |w| > 5 -> origin
+    vbo, col = T.empty((n, 4), device="cuda"), T.zeros((n, 4), device="cuda")
+    lib.call("sfmb200_la_copy_to_vbo", n, dp(pts), dp(vbo), C.c_float(2.0), None)
+    lib.call("sfmb200_la_copy_to_vbo", n, None, dp(col), C.c_float(1.0), None)
+    assert np.array_equal(vbo.cpu().numpy()[:, :3], 2 * got[:3].T) and np.all(vbo.cpu().numpy()[:, 3] == 1) and np.all(col.cpu().numpy() == 1)
