@@ -183,7 +183,8 @@ def test_reference_stage_kernels_by_name(lib, T, O):
     u, _, v = O.svd_rot(Eo[0])
     if O.det_reference_typo(u @ v.T) < 0:
         v = -v
-    du, dv = T.from_numpy(u.astype(np.float32)).cuda(), T.from_numpy(v.astype(np.float32)).cuda()
+    du = T.from_numpy(np.ascontiguousarray(u, dtype=np.float32)).cuda()
+    dv = T.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).cuda()       # V = Vt.T is a strided view
     dP = T.empty((4, 4, 4), device="cuda")
     lib.call("sfmb200_la_candidate_poses", dp(dP), dp(du), dp(dv), None)
     P = dP.cpu().numpy().astype(np.float64)
