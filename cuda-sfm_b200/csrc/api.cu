@@ -35,6 +35,8 @@ struct sfmb200_handle {
     DeviceState s;
     RefitState refit;
     BAState ba;
+    ChainState chain;
+    void* chain_arena;     // lazily allocated by sfmb200_chain_views
     cudaStream_t stream;
     bool own_stream;
     int device;
@@ -214,6 +216,7 @@ int sfmb200_destroy(sfmb200_t* h) {
         delete[] h->prof_mask;
     }
     cudaFree(h->arena);
+    if (h->chain_arena) cudaFree(h->chain_arena);
     delete h;
     return SFMB200_OK;
 }
@@ -505,6 +508,40 @@ int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float*
         CK(cudaMemcpyAsync(h_stats, h->ba.stats, (size_t)h->s.B * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    return SFMB200_OK;
+}
+
+// N-view chaining (chain.cu): pairs of the handle = consecutive view pairs over index-aligned tracks.
+int sfmb200_chain_views(sfmb200_t* h, float* d_cloud, int32_t* d_count, float* h_cameras, float* h_scales, int32_t* h_used) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (h->s.B > 256) return fail(SFMB200_ERR_ARG, "chain_views handles at most 256 pairs (257 views)%s");
+    if (!h->have_points || !h->have_E || !h->have_pose || h->model != 0)
+        return fail(SFMB200_ERR_STATE, "chain_views needs an essential matrix, a chosen pose and triangulated points per pair%s");
+    const size_t B = h->s.B;
+    if (!h->chain_arena) {
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+        size_t o_h = carve(B * 2048 * sizeof(int)), o_m = carve(B * sizeof(int)), o_u = carve(B * sizeof(int));
+        size_t o_s = carve(B * sizeof(unsigned long long)), o_c = carve(B * sizeof(int)), o_sc = carve(B * sizeof(float));
+        size_t o_cs = carve(B * sizeof(float)), o_cam = carve((B + 1) * 12 * sizeof(float));
+        CK(cudaMalloc(&h->chain_arena, off));
+        char* base = (char*)h->chain_arena;
+        h->chain.hist = (int*)(base + o_h);
+        h->chain.median_bin = (int*)(base + o_m);
+        h->chain.used = (int*)(base + o_u);
+        h->chain.bin_sum = (unsigned long long*)(base + o_s);
+        h->chain.bin_cnt = (int*)(base + o_c);
+        h->chain.scales = (float*)(base + o_sc);
+        h->chain.cum_scales = (float*)(base + o_cs);
+        h->chain.cameras = (float*)(base + o_cam);
+        CK(cudaMemsetAsync(h->chain_arena, 0, off, h->stream));
+    }
+    h->launches += launch_chain(h->s, h->chain, h->thr > 0 ? h->thr : 1e-6f, d_cloud, d_count, h->stream);
+    CKL();
+    if (h_cameras) CK(cudaMemcpyAsync(h_cameras, h->chain.cameras, (B + 1) * 12 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_scales) CK(cudaMemcpyAsync(h_scales, h->chain.scales, B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_used) CK(cudaMemcpyAsync(h_used, h->chain.used, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h_cameras || h_scales || h_used) CK(cudaStreamSynchronize(h->stream));
     return SFMB200_OK;
 }
 

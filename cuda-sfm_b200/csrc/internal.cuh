@@ -74,6 +74,19 @@ struct BAState {
     float* stats;           // [B][8] device copy of the statistics of the last round
     int max_blocks;
 };
+// Scratch and results of the N-view chaining stage (chain.cu); allocated on first use.
+struct ChainState {
+    int* hist;                      // [B][2048] log-ratio histograms of the links
+    int* median_bin;                // [B]
+    int* used;                      // [B] tracks linking pair b-1 and b
+    unsigned long long* bin_sum;    // [B] fixed-point sum of the log ratios in the median bin
+    int* bin_cnt;                   // [B]
+    float* scales;                  // [B] scale of pair b relative to pair b-1 (scale[0] = 1)
+    float* cum_scales;              // [B]
+    float* cameras;                 // [B+1][12] world (camera 0) -> camera k, row-major 3x4
+};
+int launch_chain(const DeviceState& s, const ChainState& c, float thr, float* d_cloud, int* d_count, cudaStream_t st);
+
 int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int iterations, float lambda0,
                          int tri_inliers_only, float* d_stats, cudaStream_t st);
 

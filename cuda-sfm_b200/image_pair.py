@@ -152,11 +152,23 @@ class BatchedPairs:
 
     BA_STATS = ("active", "cost_entry", "cost", "accepted", "lambda", "gauge_scale", "inliers", "spare")
 
-    def bundle_adjust(self, outer_rounds: int = 3, iterations: int = 10) -> np.ndarray:
+    def bundle_adjust(self, outer_rounds: int = 4, iterations: int = 40) -> np.ndarray:
         """Two-view bundle adjustment with inlier re-selection; returns the [pairs, 8] statistics of the last round (BA_STATS)."""
         st = np.empty((self.pairs, 8), np.float32)
         self.lib.call("sfmb200_bundle_adjust", self._h, outer_rounds, iterations, _hptr(st))
         return st
+
+    def chain_views(self, want_cloud: bool = True):
+        """N-view chaining over consecutive pairs with index-aligned tracks; returns dict(cameras [pairs+1,3,4],
+        scales [pairs], used [pairs], cloud torch [4,n] or None, count torch [n] or None)."""
+        torch = _torch()
+        cams = np.empty((self.pairs + 1, 3, 4), np.float32)
+        scales = np.empty(self.pairs, np.float32)
+        used = np.empty(self.pairs, np.int32)
+        cloud = torch.empty((4, self.n), dtype=torch.float32, device="cuda") if want_cloud else None
+        count = torch.empty(self.n, dtype=torch.int32, device="cuda") if want_cloud else None
+        self.lib.call("sfmb200_chain_views", self._h, _dptr(cloud), _dptr(count), _hptr(cams), _hptr(scales), _hptr(used))
+        return dict(cameras=cams, scales=scales, used=used, cloud=cloud, count=count)
 
     def pose_candidates(self):
         self.lib.call("sfmb200_pose_candidates", self._h)

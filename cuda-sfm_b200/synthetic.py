@@ -73,6 +73,57 @@ def synthetic_pair(n: int, outlier_frac: float = 0.3, noise_px: float = 1.0, see
     return {"px": px.astype(np.float32), "R": R, "t": t, "is_outlier": is_out, "X": X}
 
 
+def synthetic_sequence(views: int, n: int, outlier_frac: float = 0.2, noise_px: float = 0.5, seed: int = 4321,
+                       step_deg: float = -6.0, depth=(4.0, 8.0)):
+    """N-view scene for the pose-chaining stage: camera 0 = [I|0], camera k+1 =
+    [R_s | t_k] * camera k with R_s = step_deg about (0.1, 1, 0.05) verging towards the scene and
+    baselines of DIFFERENT lengths along (1, 0.05, 0.1), so that the relative scales are not all 1.
+    Every one of the n tracks is visible in every view (index-aligned tracks); per view k >= 1 a fraction
+    of the observations is replaced by uniform pixels.
+
+    Returns dict: px_views (views, n, 2) float32, px_pairs (views-1, n, 4) float32 = (view b, view b+1),
+    G (views, 4, 4) world(camera 0)->camera k, X (n, 3), is_outlier (views, n), baselines (views-1,)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f, cx, cy = F_REF, W_REF / 2.0, H_REF / 2.0
+    Rs = _rot([0.1, 1.0, 0.05], step_deg)
+    tdir = np.array([1.0, 0.05, 0.1])
+    tdir = tdir / np.linalg.norm(tdir)
+    baselines = 0.5 + 0.5 * rng.random(views - 1)
+    G = [np.eye(4)]
+    for k in range(views - 1):
+        S = np.eye(4)
+        S[:3, :3], S[:3, 3] = Rs, tdir * baselines[k]
+        G.append(S @ G[-1])
+    G = np.stack(G)
+    Xs, have = [], 0
+    while have < n:
+        m = max(4 * (n - have), 1024)
+        z = rng.uniform(depth[0], depth[1], m)
+        X = np.stack([rng.uniform(-1.2, 1.2, m) * z * (cx / f), rng.uniform(-1.2, 1.2, m) * z * (cy / f), z], 1)
+        ok = np.ones(m, bool)
+        for k in range(views):
+            Y = X @ G[k, :3, :3].T + G[k, :3, 3]
+            u, v = f * Y[:, 0] / Y[:, 2] + cx, f * Y[:, 1] / Y[:, 2] + cy
+            ok &= (Y[:, 2] > 0) & (u >= 0) & (u < W_REF) & (v >= 0) & (v < H_REF)
+        Xs.append(X[ok])
+        have += int(ok.sum())
+    X = np.concatenate(Xs)[:n]
+    px = np.empty((views, n, 2))
+    for k in range(views):
+        Y = X @ G[k, :3, :3].T + G[k, :3, 3]
+        px[k, :, 0], px[k, :, 1] = f * Y[:, 0] / Y[:, 2] + cx, f * Y[:, 1] / Y[:, 2] + cy
+    px += rng.normal(0.0, noise_px, px.shape)
+    is_out = np.zeros((views, n), bool)
+    for k in range(1, views):
+        is_out[k] = rng.random(n) < outlier_frac
+        c = int(is_out[k].sum())
+        px[k, is_out[k], 0] = rng.uniform(0, W_REF, c)
+        px[k, is_out[k], 1] = rng.uniform(0, H_REF, c)
+    px = px.astype(np.float32)
+    pairs = np.stack([np.concatenate([px[b], px[b + 1]], 1) for b in range(views - 1)])
+    return {"px_views": px, "px_pairs": pairs, "G": G, "X": X, "is_outlier": is_out, "baselines": baselines}
+
+
 def planar_pair(n: int, outlier_frac: float = 0.3, noise_px: float = 0.5, seed: int = 7):
     """Correspondences of a planar scene (points on a slanted plane seen by the same two
     cameras as synthetic_pair): image 2 = H(image 1) + noise, plus uniform outliers.

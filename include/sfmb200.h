@@ -146,6 +146,20 @@ int sfmb200_refine_e(sfmb200_t* h, int iterations);
  * active points, cost at entry, cost at exit (sum of squared residuals), accepted steps,
  * lambda, gauge scale, inliers of the refined E, spare. */
 int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float* h_stats);
+/* N-view chaining (the reference shapes Image_pair for image_count views,
+ * sfm.h:23,30-31, but handles two).  The handle's pairs are CONSECUTIVE view pairs - pair b =
+ * (view b, view b+1) - over index-aligned tracks: correspondence i is the same track in every
+ * pair.  After every pair has an E, a chosen pose and triangulated points (and ideally
+ * sfmb200_bundle_adjust), this puts them in one frame: relative scale of pair b against pair
+ * b-1 = median-bin mean of the depth ratios of the tracks valid in both (valid = inlier of the
+ * pair's E, point finite and in front of both cameras); cameras G_0 = [I|0],
+ * G_{b+1} = [R_b | S_b t_b] G_b in units of the first baseline; cloud = per track the mean over
+ * the pairs where it is valid of G_b^-1 (S_b X_b).  At most 256 pairs.
+ * d_cloud: NULL or device float [4][n] SoA (x,y,z,1; zeros when no pair sees the track);
+ * d_count: NULL or device int32 [n] pairs that saw the track; h_cameras: NULL or host float
+ * [pairs+1][12] row-major 3x4; h_scales: NULL or host float [pairs]; h_used: NULL or host int32
+ * [pairs] tracks that linked pair b-1 and b.  Host outputs force a synchronise. */
+int sfmb200_chain_views(sfmb200_t* h, float* d_cloud, int32_t* d_count, float* h_cameras, float* h_scales, int32_t* h_used);
 int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_accepted /* [pairs] */);
 
 /* ---- poses: computePosecandidates (sfm.cu:238-252), choosePose (254-307) ---- */

@@ -43,6 +43,7 @@ F_REF, W_REF, H_REF = _synthetic.F_REF, _synthetic.W_REF, _synthetic.H_REF
 reference_K = _synthetic.reference_K
 synthetic_pair = _synthetic.synthetic_pair
 planar_pair = _synthetic.planar_pair
+synthetic_sequence = _synthetic.synthetic_sequence
 
 
 def normalise_points(px: np.ndarray, Kinv: np.ndarray) -> np.ndarray:
@@ -580,6 +581,76 @@ def bundle_adjust_rounds(x: np.ndarray, M: np.ndarray, E: np.ndarray, thr: float
         E = essential_from_pose(M)
         rounds.append(r)
     return dict(M=M, E=E, X=X, inliers=int(sampson_mask_f32(E, x, thr).sum()), rounds=rounds)
+
+
+# --------------------------------------------------------------------------
+# N-view chaining of consecutive pairs (new functionality, SURVEY.md 8f rank 4:
+# the reference shapes Image_pair for image_count views, sfm.h:23,30-31, but only
+# ever handles two).  Pair b = (view b, view b+1); correspondence i is the same
+# track in every pair.  Restates cuda-sfm_b200/csrc/chain.cu.
+# --------------------------------------------------------------------------
+CHAIN_BINS = 2048
+CHAIN_LOG_RANGE = math.log(16.0)      # ratios in [1/16, 16]
+
+
+def chain_valid(x: np.ndarray, M: np.ndarray, X: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """A track contributes from a pair when it is an inlier of the pair's E and its point is finite and in
+    front of both cameras."""
+    return ba_active(x, M, X, mask)
+
+
+def chain_scales(Ms, Xs, valids):
+    """scale[b] (b >= 1) = robust central value of depth_in_camera_b(pair b-1) / depth_in_camera_b(pair b)
+    over the tracks valid in both pairs: median bin of a 2048-bin histogram of the log ratio over
+    [ln 1/16, ln 16], refined to the mean log ratio of the entries of that bin.  scale[0] = 1.
+    Also returns the number of tracks used."""
+    B = len(Ms)
+    scales, used = np.ones(B), np.zeros(B, int)
+    for b in range(1, B):
+        both = valids[b - 1] & valids[b]
+        Xp = Xs[b - 1][:3].T[both]
+        zprev = Xp @ Ms[b - 1][2, :3] + Ms[b - 1][2, 3]
+        zcur = Xs[b][2][both]
+        lr = np.log(zprev / zcur)
+        ok = np.isfinite(lr) & (np.abs(lr) < CHAIN_LOG_RANGE)
+        lr = lr[ok]
+        used[b] = len(lr)
+        if len(lr) == 0:
+            continue
+        bins = np.minimum(((lr + CHAIN_LOG_RANGE) * (CHAIN_BINS / (2 * CHAIN_LOG_RANGE))).astype(int), CHAIN_BINS - 1)
+        hist = np.bincount(bins, minlength=CHAIN_BINS)
+        cum = np.cumsum(hist)
+        mb = int(np.searchsorted(cum, (len(lr) + 1) // 2))
+        scales[b] = math.exp(lr[bins == mb].mean())
+    return scales, used
+
+
+def chain_cameras(Ms, scales):
+    """Global world(camera 0) -> camera k matrices in units of the first baseline:
+    G_0 = I, G_{b+1} = [R_b | S_b t_b] G_b with S_b = prod_{j<=b} scale[j]."""
+    G = [np.eye(4)]
+    S = np.cumprod(scales)
+    for b, M in enumerate(Ms):
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = M[:3, :3], S[b] * M[:3, 3]
+        G.append(T @ G[-1])
+    return np.stack(G), S
+
+
+def chain_merge(Xs, valids, G, S):
+    """Global position of every track: mean over the pairs where it is valid of G_b^-1 (S_b X_b);
+    (0,0,0,1) and count 0 when no pair sees it."""
+    n = Xs[0].shape[1]
+    acc, cnt = np.zeros((3, n)), np.zeros(n, int)
+    for b, X in enumerate(Xs):
+        R, t = G[b][:3, :3], G[b][:3, 3]
+        W = R.T @ (S[b] * X[:3] - t[:, None])
+        acc[:, valids[b]] += W[:, valids[b]]
+        cnt += valids[b]
+    out = np.zeros((4, n))
+    out[:3, cnt > 0] = acc[:, cnt > 0] / cnt[cnt > 0]
+    out[3] = 1.0
+    return out, cnt
 
 
 def to_vbo(points_soa: np.ndarray) -> np.ndarray:

@@ -216,3 +216,28 @@ def test_adaptive_termination_rule(O):
     assert O.adaptive_used([np.array([100, 50])] * len(b), 100, 0.99, b) == 2048
     rising = [np.array([30]), np.array([50]), np.array([80]), np.array([80]), np.array([80])]
     assert O.adaptive_used(rising, 100, 0.99, b) == 1024   # w=0.8: needed 25.1, reached when the count reaches 80
+
+
+def test_chain_restatement_on_exact_reconstructions(O):
+    """Chaining of per-pair reconstructions built from ground truth recovers baselines, cameras and points."""
+    views, n = 4, 500
+    sc = O.synthetic_sequence(views, n, outlier_frac=0.0, noise_px=0.0, seed=5)
+    Ms, Xs, valids = [], [], []
+    for b in range(views - 1):
+        Grel = sc["G"][b + 1] @ np.linalg.inv(sc["G"][b])
+        bl = np.linalg.norm(Grel[:3, 3])
+        M = Grel.copy()
+        M[:3, 3] /= bl                                              # unit baseline, like the two-view path
+        Xb = (sc["X"] @ sc["G"][b][:3, :3].T + sc["G"][b][:3, 3]) / bl   # points in camera b's frame, pair units
+        Ms.append(M)
+        Xs.append(np.vstack([Xb.T, np.ones(n)]))
+        valids.append(np.ones(n, bool))
+    scales, used = O.chain_scales(Ms, Xs, valids)
+    assert np.all(used[1:] == n)
+    assert np.allclose(scales[1:], sc["baselines"][1:] / sc["baselines"][:-1], rtol=1e-9)
+    G, S = O.chain_cameras(Ms, scales)
+    Gt = sc["G"].copy()
+    Gt[:, :3, 3] /= sc["baselines"][0]
+    assert np.allclose(G, Gt, atol=1e-9)
+    cloud, cnt = O.chain_merge(Xs, valids, G, S)
+    assert np.all(cnt == views - 1) and np.allclose(cloud[:3].T, sc["X"] / sc["baselines"][0], atol=1e-9)
