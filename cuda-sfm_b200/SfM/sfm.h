@@ -57,15 +57,17 @@ class Image_pair {
     }
 
 public:
-    // k, k_inv: host 3x3 row-major; image_count must be 2; num_points = correspondences.
+    // k, k_inv: host 3x3 row-major; num_points = correspondences per pair.  image_count = 2 is the reference's
+    // only use (main.cpp:298); image_count > 2 = a sequence: image_count - 1 consecutive pairs over index-aligned
+    // tracks, filled with fillXU(d_pixels [pairs][n][4], n), every stage batched, chainViews() at the end.
     Image_pair(float k[9], float k_inv[9], int image_count, int num_points)
         : image_count(image_count), num_points(num_points) {
-        if (image_count != 2) {
-            fprintf(stderr, "Image_pair handles exactly two images\n");
+        if (image_count < 2 || image_count > 257) {
+            fprintf(stderr, "Image_pair handles 2 to 257 images\n");
             exit(EXIT_FAILURE);
         }
         int max_h = num_points / 8 > 0 ? num_points / 8 : 1;
-        check(sfmb200_create(k, k_inv, 1, num_points, max_h > 65536 ? max_h : 65536, &h_), "Image_pair");
+        check(sfmb200_create(k, k_inv, image_count - 1, num_points, max_h > 65536 ? max_h : 65536, &h_), "Image_pair");
     }
     ~Image_pair() { sfmb200_destroy(h_); }
     Image_pair(const Image_pair&) = delete;
@@ -131,35 +133,42 @@ public:
     }
     // LO-RANSAC refit of E on its inlier set; returns the accepted refits
     int refineE(int iterations = 4) {
-        int32_t acc = 0;
+        std::vector<int32_t> acc(pairs(), 0);
         check(sfmb200_refine_e(h_, iterations), "refineE");
-        check(sfmb200_get_refit_iterations(h_, &acc), "refineE");
-        return acc;
+        check(sfmb200_get_refit_iterations(h_, acc.data()), "refineE");
+        return acc[0];
     }
     // CudaSift FindHomography semantics (matching.cu:907-1087) on this pair; returns the matches, H row-major 3x3
-    int findHomography(float H[9], int loops = 10000, float thresh = 5.0f, uint64_t seed = 0) {
-        int32_t matches = 0;
-        check(sfmb200_find_homography(h_, loops, seed, thresh, H, &matches), "findHomography");
-        return matches;
+    int findHomography(float* H, int loops = 10000, float thresh = 5.0f, uint64_t seed = 0) {      // H [pairs()][9]
+        std::vector<int32_t> matches(pairs(), 0);
+        check(sfmb200_find_homography(h_, loops, seed, thresh, H, matches.data()), "findHomography");
+        return matches[0];
     }
     // bundle adjustment of the chosen pose and the inlier points, with inlier re-selection; stats: see sfmb200.h
-    void bundleAdjust(int outerRounds = 3, int iterations = 10, float stats[8] = nullptr) {
+    void bundleAdjust(int outerRounds = 4, int iterations = 40, float* stats = nullptr)   /* stats [pairs()][8] */ {
         check(sfmb200_bundle_adjust(h_, outerRounds, iterations, stats), "bundleAdjust");
         check(sfmb200_synchronize(h_), "bundleAdjust");
     }
-    void setCompat(bool reference_semantics) { check(sfmb200_set_option(h_, SFMB200_OPT_COMPAT, reference_semantics), "setCompat"); }
-    void getE(float E[9]) { check(sfmb200_get_E(h_, E), "getE"); }
-    void getPoses(float P[64]) { check(sfmb200_get_poses(h_, P), "getPoses"); }
-    int getPoseIndex() {
-        int32_t i = 0;
-        check(sfmb200_get_pose_index(h_, &i), "getPoseIndex");
-        return i;
+    // image_count > 2: consecutive pairs into one frame; any output pointer may be null (see sfmb200_chain_views)
+    void chainViews(float* d_cloud_4xN, int32_t* d_seen, float* cameras_3x4, float* scales = nullptr, int32_t* links = nullptr) {
+        check(sfmb200_chain_views(h_, d_cloud_4xN, d_seen, cameras_3x4, scales, links), "chainViews");
+        check(sfmb200_synchronize(h_), "chainViews");
     }
-    int getBest(int* inliers = nullptr) {
-        int32_t idx = 0, cnt = 0;
-        check(sfmb200_get_best(h_, &idx, &cnt), "getBest");
-        if (inliers) *inliers = cnt;
-        return idx;
+    int pairs() const { return image_count - 1; }
+    void setCompat(bool reference_semantics) { check(sfmb200_set_option(h_, SFMB200_OPT_COMPAT, reference_semantics), "setCompat"); }
+    // host getters; with image_count > 2 the arrays hold one entry per pair: E [pairs()][9], P [pairs()][64]
+    void getE(float* E) { check(sfmb200_get_E(h_, E), "getE"); }
+    void getPoses(float* P) { check(sfmb200_get_poses(h_, P), "getPoses"); }
+    int getPoseIndex(int pair = 0) {
+        std::vector<int32_t> i(pairs(), 0);
+        check(sfmb200_get_pose_index(h_, i.data()), "getPoseIndex");
+        return i[pair];
+    }
+    int getBest(int* inliers = nullptr, int pair = 0) {
+        std::vector<int32_t> idx(pairs(), 0), cnt(pairs(), 0);
+        check(sfmb200_get_best(h_, idx.data(), cnt.data()), "getBest");
+        if (inliers) *inliers = cnt[pair];
+        return idx[pair];
     }
     void getPoints(float* d_4xN) {
         check(sfmb200_get_points(h_, 0, d_4xN), "getPoints");
