@@ -393,18 +393,24 @@ __global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inl
     if (threadIdx.x < 9) sE[threadIdx.x] = s.E[(size_t)b * 9 + threadIdx.x];
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.n) return;
-    float4 p = __ldg(s.corr + (size_t)b * s.n_stride + i);
+    const bool inside = i < s.n;
+    float4 p = inside ? __ldg(s.corr + (size_t)b * s.n_stride + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float X = 0.0f, Y = 0.0f, Z = 0.0f;
-    bool keep = !inliers_only || sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f;
-    if (keep) {
+    const bool keep = inside && (!inliers_only || sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f);
+    {
+        // every lane makes the call (the adaptive iteration votes across the warp); lanes without a point are not live.
+        // Inverse iteration: cross-product start, up to 5 solves on one Cholesky factor, the warp stops once every live
+        // lane has converged (2 solves for inliers); Jacobi only for the rare point whose two smallest singular values
+        // nearly coincide.
         float A[16], v[4];
         dlt_matrix(p.x, p.y, p.z, p.w, sM, A);
-        // inverse iteration (cross-product start, 5 solves on one Cholesky factor); Jacobi only for the
-        // rare point whose two smallest singular values nearly coincide
-        if (!null4_inverse_iteration<5>(A, v)) null4<5>(A, v);
-        dehomogenise(v, X, Y, Z);
+        const bool ok = null4_inverse_iteration<5, true>(A, v, keep);
+        if (keep) {
+            if (!ok) null4<5>(A, v);
+            dehomogenise(v, X, Y, Z);
+        }
     }
+    if (!inside) return;
     float* out = s.points + (size_t)b * 4 * s.n_stride;
     out[i] = X;
     out[(size_t)s.n_stride + i] = Y;

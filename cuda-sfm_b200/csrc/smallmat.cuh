@@ -310,8 +310,12 @@ SFM_HD void null4(const float* A, float* x) {
 // ~1/7 of the Jacobi solve's instructions.  Returns false when the last step
 // still moved the vector by more than 1e-5 (or anything is non-finite): the
 // caller then falls back to null4().
-template <int ITERS = 4>
-SFM_HD bool null4_inverse_iteration(const float* A, float* x) {
+// ADAPTIVE (device only): a thread freezes its vector at the first step that moved it by less than
+// 1e-5 - the same acceptance test - and the warp leaves the loop once every lane has frozen, so the
+// result of a point does not depend on its neighbours; inliers need 2 of the ITERS solves.
+// With ADAPTIVE every lane of the warp must make the call; lanes without a point pass live = false.
+template <int ITERS = 4, bool ADAPTIVE = false>
+SFM_HD bool null4_inverse_iteration(const float* A, float* x, bool live = true) {
     float g[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -357,6 +361,8 @@ SFM_HD bool null4_inverse_iteration(const float* A, float* x) {
         v0 = ok ? v0 * n : 0.5f; v1 = ok ? v1 * n : 0.5f; v2 = ok ? v2 * n : 0.5f; v3 = ok ? v3 * n : 0.5f;
     }
     float diff2 = 1.0f;
+    bool frozen = !live;
+    (void)frozen;
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
         float y0 = v0 * i0;
@@ -370,6 +376,17 @@ SFM_HD bool null4_inverse_iteration(const float* A, float* x) {
         float n = sfm_rsqrt(fmaf(z3, z3, fmaf(z2, z2, fmaf(z1, z1, z0 * z0))));
         z0 *= n; z1 *= n; z2 *= n; z3 *= n;
         float e0 = z0 - v0, e1 = z1 - v1, e2 = z2 - v2, e3 = z3 - v3;
+#ifdef __CUDA_ARCH__
+        if (ADAPTIVE) {
+            if (!frozen) {
+                diff2 = fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0)));
+                v0 = z0; v1 = z1; v2 = z2; v3 = z3;
+                frozen = diff2 < 1e-10f;
+            }
+            if (__all_sync(0xFFFFFFFFu, frozen)) break;
+            continue;
+        }
+#endif
         diff2 = fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0)));
         v0 = z0; v1 = z1; v2 = z2; v3 = z3;
     }
