@@ -1,0 +1,81 @@
+"""GPU tier: degenerate inputs through the 8f stages (adaptive termination, refit, bundle adjustment,
+chaining): nothing may crash, hang or produce non-finite state; no-op cases must be no-ops."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+THR = 1e-6
+
+
+def test_all_outliers_and_tiny_inputs(pkg, O):
+    import torch
+
+    K, Kinv = O.reference_K()
+    rng = np.random.default_rng(0)
+    # pure noise: uniform pixels in both views, two pairs
+    n = 900
+    px = np.stack([np.c_[rng.uniform(0, 720, n), rng.uniform(0, 576, n), rng.uniform(0, 720, n), rng.uniform(0, 576, n)]
+                   for _ in range(2)]).astype(np.float32)
+    h = pkg.BatchedPairs(K, Kinv, 2, n, 1024)
+    h.set_option(1, 0)
+    h.set_points_xy(torch.from_numpy(px).cuda())
+    used = h.estimate_e_adaptive(1024, 1, THR, 0.99, 128, 2)
+    assert used == 1024                                   # no consensus: never stops early
+    h.refine_e(3)
+    h.pose_candidates(); h.choose_pose(); h.triangulate()
+    E0, P0 = h.get_E().copy(), h.get_poses().copy()
+    st = h.bundle_adjust(2, 5)
+    assert np.all(np.isfinite(st)) and np.all(st[:, 2] <= st[:, 1] + 1e-12)
+    assert np.all(np.isfinite(h.get_E())) and np.all(np.isfinite(h.get_poses()))
+    for b in range(2):
+        assert np.all(np.isfinite(h.get_points_host(b)))
+        if st[b, 0] < 8:                                  # fewer than 8 active points: the pair is left alone
+            assert np.array_equal(h.get_E()[b], E0[b]) and np.array_equal(h.get_poses()[b], P0[b])
+    ch = h.chain_views()
+    assert np.all(np.isfinite(ch["cameras"])) and np.all(np.isfinite(ch["scales"])) and np.all(ch["scales"] > 0)
+    assert np.all(np.isfinite(ch["cloud"].cpu().numpy()))
+    if ch["used"][1] == 0:
+        assert ch["scales"][1] == 1.0                     # no linking track: scale stays 1
+    h.close()
+    # the smallest input the handle accepts: 8 correspondences
+    sc = O.synthetic_pair(8, outlier_frac=0.0, noise_px=0.0, seed=2)
+    h = pkg.BatchedPairs(K, Kinv, 1, 8, 64)
+    h.set_option(1, 0)
+    h.set_points_xy(torch.from_numpy(sc["px"][None]).cuda())
+    assert h.estimate_e_adaptive(64, 1, THR, 0.999, 8, 2) in (8, 16, 32, 64)
+    h.refine_e(2)
+    h.pose_candidates(); h.choose_pose(); h.triangulate()
+    st = h.bundle_adjust(1, 3)
+    assert np.all(np.isfinite(st)) and np.all(np.isfinite(h.get_points_host(0)))
+    ch = h.chain_views()
+    assert np.array_equal(ch["used"], [0]) and np.all(np.isfinite(ch["cameras"]))
+    h.close()
+
+
+def test_bundle_adjust_then_rest_of_the_api_still_consistent(pkg, O):
+    """After BA the handle's E / pose / points / count describe ONE model: re-running the downstream getters and
+    a second adjustment from that state is idempotent up to LM's own progress (cost never increases)."""
+    import torch
+
+    K, Kinv = O.reference_K()
+    n = 2500
+    sc = O.synthetic_pair(n, noise_px=0.5, seed=17)
+    h = pkg.BatchedPairs(K, Kinv, 1, n, 4096)
+    h.set_option(1, 0)
+    h.set_points_xy(torch.from_numpy(sc["px"][None]).cuda())
+    h.estimate_e(4096, 2, THR); h.refine_e(4); h.pose_candidates(); h.choose_pose(); h.triangulate()
+    s1 = h.bundle_adjust(4, 40)[0]
+    c1 = int(h.get_best()[1][0])
+    s2 = h.bundle_adjust(1, 40)[0]
+    c2 = int(h.get_best()[1][0])
+    assert s2[1] <= s1[2] * 1.02 + 1e-12 and s2[2] <= s2[1]       # starts where the first run ended (same active set up to re-selection)
+    assert abs(c2 - c1) <= 0.01 * c1
+    x = O.normalise_points(sc["px"], Kinv)
+    assert c2 == int(O.sampson_mask_f32(h.get_E()[0], x, THR).sum())
+    # the adjusted pose can be handed back through set_E + the pose stages: same pose index, same camera up to rounding
+    M = h.get_poses()[0][int(h.get_pose_index()[0])].copy()
+    h.set_E(h.get_E())
+    h.pose_candidates(); h.choose_pose()
+    M2 = h.get_poses()[0][int(h.get_pose_index()[0])]
+    assert np.linalg.norm(M2[:3, :3] - M[:3, :3]) < 1e-3 and np.linalg.norm(M2[:3, 3] - M[:3, 3]) < 1e-3
+    h.close()

@@ -33,4 +33,19 @@ for n, H, pairs, variant in ((700, 300, 1, -1), (1100, 2500, 2, -1), (520, 1030,
     h.synchronize()
     print(n, H, pairs, variant, "inliers", out["inliers"].tolist(), out2["inliers"].tolist(), h.score_plan())
     h.close()
+# the 8f stages: filtered ingest is covered by its test; here refit, adaptive termination, homography,
+# bundle adjustment and N-view chaining at sizes with partial CTAs
+seq = O.synthetic_sequence(3, 1300, seed=8)
+h = pkg.BatchedPairs(K, Kinv, 2, 1300, 2048)
+h.set_option(1, 0)
+h.set_points_xy(torch.from_numpy(seq["px_pairs"]).cuda())
+used = h.estimate_e_adaptive(2048, 5, 1e-6, 0.99, 256, 2)
+acc = h.refine_e(3)
+h.pose_candidates(); h.choose_pose(); h.triangulate()
+st = h.bundle_adjust(2, 4)
+ch = h.chain_views()
+Hm, cnt = h.find_homography(1500, 3, 5.0)
+h.synchronize()
+print("8f stages: used", used, "refits", acc.tolist(), "ba inliers", st[:, 6].tolist(), "scales", ch["scales"].tolist(), "h matches", cnt.tolist())
+h.close()
 print("sanitize run done")
