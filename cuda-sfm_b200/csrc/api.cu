@@ -11,6 +11,7 @@
 
 #include "../../include/sfmb200.h"
 #include "internal.cuh"
+#include "sampson.cuh"
 
 using namespace sfmb200;
 
@@ -113,6 +114,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t B = pairs, off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_corr = carve(B * s.n_stride * sizeof(float4));
+    size_t o_cs = carve(B * s.n_stride * sizeof(float4));
     size_t o_dup = carve(B * s.n_stride * 2 * sizeof(float4));
     size_t o_px = carve(B * s.n_stride * 4 * sizeof(float));
     size_t o_ec = carve(B * 9 * (size_t)s.h_stride * sizeof(float));
@@ -154,7 +156,9 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     }
     char* base = (char*)h->arena;
     s.corr = (float4*)(base + o_corr);
+    s.corr_s = (float4*)(base + o_cs);
     s.corr_dup = (float4*)(base + o_dup);
+    s.pt_scale = make_thr_scale(1e-6f).ik;     // the reference's threshold literal (sfm.cu:220) until told otherwise
     s.px = (float*)(base + o_px);
     s.Ecand = (float*)(base + o_ec);
     s.counts = (int*)(base + o_cnt);
@@ -334,6 +338,18 @@ int sfmb200_set_points_normalised(sfmb200_t* h, const float* d_x, int n) {
     return SFMB200_OK;
 }
 
+// The scoring kernels read coordinates scaled by 1/sqrt(thr) (sampson.cuh).  The ingest kernels write them
+// with the scale the handle currently holds; when an estimate asks for another one (a different threshold,
+// or 1 for the homography model) the copies are re-materialised first.
+static int ensure_scaled(sfmb200_handle* h, float scale) {
+    if (h->s.pt_scale == scale) return SFMB200_OK;
+    h->s.pt_scale = scale;
+    launch_rescale_points(h->s, h->stream);
+    CKL();
+    h->launches++;
+    return SFMB200_OK;
+}
+
 int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, int h_begin, int H, uint64_t seed,
                              float thr) {
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
@@ -344,6 +360,7 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     h->H = H;
     h->h_begin = h_begin;
     h->thr = thr;
+    if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;
     h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
     launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->hyp_solver, h->stream);
     prof_mark(h, 2);
@@ -368,6 +385,7 @@ int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh
     if (loops < 1 || loops > h->s.h_max) return fail(SFMB200_ERR_ARG, "loops out of range / above max_hypotheses%s");
     if (!(thresh > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
     const float thr2 = thresh * thresh;
+    if (int rc = ensure_scaled(h, 1.0f)) return rc;      // the transfer-error test works on the unscaled coordinates
     h->H = loops;
     h->h_begin = 0;
     h->thr = thr2;
@@ -425,6 +443,7 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
         }
     }
     const double log1mp = log1p(-(double)confidence);
+    if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;
     CK(cudaMemsetAsync(h->adapt, 0, 4 * sizeof(int), h->stream));
     DeviceState s = h->s;
     s.skip = h->adapt;
@@ -591,6 +610,7 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
     h->H = H;
     h->h_begin = 0;
     h->thr = thr;
+    if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;     // no-op after run_device / run_host's own ingest
     h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
     launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->hyp_solver, h->stream);
     prof_mark(h, 2);
@@ -615,6 +635,7 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
 
 int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t seed, float thr) {
     if (h) prof_next(h);
+    if (h && thr > 0.0f) h->s.pt_scale = make_thr_scale(thr).ik;      // the ingest below writes the scaled copies for this threshold
     int rc = sfmb200_set_points_xy(h, d_px, n);
     if (rc) return rc;
     return run_stages(h, H, seed, thr);
@@ -647,6 +668,7 @@ __global__ void pack_results_kernel(DeviceState s, float* header, float* points,
 int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t seed, float thr, float* h_E, float* h_P,
                      int32_t* h_pose_index, int32_t* h_inliers, float* h_points) {
     if (h) prof_next(h);
+    if (h && thr > 0.0f) h->s.pt_scale = make_thr_scale(thr).ik;
     int rc = sfmb200_set_points_xy_host(h, h_px, n);
     if (rc) return rc;
     if ((rc = run_stages(h, H, seed, thr))) return rc;

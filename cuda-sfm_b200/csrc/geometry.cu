@@ -14,6 +14,14 @@ struct Mat9 { float v[9]; };
 // reference).  Writes the float4 correspondence array every later stage reads
 // and the duplicated layout the packed scoring path stages through TMA.
 // ---------------------------------------------------------------------------
+// Threshold-scaled copies for the scoring kernels (sampson.cuh): coordinates * pt_scale, plain and duplicated.
+__device__ __forceinline__ void store_scaled(const DeviceState& s, size_t o, float x1, float y1, float x2, float y2) {
+    const float k = s.pt_scale;
+    x1 *= k; y1 *= k; x2 *= k; y2 *= k;
+    s.corr_s[o] = make_float4(x1, y1, x2, y2);
+    s.corr_dup[2 * o] = make_float4(x1, x1, y1, y1);
+    s.corr_dup[2 * o + 1] = make_float4(x2, x2, y2, y2);
+}
 __device__ __forceinline__ void normalise_store(const DeviceState& s, int b, int i, float u1, float v1, float u2, float v2,
                                                 const Mat9& k) {
     float x1 = fmaf(k.v[1], v1, fmaf(k.v[0], u1, k.v[2]));
@@ -28,8 +36,7 @@ __device__ __forceinline__ void normalise_store(const DeviceState& s, int b, int
     if (z2 != 1.0f) { x2 /= z2; y2 /= z2; }
     size_t o = (size_t)b * s.n_stride + i;
     s.corr[o] = make_float4(x1, y1, x2, y2);
-    s.corr_dup[2 * o] = make_float4(x1, x1, y1, y1);
-    s.corr_dup[2 * o + 1] = make_float4(x2, x2, y2, y2);
+    store_scaled(s, o, x1, y1, x2, y2);
 }
 
 // SiftPoint is 576 bytes (CudaSift/cudaSift.h:6-22); only xpos@0, ypos@4,
@@ -125,6 +132,18 @@ sift_filter_scatter_kernel(DeviceState s, const float* __restrict__ sift, int n,
     normalise_store(s, 0, dst, a.x, a.y, __ldg(p + 9), __ldg(p + 10), k);
     if (kept_index) kept_index[dst] = i;
 }
+// Re-materialise the scaled copies after the threshold (or the model) changed without a new ingest.
+__global__ void rescale_points_kernel(DeviceState s) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    size_t o = (size_t)blockIdx.y * s.n_stride + i;
+    float4 p = s.corr[o];
+    store_scaled(s, o, p.x, p.y, p.z, p.w);
+}
+void launch_rescale_points(const DeviceState& s, cudaStream_t st) {
+    rescale_points_kernel<<<dim3((s.n + 255) / 256, s.B), 256, 0, st>>>(s);
+}
+
 void launch_ingest_sift_filtered(const DeviceState& s, const void* d_sift, int n, float min_score, float max_ambiguity,
                                  int* d_scratch, int* d_kept_index, cudaStream_t st) {
     Mat9 k;

@@ -1,15 +1,35 @@
 // The inlier test shared by every kernel that classifies a correspondence:
-//   d = num^2 - thr * den,  num = x1^T E x2,  den = (E x2)_0^2 + (E x2)_1^2 + (E^T x1)_0^2 + (E^T x1)_1^2
-// (Sampson error < thr  <=>  d < 0; z = 1 in both views; reference convention
-// x1^T E x2 = 0; threshold literal 1e-6 from SfM/sfm.cu:220).
-// ONE fma tree, so scoring, cheirality vote, inlier mask, triangulation mask and
+//   Sampson error  num^2 / den < thr,  num = x1^T E x2,  den = (E x2)_0^2 + (E x2)_1^2 + (E^T x1)_0^2 + (E^T x1)_1^2
+// (z = 1 in both views; reference convention x1^T E x2 = 0; threshold literal 1e-6 from
+// SfM/sfm.cu:220).  ONE fma tree, so scoring, cheirality vote, inlier mask, triangulation mask and
 // refit agree bit for bit; oracle/oracle_c.c:sampson_d_f32 mirrors it on the CPU.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace sfmb200 {
 
-__device__ __forceinline__ float sampson_d(const float* e, float x1, float y1, float x2, float y2, float nthr) {
+// The threshold is folded into the coordinates: with k = sqrt(thr), points scaled by 1/k and
+// E~ = D E D, D = diag(k, k, 1), the Sampson error in the scaled coordinates is error / thr, so
+//   inlier  <=>  num~^2 - den~ < 0,   num~ = x1~^T E~ x2~,  den~ = (E~ x2~)_0^2 + (E~ x2~)_1^2 + (E~^T x1~)_0^2 + (E~^T x1~)_1^2:
+// 17 FP32-pipe instructions per evaluation instead of 18 (no thr * den product).  The scoring kernels read
+// pre-scaled correspondences (DeviceState::corr_s / corr_dup) and scale each hypothesis once when it is
+// loaded; every other classifier calls sampson_d, which applies the same scaling per call - same operations in
+// the same order, so all of them agree bit for bit.
+struct ThrScale { float k, ik, k2; };
+__host__ __device__ __forceinline__ ThrScale make_thr_scale(float thr) {
+    ThrScale t;
+    t.k = sqrtf(thr);          // correctly rounded on host and device (no fast-math)
+    t.ik = 1.0f / t.k;
+    t.k2 = t.k * t.k;
+    return t;
+}
+// factor of entry q of E~ = D E D: k^2 for the upper-left 2x2, k for the rest of row / column 2, 1 for e8
+__host__ __device__ __forceinline__ float thr_scale_factor(const ThrScale& t, int q) {
+    return (q == 8) ? 1.0f : ((q == 2 || q == 5 || q == 6 || q == 7) ? t.k : t.k2);
+}
+
+// scaled E, scaled coordinates -> d (negative = inlier)
+__device__ __forceinline__ float sampson_unit_d(const float* e, float x1, float y1, float x2, float y2) {
     float l0 = fmaf(e[0], x2, fmaf(e[1], y2, e[2]));
     float l1 = fmaf(e[3], x2, fmaf(e[4], y2, e[5]));
     float l2 = fmaf(e[6], x2, fmaf(e[7], y2, e[8]));
@@ -17,12 +37,10 @@ __device__ __forceinline__ float sampson_d(const float* e, float x1, float y1, f
     float m0 = fmaf(e[0], x1, fmaf(e[3], y1, e[6]));
     float m1 = fmaf(e[1], x1, fmaf(e[4], y1, e[7]));
     float den = fmaf(l0, l0, fmaf(l1, l1, fmaf(m0, m0, m1 * m1)));
-    return fmaf(den, nthr, num * num);
+    return fmaf(num, num, -den);
 }
-
-// Two hypotheses at once with packed FFMA2 / FMUL2 (fma.rn.f32x2, sm_100+):
-// lane-wise identical to sampson_d.
-__device__ __forceinline__ float2 sampson_d2(const float2* e, float2 x1, float2 y1, float2 x2, float2 y2, float2 nthr) {
+// Two hypotheses at once with packed FFMA2 / FMUL2 (fma.rn.f32x2, sm_100+): lane-wise identical to sampson_unit_d.
+__device__ __forceinline__ float2 sampson_unit_d2(const float2* e, float2 x1, float2 y1, float2 x2, float2 y2) {
     float2 l0 = __ffma2_rn(e[0], x2, __ffma2_rn(e[1], y2, e[2]));
     float2 l1 = __ffma2_rn(e[3], x2, __ffma2_rn(e[4], y2, e[5]));
     float2 l2 = __ffma2_rn(e[6], x2, __ffma2_rn(e[7], y2, e[8]));
@@ -30,7 +48,15 @@ __device__ __forceinline__ float2 sampson_d2(const float2* e, float2 x1, float2 
     float2 m0 = __ffma2_rn(e[0], x1, __ffma2_rn(e[3], y1, e[6]));
     float2 m1 = __ffma2_rn(e[1], x1, __ffma2_rn(e[4], y1, e[7]));
     float2 den = __ffma2_rn(l0, l0, __ffma2_rn(l1, l1, __ffma2_rn(m0, m0, __fmul2_rn(m1, m1))));
-    return __ffma2_rn(den, nthr, __fmul2_rn(num, num));
+    return __ffma2_rn(num, num, make_float2(-den.x, -den.y));
+}
+// unscaled E, unscaled coordinates, nthr = -thr: the form every classifier outside the scoring kernels uses
+__device__ __forceinline__ float sampson_d(const float* e, float x1, float y1, float x2, float y2, float nthr) {
+    const ThrScale t = make_thr_scale(-nthr);
+    float es[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) es[q] = (q == 8) ? e[q] : e[q] * thr_scale_factor(t, q);
+    return sampson_unit_d(es, x1 * t.ik, y1 * t.ik, x2 * t.ik, y2 * t.ik);
 }
 
 // Homography model (CudaSift's TestHomographies, matching.cu:953-996):
@@ -60,11 +86,12 @@ __device__ __forceinline__ float2 homography_d2(const float2* e, float2 x1, floa
 // MODEL 0: essential matrix / Sampson; MODEL 1: homography / transfer error.
 template <int MODEL>
 __device__ __forceinline__ float model_d(const float* e, float x1, float y1, float x2, float y2, float nthr) {
-    return MODEL == 0 ? sampson_d(e, x1, y1, x2, y2, nthr) : homography_d(e, x1, y1, x2, y2, nthr);
+    // scoring kernels: MODEL 0 gets pre-scaled E and coordinates (see above); MODEL 1 is unscaled (pt_scale = 1)
+    return MODEL == 0 ? sampson_unit_d(e, x1, y1, x2, y2) : homography_d(e, x1, y1, x2, y2, nthr);
 }
 template <int MODEL>
 __device__ __forceinline__ float2 model_d2(const float2* e, float2 x1, float2 y1, float2 x2, float2 y2, float2 nthr) {
-    return MODEL == 0 ? sampson_d2(e, x1, y1, x2, y2, nthr) : homography_d2(e, x1, y1, x2, y2, nthr);
+    return MODEL == 0 ? sampson_unit_d2(e, x1, y1, x2, y2) : homography_d2(e, x1, y1, x2, y2, nthr);
 }
 
 }  // namespace sfmb200

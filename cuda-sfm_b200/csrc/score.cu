@@ -240,7 +240,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
         desc[stage] = d;
         if (more) {
             const float4* src = PACKED ? s.corr_dup + ((size_t)w.b * s.n_stride + w.p0) * 2
-                                       : s.corr + (size_t)w.b * s.n_stride + w.p0;
+                                       : s.corr_s + (size_t)w.b * s.n_stride + w.p0;
             uint32_t bytes = (uint32_t)w.cnt * 16u * F4_PER_PT;
             mbar_expect_tx(&full[stage], bytes);
             tma_load_1d(&buf[stage][0], src, bytes, &full[stage]);
@@ -255,7 +255,8 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
     unsigned int cnt[HPT];
     const float nthr = -thr;
     const float2 nthr2 = make_float2(nthr, nthr);
-    (void)e; (void)e2; (void)nthr2;
+    const ThrScale ts = make_thr_scale(thr);
+    (void)e; (void)e2; (void)nthr2; (void)ts;
 
     for (int k = 0;; k++) {
         if (tid == 0) produce((k + 1) & 1);     // safe: stage (k+1)&1 was released by the barrier ending iteration k-1
@@ -273,6 +274,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
 #pragma unroll
                 for (int q = 0; q < 9; q++) {
                     float v = valid ? __ldg(Eb + (size_t)q * s.h_stride + h) : 0.0f;
+                    if (MODEL == 0 && q != 8) v *= thr_scale_factor(ts, q);      // E~ = D E D (sampson.cuh)
                     if constexpr (PACKED) {
                         if (j & 1) e2[j / 2][q].y = v; else e2[j / 2][q].x = v;
                     } else {
@@ -356,6 +358,8 @@ score_const_kernel(DeviceState s, int b, int chunk, int last_np, int arrivals, i
     const float4* base = c_pts + blockIdx.y * chunk;
     const int np = (blockIdx.y == gridDim.y - 1) ? last_np : chunk;
     const float nthr = -thr;
+    const ThrScale ts = make_thr_scale(thr);
+    (void)ts;
     const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
     float e[HPT][9];
     unsigned int cnt[HPT];
@@ -364,7 +368,11 @@ score_const_kernel(DeviceState s, int b, int chunk, int last_np, int arrivals, i
         int h = t * HPC + j * THREADS + tid;
         bool valid = h < H;
 #pragma unroll
-        for (int k = 0; k < 9; k++) e[j][k] = valid ? __ldg(Eb + (size_t)k * s.h_stride + h) : 0.0f;
+        for (int k = 0; k < 9; k++) {
+            float v = valid ? __ldg(Eb + (size_t)k * s.h_stride + h) : 0.0f;
+            if (MODEL == 0 && k != 8) v *= thr_scale_factor(ts, k);      // E~ = D E D (sampson.cuh)
+            e[j][k] = v;
+        }
         cnt[j] = 0u;
     }
 #pragma unroll 4
@@ -436,7 +444,7 @@ static void launch_score_const(const DeviceState& s, const ScorePlan& plan, int 
             const int real_splits = (cnt + chunk - 1) / chunk;
             const int last_np = cnt - (real_splits - 1) * chunk;
             cudaStreamWaitEvent(st, g_const.last_use[dev], 0);
-            cudaMemcpyToSymbolAsync(c_pts, s.corr + (size_t)b * s.n_stride + off, (size_t)cnt * sizeof(float4), 0,
+            cudaMemcpyToSymbolAsync(c_pts, s.corr_s + (size_t)b * s.n_stride + off, (size_t)cnt * sizeof(float4), 0,
                                     cudaMemcpyDeviceToDevice, st);
             score_const_kernel<CONST_HPT, CONST_THREADS, CONST_MINB, MODEL>
                 <<<dim3(plan.tiles, real_splits), CONST_THREADS, 0, st>>>(s, b, chunk, last_np, arrivals, H, h_offset, thr);

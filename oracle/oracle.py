@@ -188,14 +188,20 @@ def inlier_counts(E: np.ndarray, x: np.ndarray, thr: float = 1e-6, band: float =
 
 
 def sampson_mask_f32(E: np.ndarray, x: np.ndarray, thr: float = 1e-6) -> np.ndarray:
-    """Inlier mask with the SAME fp32 fma tree as the CUDA kernels (score.cu: sampson_d),
+    """Inlier mask with the SAME fp32 fma tree as the CUDA kernels (sampson.cuh: sampson_d),
     emulated with exactly-rounded fp64 products: every fp32 fma(a,b,c) is computed as
     float32(float64(a)*float64(b) + float64(c)), which is correctly rounded because the
     fp64 product of two fp32 numbers is exact.  (The sum can still double-round in rare
     half-way cases; tests allow for a handful of such points.)"""
     f32, f64 = np.float32, np.float64
+    # threshold folded into the coordinates (sampson.cuh): k = sqrt(thr), points * 1/k, E~ = D E D, D = diag(k,k,1)
+    k = np.sqrt(f32(thr)).astype(f32)
+    ik = (f32(1.0) / k).astype(f32)
+    k2 = (k * k).astype(f32)
+    fac = np.array([k2, k2, k, k2, k2, k, k, k, f32(1.0)], f32)
     e = E.reshape(9).astype(f32)
-    x1, y1, x2, y2 = (x[:, i].astype(f32) for i in range(4))
+    e = np.where(np.arange(9) == 8, e, (e * fac).astype(f32)).astype(f32)
+    x1, y1, x2, y2 = ((x[:, i].astype(f32) * ik).astype(f32) for i in range(4))
 
     def fma(a, b, c):
         return (a.astype(f64) * np.asarray(b, f64) + np.asarray(c, f64)).astype(f32)
@@ -207,7 +213,7 @@ def sampson_mask_f32(E: np.ndarray, x: np.ndarray, thr: float = 1e-6) -> np.ndar
     m0 = fma(x1, e[0], fma(y1, e[3], np.full_like(x1, e[6])))
     m1 = fma(x1, e[1], fma(y1, e[4], np.full_like(x1, e[7])))
     den = fma(l0, l0, fma(l1, l1, fma(m0, m0, (m1 * m1).astype(f32))))
-    d = fma(den, f32(-thr), (num * num).astype(f32))
+    d = fma(num, num, -den)
     return d < 0
 
 

@@ -121,15 +121,24 @@ void oracle_hypotheses_f64(const float* x, int n, const int32_t* idx, int H, dou
 }
 
 /* ---------- scoring ---------- */
+/* Mirrors cuda-sfm_b200/csrc/sampson.cuh: the threshold is folded into the coordinates (k = sqrt(thr),
+ * points * 1/k, E~ = D E D with D = diag(k,k,1)), then d = num~^2 - den~ with one fma tree. */
 static inline float sampson_d_f32(const float* e, float x1, float y1, float x2, float y2, float nthr) {
-    float l0 = fmaf(e[0], x2, fmaf(e[1], y2, e[2]));
-    float l1 = fmaf(e[3], x2, fmaf(e[4], y2, e[5]));
-    float l2 = fmaf(e[6], x2, fmaf(e[7], y2, e[8]));
+    const float k = sqrtf(-nthr), ik = 1.0f / k, k2 = k * k;
+    float s[9];
+    for (int q = 0; q < 9; q++) {
+        float f = (q == 2 || q == 5 || q == 6 || q == 7) ? k : k2;
+        s[q] = (q == 8) ? e[q] : e[q] * f;
+    }
+    x1 *= ik; y1 *= ik; x2 *= ik; y2 *= ik;
+    float l0 = fmaf(s[0], x2, fmaf(s[1], y2, s[2]));
+    float l1 = fmaf(s[3], x2, fmaf(s[4], y2, s[5]));
+    float l2 = fmaf(s[6], x2, fmaf(s[7], y2, s[8]));
     float num = fmaf(x1, l0, fmaf(y1, l1, l2));
-    float m0 = fmaf(e[0], x1, fmaf(e[3], y1, e[6]));
-    float m1 = fmaf(e[1], x1, fmaf(e[4], y1, e[7]));
+    float m0 = fmaf(s[0], x1, fmaf(s[3], y1, s[6]));
+    float m1 = fmaf(s[1], x1, fmaf(s[4], y1, s[7]));
     float den = fmaf(l0, l0, fmaf(l1, l1, fmaf(m0, m0, m1 * m1)));
-    return fmaf(den, nthr, num * num);
+    return fmaf(num, num, -den);
 }
 
 /* E: H x 9 fp32 (exactly what the GPU scored); counts[h] = #{i : d < 0} */
