@@ -39,7 +39,7 @@ N_CORR, N_HYP, THR, SEED = 10_000, 65_536, 1e-6, 1237
 FLOP_PER_EVAL = 34.0              # 15 FFMA x2 + 3 FMUL + 1 compare
 # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch at this config,
 # from the ncu --set full capture summarised in profiles/r01_ncu_summary.md
-SCORE_TRAFFIC_BYTES_NCU = 2_969_856
+SCORE_TRAFFIC_BYTES_NCU = 2_972_416
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4
 
 
