@@ -332,8 +332,9 @@ def run_reference(args):
     K, Kinv = O.reference_K()
     scene = O.synthetic_pair(N_CORR, 0.3, 1.0, seed=1234)
     px = scene["px"]
-    base = {"impl": "reference", "metric": "RANSAC hyp*corr evals/s", "unit": "hyp*corr evals/s", "n_gpus": 1,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    # n_gpus = the N of this launch; the reference is single-GPU, so rank 0 alone runs it (gpus_used = 1)
+    base = {"impl": "reference", "metric": "RANSAC hyp*corr evals/s", "unit": "hyp*corr evals/s", "n_gpus": max(args.gpus, 1),
+            "gpus_used": 1, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
     path = os.path.join(ROOT, "oracle", "_ref", "libsfm_ref.so")
     if not (os.path.exists(path) and torch.cuda.is_available()):
         # no rebuilt reference (or no GPU for its CUDA-only path): time the oracle port instead
