@@ -97,6 +97,10 @@ public:
     void copyBoidsToVBO(float* vbodptr_positions, float* vbodptr_velocities) {
         check(sfmb200_copy_to_vbo(h_, 0, vbodptr_positions, vbodptr_velocities), "copyBoidsToVBO");
     }
+    // same with a position scale and colours: mode 1 inlier / outlier, mode 2 depth ramp (see sfmb200.h)
+    void copyBoidsToVBO(float* vbodptr_positions, float* vbodptr_colours, float scale, int mode, float z_near = 0.0f, float z_far = 1.0f) {
+        check(sfmb200_copy_to_vbo_coloured(h_, 0, vbodptr_positions, vbodptr_colours, scale, mode, z_near, z_far), "copyBoidsToVBO");
+    }
     // The reference's print-only self tests (sfm.cu:389-510), now asserting: each
     // runs its literal through the kernels.h-equivalent entry point and returns
     // whether the result matches the value the reference's comments expect.

@@ -701,6 +701,17 @@ int sfmb200_copy_to_vbo(sfmb200_t* h, int pair, float* d_pos, float* d_col) {
     return SFMB200_OK;
 }
 
+int sfmb200_copy_to_vbo_coloured(sfmb200_t* h, int pair, float* d_pos, float* d_col, float scale, int mode, float z_near, float z_far) {
+    if (!h || pair < 0 || pair >= h->s.B) return fail(SFMB200_ERR_ARG, "bad handle / pair%s");
+    if (mode < 0 || mode > 2) return fail(SFMB200_ERR_ARG, "colour mode must be 0 (ones), 1 (inlier / outlier) or 2 (depth ramp)%s");
+    if (mode == 1 && (!h->have_E || h->model != 0)) return fail(SFMB200_ERR_STATE, "inlier colouring needs an essential matrix%s");
+    launch_vbo_colour(h->s, pair, d_pos, d_col, scale, mode, h->thr > 0 ? h->thr : 1e-6f, z_near, z_far, h->stream);
+    CKL();
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return SFMB200_OK;
+}
+
 int sfmb200_get_E(sfmb200_t* h, float* h_E) {
     if (!h || !h_E) return fail(SFMB200_ERR_ARG, "null argument%s");
     CK(cudaMemcpyAsync(h_E, h->s.E, (size_t)h->s.B * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -452,6 +452,39 @@ __global__ void vbo_kernel(DeviceState s, int pair, float4* pos, float4* col, fl
     if (pos) pos[i] = make_float4(in[i] * scale, in[(size_t)s.n_stride + i] * scale, in[(size_t)2 * s.n_stride + i] * scale, 1.0f);
     if (col) col[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
 }
+// Egress with per-point colour ("AoS VBO writer with colour"; the reference writes all
+// ones, kernels.h:485-495).  mode 1: inliers of the selected E green, others red.  mode 2: depth ramp
+// blue (z <= z_near) -> red (z >= z_far) for points in front of the camera, grey for the rest.
+__global__ void vbo_colour_kernel(DeviceState s, int pair, float4* pos, float4* col, float scale, int mode, float thr,
+                                  float z_near, float z_far) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    const float* in = s.points + (size_t)pair * 4 * s.n_stride;
+    const float X = in[i], Y = in[(size_t)s.n_stride + i], Z = in[(size_t)2 * s.n_stride + i];
+    if (pos) pos[i] = make_float4(X * scale, Y * scale, Z * scale, 1.0f);
+    if (!col) return;
+    float4 c = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (mode == 1) {
+        float e[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) e[k] = s.E[(size_t)pair * 9 + k];
+        const float4 p = s.corr[(size_t)pair * s.n_stride + i];
+        const bool inl = sampson_d(e, p.x, p.y, p.z, p.w, -thr) < 0.0f;
+        c = inl ? make_float4(0.0f, 1.0f, 0.0f, 1.0f) : make_float4(1.0f, 0.0f, 0.0f, 1.0f);
+    } else if (mode == 2) {
+        if (Z > 0.0f && z_far > z_near) {
+            const float t = fminf(fmaxf((Z - z_near) / (z_far - z_near), 0.0f), 1.0f);
+            c = make_float4(t, 0.0f, 1.0f - t, 1.0f);
+        } else {
+            c = make_float4(0.5f, 0.5f, 0.5f, 1.0f);
+        }
+    }
+    col[i] = c;
+}
+void launch_vbo_colour(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, int mode, float thr, float z_near,
+                       float z_far, cudaStream_t st) {
+    vbo_colour_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, (float4*)d_pos, (float4*)d_col, scale, mode, thr, z_near, z_far);
+}
 void launch_vbo(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, cudaStream_t st) {
     vbo_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(s, pair, (float4*)d_pos, (float4*)d_col, scale);
 }

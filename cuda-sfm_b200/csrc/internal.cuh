@@ -114,6 +114,8 @@ void launch_select_pose_choose(const DeviceState& s, int h_offset, int compat, c
 void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_t st);
 void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st);
 void launch_vbo(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, cudaStream_t st);
+void launch_vbo_colour(const DeviceState& s, int pair, float* d_pos, float* d_col, float scale, int mode, float thr, float z_near,
+                       float z_far, cudaStream_t st);
 void launch_export_ecand(const DeviceState& s, int pair, int H, float* d_out_Hx9, cudaStream_t st);
 void launch_export_X(const DeviceState& s, int pair, int image, float* d_out_3xN, cudaStream_t st);
 void launch_inlier_mask(const DeviceState& s, int pair, float thr, int model, unsigned char* d_mask, cudaStream_t st);

@@ -270,6 +270,11 @@ class BatchedPairs:
     def copy_to_vbo(self, d_pos, d_col, pair: int = 0):
         self.lib.call("sfmb200_copy_to_vbo", self._h, pair, _dptr(d_pos), _dptr(d_col))
 
+    def copy_to_vbo_coloured(self, d_pos, d_col, pair: int = 0, scale: float = 1.0, mode: int = 1, z_near: float = 0.0, z_far: float = 1.0):
+        """mode 0 ones, 1 inlier green / outlier red, 2 depth ramp blue -> red between z_near and z_far."""
+        self.lib.call("sfmb200_copy_to_vbo_coloured", self._h, pair, _dptr(d_pos), _dptr(d_col), C.c_float(scale), mode,
+                      C.c_float(z_near), C.c_float(z_far))
+
     def score_plan(self) -> dict:
         out = (C.c_int32 * 4)()
         self.lib.call("sfmb200_score_plan", self._h, out)

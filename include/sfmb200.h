@@ -179,6 +179,12 @@ int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t s
 /* ---- egress: copyBoidsToVBO (sfm.cu:374-383) ---- */
 /* pos / col: device [n][4]; either may be NULL.  Synchronises like the reference. */
 int sfmb200_copy_to_vbo(sfmb200_t* h, int pair, float* d_pos, float* d_col);
+/* Same with a position scale (kernCopyPositionsToVBO's s_scale, kernels.h:471) and per-point colours
+ * (the reference writes ones, kernels.h:485-495).  mode 0: ones; 1: inliers of the
+ * selected E (0,1,0,1), others (1,0,0,1); 2: depth ramp (t,0,1-t,1), t = clamp((z - z_near) / (z_far - z_near)),
+ * for points with z > 0, grey (0.5,0.5,0.5,1) otherwise. */
+int sfmb200_copy_to_vbo_coloured(sfmb200_t* h, int pair, float* d_pos, float* d_col, float scale, int mode, float z_near,
+                                 float z_far);
 
 /* ---- getters (the reference keeps these members private, sfm.h:21-41) ---- */
 int sfmb200_get_E(sfmb200_t* h, float* h_E /* [pairs][9] */);

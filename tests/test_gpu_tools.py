@@ -17,3 +17,36 @@ def test_configs_tool_small_scale():
     lines = [json.loads(l) for l in r.stdout.strip().splitlines() if l.startswith("{")]
     assert [l["config"] for l in lines] == ["c3", "c4", "c5"]
     assert lines[0]["inliers"] > 0 and lines[1]["pairs"] == 16 and lines[2]["tri_points_per_s"] > 0
+
+
+def test_coloured_vbo(pkg, O):
+    """Egress with colours: positions as copyBoidsToVBO (scaled), colours by inlier status or depth."""
+    import numpy as np
+    import torch
+
+    K, Kinv = O.reference_K()
+    n = 1500
+    sc = O.synthetic_pair(n, seed=21)
+    h = pkg.BatchedPairs(K, Kinv, 1, n, 2048)
+    h.set_option(1, 0)
+    h.run_device(torch.from_numpy(sc["px"][None]).cuda(), 2048, 4, 1e-6)
+    pos, col = torch.empty((n, 4), device="cuda"), torch.empty((n, 4), device="cuda")
+    X = h.get_points_host(0)
+    mask = h.get_inlier_mask().cpu().numpy().astype(bool)
+    h.copy_to_vbo_coloured(pos, col, scale=2.0, mode=1)
+    assert np.array_equal(pos.cpu().numpy(), np.c_[2.0 * X[:3].T, np.ones(n, np.float32)])
+    c = col.cpu().numpy()
+    assert np.all(c[mask] == [0, 1, 0, 1]) and np.all(c[~mask] == [1, 0, 0, 1])
+    h.copy_to_vbo_coloured(pos, col, mode=2, z_near=4.0, z_far=8.0)
+    c = col.cpu().numpy()
+    front = X[2] > 0
+    t = np.clip((X[2] - 4.0) / 4.0, 0, 1).astype(np.float32)
+    assert np.allclose(c[front], np.c_[t, np.zeros(n), 1 - t, np.ones(n)][front], atol=1e-6)
+    assert np.all(c[~front] == [0.5, 0.5, 0.5, 1])
+    h.copy_to_vbo_coloured(pos, col, mode=0)
+    ref_pos, ref_col = torch.empty((n, 4), device="cuda"), torch.empty((n, 4), device="cuda")
+    h.copy_to_vbo(ref_pos, ref_col)
+    assert torch.equal(pos, ref_pos) and torch.equal(col, ref_col)
+    with pytest.raises(Exception):
+        h.copy_to_vbo_coloured(pos, col, mode=3)
+    h.close()
