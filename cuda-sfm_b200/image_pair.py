@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from .binding import Lib, load_library
+from .binding import Lib, SfmError, load_library
 
 OPT_COMPAT, OPT_SCORE_VARIANT, OPT_TRI_INLIERS_ONLY = 1, 2, 3
 
@@ -200,6 +200,28 @@ class BatchedPairs:
                       _hptr(pts) if pts is not None else C.c_void_p(0))
         self.n, self.H = n, H
         return out
+
+    def prepare_run_host(self, h_px: np.ndarray, H: int, seed: int = 0, thr: float = 1e-6, out: dict | None = None):
+        """run_host with the argument marshalling done once: returns (call, out); call() runs the whole path on the
+        buffers captured here (a caller that processes a stream of pairs through the same buffers pays the ctypes
+        conversions once, not ~10 us per call)."""
+        n = h_px.shape[-2]
+        B = self.pairs
+        if out is None:
+            out = {"E": np.empty((B, 9), np.float32), "P": np.empty((B, 16), np.float32), "pose_index": np.empty(B, np.int32),
+                   "inliers": np.empty(B, np.int32), "points": np.empty((B, 4, n), np.float32)}
+        pts = out.get("points")
+        args = (self._h, _hptr(h_px), n, H, C.c_uint64(seed), C.c_float(thr), _hptr(out["E"]), _hptr(out["P"]),
+                _hptr(out["pose_index"]), _hptr(out["inliers"]), _hptr(pts) if pts is not None else C.c_void_p(0))
+        fn = self.lib.raw("sfmb200_run_host")
+        lib = self.lib
+        self.n, self.H = n, H
+
+        def call():
+            rc = fn(*args)
+            if rc != 0:
+                raise SfmError(rc, lib.last_error())
+        return call, out
 
     # ---- getters ----
     def get_E(self) -> np.ndarray:
