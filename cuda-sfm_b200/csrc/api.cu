@@ -141,6 +141,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_bi2 = carve(B * 8 * sizeof(int));
     size_t o_bf = carve(B * 8 * sizeof(float));
     size_t o_bpart = carve(B * ba_blocks * 34 * sizeof(double));
+    size_t o_bpart2 = carve(B * ba_blocks * 2 * sizeof(double));
     size_t o_bs = carve(B * 8 * sizeof(float));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
@@ -182,6 +183,8 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->ba.ctl_i = (int*)(base + o_bi2);
     h->ba.ctl_f = (float*)(base + o_bf);
     h->ba.part = (double*)(base + o_bpart);
+    h->ba.part2 = (double*)(base + o_bpart2);
+    h->ba.persistent = 1;
     h->ba.stats = (float*)(base + o_bs);
     h->ba.max_blocks = ba_blocks;
     h->refit.cand = (float*)(base + o_rc);
@@ -238,6 +241,7 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
             if (value < 0 || value > 1) return fail(SFMB200_ERR_ARG, "hypothesis solver must be 0 (Jacobi) or 1 (Cholesky projector)%s");
             h->hyp_solver = value;
             break;
+        case SFMB200_OPT_BA_PERSISTENT: h->ba.persistent = value ? 1 : 0; break;
         case SFMB200_OPT_PROFILE:
             if (value && !h->prof_ev) {
                 h->prof_ev = new cudaEvent_t[PROF_RING][8];

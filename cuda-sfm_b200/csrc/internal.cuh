@@ -72,7 +72,9 @@ struct BAState {
     double* dc;             // [B][6] camera step of the current iteration
     int* ctl_i;             // [B][8] see bundle.cu
     float* ctl_f;           // [B][8]
-    double* part;           // [B][max_blocks][34] per-CTA partial sums
+    double* part;           // [B][max_blocks][34] per-CTA partial sums of the normal equations
+    double* part2;          // [B][max_blocks][2]  per-CTA candidate cost / bad-point count
+    int persistent;         // 1: one cooperative launch per round when the grid is resident (default); 0: two launches per iteration
     float* stats;           // [B][8] device copy of the statistics of the last round
     int max_blocks;
 };

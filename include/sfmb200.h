@@ -52,8 +52,10 @@ typedef enum {
     SFMB200_OPT_HYP_SOLVER = 5,    /* null vector of the 8x9 design matrix: 0 register-resident 9x9 Jacobi eigensolve +
                                       design-row refinement; 1 (default) 8x8 Cholesky projector: same measured
                                       accuracy, 3.5-4.4x faster on B200 (see hyp_solver.cuh) */
-    SFMB200_OPT_PROFILE = 4        /* 1: record CUDA events between the stages of run_device / run_host
+    SFMB200_OPT_PROFILE = 4,       /* 1: record CUDA events between the stages of run_device / run_host
                                       (the reference's unused PerformanceTimer, common.h:48-132, done per stage) */
+    SFMB200_OPT_BA_PERSISTENT = 6  /* bundle adjustment: 1 (default) all LM iterations of a round in one cooperative
+                                      launch when the grid is resident; 0: two launches per iteration (same bits) */
 } sfmb200_option;
 
 const char* sfmb200_last_error(void);

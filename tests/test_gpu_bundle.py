@@ -113,6 +113,29 @@ def test_bundle_adjust_batched_equals_single_and_is_deterministic(pkg, O):
     assert np.all(st[:, 2] <= st[:, 1]) and np.all(st[:, 0] >= 8)
 
 
+def test_bundle_adjust_persistent_equals_two_kernel_path(pkg, O):
+    """One cooperative launch per round (grid barriers) and two launches per iteration (tickets) share their
+    phases and reduction orders: same bits."""
+    n = 3000
+
+    def run(persistent, pairs):
+        h, _, _ = _prepare(pkg, O, n, 13, 0.8, pairs=pairs)
+        h.set_option(6, persistent)
+        l0 = h.launch_count()
+        st = h.bundle_adjust(3, 12)
+        launches = h.launch_count() - l0
+        out = (h.get_poses().copy(), h.get_E().copy(), np.stack([h.get_points_host(b) for b in range(pairs)]), st.copy())
+        h.close()
+        return out, launches
+
+    for pairs in (1, 2):
+        (a, la), (b, lb) = run(1, pairs), run(0, pairs)
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+        assert la == 3 * 7 and lb == 3 * (6 + 2 * 12)
+        assert a[3][0, 3] >= 1 and a[3][0, 2] < a[3][0, 1]          # steps were accepted, the cost went down
+
+
 def test_bundle_adjust_compat_mode_and_errors(pkg, O):
     import torch
 
