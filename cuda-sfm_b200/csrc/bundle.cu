@@ -609,9 +609,8 @@ int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int
     ba_init_kernel<<<dim3(nb_all, s.B), BA_THREADS, 0, st>>>(s, ba, thr, lambda0);
     launches += 2;
     // one cooperative launch for all iterations when the whole grid is resident, else two launches per iteration
-    static int resident_per_sm = -1, sms = 0;
-    if (resident_per_sm < 0) {
-        int dev = 0;
+    int resident_per_sm = 0, sms = 0, dev = 0;
+    if (ba.persistent) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_per_sm, ba_persistent_kernel, BA_THREADS, 0);
