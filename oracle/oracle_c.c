@@ -123,14 +123,14 @@ void oracle_hypotheses_f64(const float* x, int n, const int32_t* idx, int H, dou
 /* ---------- scoring ---------- */
 /* Mirrors cuda-sfm_b200/csrc/sampson.cuh: the threshold is folded into the coordinates (k = sqrt(thr),
  * points * 1/k, E~ = D E D with D = diag(k,k,1)), then d = num~^2 - den~ with one fma tree. */
-static inline float sampson_d_f32(const float* e, float x1, float y1, float x2, float y2, float nthr) {
-    const float k = sqrtf(-nthr), ik = 1.0f / k, k2 = k * k;
-    float s[9];
+static inline void thr_scale_E(const float* e, float thr, float* s) {
+    const float k = sqrtf(thr), k2 = k * k;
     for (int q = 0; q < 9; q++) {
         float f = (q == 2 || q == 5 || q == 6 || q == 7) ? k : k2;
         s[q] = (q == 8) ? e[q] : e[q] * f;
     }
-    x1 *= ik; y1 *= ik; x2 *= ik; y2 *= ik;
+}
+static inline float sampson_unit_d_f32(const float* s, float x1, float y1, float x2, float y2) {
     float l0 = fmaf(s[0], x2, fmaf(s[1], y2, s[2]));
     float l1 = fmaf(s[3], x2, fmaf(s[4], y2, s[5]));
     float l2 = fmaf(s[6], x2, fmaf(s[7], y2, s[8]));
@@ -140,23 +140,34 @@ static inline float sampson_d_f32(const float* e, float x1, float y1, float x2, 
     float den = fmaf(l0, l0, fmaf(l1, l1, fmaf(m0, m0, m1 * m1)));
     return fmaf(num, num, -den);
 }
+static inline float sampson_d_f32(const float* e, float x1, float y1, float x2, float y2, float nthr) {
+    const float ik = 1.0f / sqrtf(-nthr);
+    float s[9];
+    thr_scale_E(e, -nthr, s);
+    return sampson_unit_d_f32(s, x1 * ik, y1 * ik, x2 * ik, y2 * ik);
+}
 
-/* E: H x 9 fp32 (exactly what the GPU scored); counts[h] = #{i : d < 0} */
+/* E: H x 9 fp32 (exactly what the GPU scored); counts[h] = #{i : d < 0}.  Like the GPU path the coordinates are
+ * scaled once and each hypothesis once (same operations as sampson_d_f32, hoisted). */
 void oracle_counts_f32(const float* E, int H, const float* x, int n, float thr, int32_t* counts) {
-    const float nthr = -thr;
+    const float ik = 1.0f / sqrtf(thr);
+    float* xs = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    for (size_t i = 0; i < 4 * (size_t)n; i++) xs[i] = x[i] * ik;
 #pragma omp parallel for schedule(static)
     for (int h = 0; h < H; h++) {
-        const float* e = E + 9 * (size_t)h;
+        float s[9];
+        thr_scale_E(E + 9 * (size_t)h, thr, s);
         int c = 0;
         for (int i = 0; i < n; i++) {
-            const float* p = x + 4 * (size_t)i;
-            float d = sampson_d_f32(e, p[0], p[1], p[2], p[3], nthr);
+            const float* p = xs + 4 * (size_t)i;
+            float d = sampson_unit_d_f32(s, p[0], p[1], p[2], p[3]);
             uint32_t bits;
             memcpy(&bits, &d, 4);
             c += (int)(bits >> 31);
         }
         counts[h] = c;
     }
+    free(xs);
 }
 
 /* fp64 truth on the same fp32 inputs; borderline[h] = #{i : |num^2 - thr*den| <= band*thr*den} */
