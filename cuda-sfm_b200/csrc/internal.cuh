@@ -15,7 +15,10 @@ struct ScorePlan {
     int ctas;           // persistent grid size (SMs x resident CTAs, capped by the work)
 };
 
-constexpr int SCORE_CHUNK = 512;     // points per TMA stage
+#ifndef SFMB200_SCORE_CHUNK
+#define SFMB200_SCORE_CHUNK 512
+#endif
+constexpr int SCORE_CHUNK = SFMB200_SCORE_CHUNK;     // points per TMA stage
 constexpr int SCORE_GRAIN = 64;      // work-partition granularity in points
 constexpr int SCORE_MIN_TILE = 256;  // smallest hypothesis tile of any kernel variant
 

@@ -36,7 +36,13 @@
 #include "internal.cuh"
 #include "sampson.cuh"
 
+#ifndef SFMB200_SCORE_UNROLL
+#define SFMB200_SCORE_UNROLL 4      // points per unrolled step of the packed inner loop (swept: profiles/r01_variant_sweep.md)
+#endif
+
 namespace sfmb200 {
+
+constexpr int kScoreUnroll = SFMB200_SCORE_UNROLL;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -286,7 +292,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
         }
         const float4* pb = buf[k & 1];
         if constexpr (PACKED) {
-#pragma unroll 4
+#pragma unroll kScoreUnroll
             for (int i = 0; i < n_here; i++) {
                 float4 a = pb[2 * i], q = pb[2 * i + 1];
                 float2 x1 = make_float2(a.x, a.y), y1 = make_float2(a.z, a.w);

@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""A/B of experimental builds of the library (tools/proto/libs/*.so) against the product build:
+score-kernel and whole-step time of config 2, CUDA events, mean of 30; each build in its own process."""
+import glob, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if len(sys.argv) > 1 and sys.argv[1] == "--one":
+    path = sys.argv[2]
+    sys.path.insert(0, ROOT)
+    import numpy as np, torch
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    pkg.load_library(path)
+    K, Kinv = pkg.synthetic.reference_K()
+    n, H = 10000, 65536
+    px = pkg.synthetic.synthetic_pair(n, 0.3, 1.0, seed=1234)["px"]
+    d_px = torch.from_numpy(px[None]).cuda()
+    h = pkg.BatchedPairs(K, Kinv, 1, n, H, lib=pkg.load_library(path))
+    h.set_option(4, 1)
+    for _ in range(5):
+        h.run_device(d_px, H, 1237, 1e-6)
+    h.set_option(4, 1)
+    for _ in range(30):
+        h.run_device(d_px, H, 1237, 1e-6)
+    st = h.stage_times().mean(axis=0)
+    h.set_option(4, 0)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(50):
+        h.run_device(d_px, H, 1237, 1e-6)
+    b.record(); torch.cuda.synchronize()
+    idx, cnt = h.get_best()
+    print(json.dumps(dict(lib=os.path.basename(path), score_ms=float(st[2]), step_ms=a.elapsed_time(b) / 50, best=[int(idx[0]), int(cnt[0])])), flush=True)
+else:
+    libs = [os.path.join(ROOT, "cuda-sfm_b200", "libsfmb200.so")] + sorted(glob.glob(os.path.join(ROOT, "tools", "proto", "libs", "*.so")))
+    for l in libs + libs[:1]:
+        subprocess.run([sys.executable, __file__, "--one", l])
