@@ -42,6 +42,12 @@ SIGNATURES = {
     "sfmb200_estimate_e": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, C.c_float]),
     "sfmb200_estimate_e_slice": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float]),
     "sfmb200_copy_to_vbo_coloured": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_float, C.c_int, C.c_float, C.c_float]),
+    "sfmb200_mg_handle_bytes": (C.c_int, []),
+    "sfmb200_mg_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "sfmb200_mg_connect": (C.c_int, [_vp, _vp]),
+    "sfmb200_estimate_e_mg": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, C.c_float]),
+    "sfmb200_mg_status": (C.c_int, [_vp, _vp]),
+    "sfmb200_mg_close": (C.c_int, [_vp]),
     "sfmb200_chain_views": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sfmb200_bundle_adjust": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sfmb200_estimate_e_adaptive": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float, C.c_float, _vp]),

@@ -38,6 +38,11 @@ struct sfmb200_handle {
     BAState ba;
     ChainState chain;
     void* chain_arena;     // lazily allocated by sfmb200_chain_views
+    MgPeers mg;            // multi-GPU peer exchange (mg.cu); mg.world == 0 until sfmb200_mg_init
+    void* mg_local;        // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
+    bool mg_connected;
+    long long mg_calls;
+    int* mg_status;        // device counter of timed-out waits
     cudaStream_t stream;
     bool own_stream;
     int device;
@@ -224,6 +229,7 @@ int sfmb200_destroy(sfmb200_t* h) {
     }
     cudaFree(h->arena);
     if (h->chain_arena) cudaFree(h->chain_arena);
+    sfmb200_mg_close(h);
     delete h;
     return SFMB200_OK;
 }
@@ -482,6 +488,94 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
         CK(cudaMemcpyAsync(h_used, h->adapt + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    return SFMB200_OK;
+}
+
+// ---- multi-GPU, hypothesis-sharded, peer-memory exchange (mg.cu) ----
+int sfmb200_mg_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int sfmb200_mg_init(sfmb200_t* h, int rank, int world, void* h_handle_out) {
+    if (!h || !h_handle_out) return fail(SFMB200_ERR_ARG, "null argument%s");
+    if (world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world) return fail(SFMB200_ERR_ARG, "bad rank / world (at most 16 ranks)%s");
+    if (h->mg_local) return fail(SFMB200_ERR_STATE, "mg_init called twice%s");
+    const size_t bytes = 2 * (size_t)h->s.B * sizeof(unsigned long long) + 64;
+    CK(cudaMalloc(&h->mg_local, bytes));
+    CK(cudaMemset(h->mg_local, 0, bytes));
+    CK(cudaMalloc((void**)&h->mg_status, sizeof(int)));
+    CK(cudaMemset(h->mg_status, 0, sizeof(int)));
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->mg_local));
+    memcpy(h_handle_out, &ipc, sizeof(ipc));
+    memset(&h->mg, 0, sizeof(h->mg));
+    h->mg.rank = rank;
+    h->mg.world = world;
+    h->mg.base[rank] = (unsigned long long*)h->mg_local;
+    h->mg_connected = false;
+    h->mg_calls = 0;
+    return SFMB200_OK;
+}
+
+int sfmb200_mg_connect(sfmb200_t* h, const void* h_handles) {
+    if (!h || !h_handles) return fail(SFMB200_ERR_ARG, "null argument%s");
+    if (!h->mg_local) return fail(SFMB200_ERR_STATE, "mg_connect before mg_init%s");
+    if (h->mg_connected) return fail(SFMB200_ERR_STATE, "mg_connect called twice%s");
+    const cudaIpcMemHandle_t* all = (const cudaIpcMemHandle_t*)h_handles;
+    for (int r = 0; r < h->mg.world; r++) {
+        if (r == h->mg.rank) continue;
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+        h->mg.base[r] = (unsigned long long*)p;
+    }
+    h->mg_connected = true;
+    return SFMB200_OK;
+}
+
+int sfmb200_mg_close(sfmb200_t* h) {
+    if (!h) return SFMB200_OK;
+    if (h->mg_local) {
+        cudaStreamSynchronize(h->stream);
+        for (int r = 0; r < h->mg.world; r++)
+            if (r != h->mg.rank && h->mg.base[r]) cudaIpcCloseMemHandle(h->mg.base[r]);
+        cudaFree(h->mg_local);
+        cudaFree(h->mg_status);
+        h->mg_local = nullptr;
+        h->mg_status = nullptr;
+        h->mg_connected = false;
+        memset(&h->mg, 0, sizeof(h->mg));
+    }
+    return SFMB200_OK;
+}
+
+// Every rank calls this with the same arguments on the same correspondences: scores its own slice of the
+// H_total hypotheses, exchanges the packed winners through peer memory and regenerates the global winner.
+int sfmb200_estimate_e_mg(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed, float thr) {
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!h->mg_connected) return fail(SFMB200_ERR_STATE, "estimate_e_mg before mg_init / mg_connect%s");
+    const int world = h->mg.world, rank = h->mg.rank;
+    if (H_total < world) return fail(SFMB200_ERR_ARG, "fewer hypotheses than ranks%s");
+    const long long base = H_total / world, rem = H_total % world;
+    const long long lo = rank * base + (rank < rem ? rank : rem), cnt = base + (rank < rem ? 1 : 0);
+    int rc = sfmb200_estimate_e_slice(h, d_idx, H_total, (int)lo, (int)cnt, seed, thr);
+    if (rc) return rc;
+    int clock_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);
+    const long long timeout_cycles = 2000LL * (clock_khz > 0 ? clock_khz : 1900000);      // ~2 s
+    launch_mg_exchange(h->s, h->mg, (int)(h->mg_calls & 1), timeout_cycles, h->mg_status, h->stream);
+    CKL();
+    h->mg_calls++;
+    launch_regen_best(h->s, d_idx, (long long)H_total * 8, seed, h->hyp_solver, h->stream);
+    CKL();
+    h->launches += 3;
+    h->have_candidates = false;        // the candidate arena holds this rank's slice only
+    return SFMB200_OK;
+}
+
+int sfmb200_mg_status(sfmb200_t* h, int32_t* h_timeouts) {
+    if (!h || !h_timeouts) return fail(SFMB200_ERR_ARG, "null argument%s");
+    *h_timeouts = 0;
+    if (!h->mg_status) return SFMB200_OK;
+    CK(cudaMemcpyAsync(h_timeouts, h->mg_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return SFMB200_OK;
 }
 

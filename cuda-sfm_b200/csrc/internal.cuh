@@ -81,6 +81,16 @@ struct BAState {
     float* stats;           // [B][8] device copy of the statistics of the last round
     int max_blocks;
 };
+// Peer exchange buffers of the hypothesis-sharded multi-GPU estimate (mg.cu): base[r] = rank r's buffer
+// (keys[2][B] uint64, then arrive[2] uint32), mapped into this process through CUDA IPC.
+constexpr int MG_MAX_WORLD = 16;
+struct MgPeers {
+    unsigned long long* base[MG_MAX_WORLD];
+    int rank, world;
+};
+void launch_mg_exchange(const DeviceState& s, const MgPeers& peers, int parity, long long timeout_cycles, int* d_status,
+                        cudaStream_t st);
+
 // Scratch and results of the N-view chaining stage (chain.cu); allocated on first use.
 struct ChainState {
     int* hist;                      // [B][2048] log-ratio histograms of the links

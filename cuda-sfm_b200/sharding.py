@@ -53,3 +53,44 @@ def estimate_e_sharded(handle, H_total: int, seed: int, thr: float, rank: int, w
         allreduce_best(handle.best_buffer(), group)
         handle.adopt_best(H_total, seed, d_idx)
     return lo, hi
+
+
+def connect_peers(handle, rank: int, world: int, group=None):
+    """One-time set-up of the peer-memory exchange (csrc/mg.cu): every rank exports the CUDA IPC handle of its
+    exchange buffer, the handles are all-gathered (plumbing, once) and every rank maps its peers' buffers."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    lib = handle.lib
+    nbytes = lib.raw("sfmb200_mg_handle_bytes")()
+    mine = (C.c_ubyte * nbytes)()
+    lib.call("sfmb200_mg_init", handle._h, rank, world, C.cast(mine, C.c_void_p))
+    t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device="cuda")
+    table = [torch.empty_like(t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(table, t, group=group)
+    else:
+        table[0] = t
+    blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in table)
+    buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+    lib.call("sfmb200_mg_connect", handle._h, C.cast(buf, C.c_void_p))
+
+
+def estimate_e_p2p(handle, H_total: int, seed: int, thr: float, d_idx=None):
+    """Hypothesis-sharded estimateE whose exchange step runs over peer memory (NVLink P2P atomics), no collective
+    call: same result as estimate_e_sharded / a single-GPU estimate over all H_total hypotheses, bit for bit."""
+    import ctypes as C
+
+    dptr = C.c_void_p(d_idx.data_ptr()) if d_idx is not None else C.c_void_p(0)
+    handle.lib.call("sfmb200_estimate_e_mg", handle._h, dptr, H_total, C.c_uint64(seed), C.c_float(thr))
+    handle.H = H_total
+
+
+def p2p_timeouts(handle) -> int:
+    import ctypes as C
+
+    v = C.c_int32(0)
+    handle.lib.call("sfmb200_mg_status", handle._h, C.byref(v))
+    return v.value

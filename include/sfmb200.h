@@ -110,6 +110,22 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
  * getters (get_inlier_counts, get_E_candidates) are not available. */
 int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, int first_round, int growth,
                                 uint64_t seed, float thr, float confidence, int32_t* h_used);
+/* ---- multi-GPU without a collective library on the data path (one process per GPU, one NVLink box) ----
+ * The exchange step of the hypothesis-sharded estimate is one 8-byte key per pair.  Instead of an
+ * all-reduce every rank pushes its key into every peer's exchange buffer with a system-scope atomicMax over
+ * peer memory, counts arrivals, and regenerates the winner locally.  Set-up: every rank calls sfmb200_mg_init
+ * (which returns an opaque handle of sfmb200_mg_handle_bytes() bytes: a CUDA IPC memory handle), the ranks
+ * exchange those handles by any means (the Python mirror uses torch.distributed.all_gather, once), and every
+ * rank calls sfmb200_mg_connect with the world x bytes table indexed by rank.  Then sfmb200_estimate_e_mg,
+ * called by every rank with the same arguments on the same correspondences, equals sfmb200_estimate_e over
+ * all H_total hypotheses bit for bit.  Waits are bounded (~2 s): sfmb200_mg_status returns the number of
+ * waits that timed out (0 in a healthy job). */
+int sfmb200_mg_handle_bytes(void);
+int sfmb200_mg_init(sfmb200_t* h, int rank, int world, void* h_handle_out);
+int sfmb200_mg_connect(sfmb200_t* h, const void* h_handles);
+int sfmb200_estimate_e_mg(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed, float thr);
+int sfmb200_mg_status(sfmb200_t* h, int32_t* h_timeouts);
+int sfmb200_mg_close(sfmb200_t* h);
 /* Device pointer to the per-pair packed winners, uint64 [pairs]:
  * (count << 32) | (0xFFFFFFFF - global hypothesis index).  Multi-GPU: all-reduce
  * this buffer with MAX over ranks (8 bytes per pair), then call
