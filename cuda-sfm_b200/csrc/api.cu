@@ -43,6 +43,7 @@ struct sfmb200_handle {
     bool mg_connected;
     long long mg_calls;
     int* mg_status;        // device counter of timed-out waits
+    long long mg_timeout_cycles;
     cudaStream_t stream;
     bool own_stream;
     int device;
@@ -512,6 +513,9 @@ int sfmb200_mg_init(sfmb200_t* h, int rank, int world, void* h_handle_out) {
     h->mg.base[rank] = (unsigned long long*)h->mg_local;
     h->mg_connected = false;
     h->mg_calls = 0;
+    int clock_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);      // slow query: once, not per call
+    h->mg_timeout_cycles = 2000LL * (clock_khz > 0 ? clock_khz : 1900000);    // ~2 s of SM clock
     return SFMB200_OK;
 }
 
@@ -557,10 +561,7 @@ int sfmb200_estimate_e_mg(sfmb200_t* h, const int32_t* d_idx, int H_total, uint6
     const long long lo = rank * base + (rank < rem ? rank : rem), cnt = base + (rank < rem ? 1 : 0);
     int rc = sfmb200_estimate_e_slice(h, d_idx, H_total, (int)lo, (int)cnt, seed, thr);
     if (rc) return rc;
-    int clock_khz = 0;
-    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);
-    const long long timeout_cycles = 2000LL * (clock_khz > 0 ? clock_khz : 1900000);      // ~2 s
-    launch_mg_exchange(h->s, h->mg, (int)(h->mg_calls & 1), timeout_cycles, h->mg_status, h->stream);
+    launch_mg_exchange(h->s, h->mg, (int)(h->mg_calls & 1), h->mg_timeout_cycles, h->mg_status, h->stream);
     CKL();
     h->mg_calls++;
     launch_regen_best(h->s, d_idx, (long long)H_total * 8, seed, h->hyp_solver, h->stream);
