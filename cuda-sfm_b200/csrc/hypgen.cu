@@ -8,6 +8,10 @@
 #include "hyp_solver.cuh"
 #include "internal.cuh"
 
+#ifndef SFMB200_HYPGEN_MINB
+#define SFMB200_HYPGEN_MINB 4       // resident CTAs per SM the projector kernel is compiled for (A/B: profiles/r01_variant_sweep.md)
+#endif
+
 namespace sfmb200 {
 
 
@@ -78,7 +82,7 @@ void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pai
     if (solver == 0)
         hypgen_kernel<128, 2, 0, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
     else if (solver == 1)
-        hypgen_kernel<128, 4, 0, 1><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
+        hypgen_kernel<128, SFMB200_HYPGEN_MINB, 0, 1><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
     else
         hypgen_kernel<128, 4, 0, 2><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
 }

@@ -29,8 +29,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         h.run_device(d_px, H, 1237, 1e-6)
     b.record(); torch.cuda.synchronize()
     idx, cnt = h.get_best()
-    print(json.dumps(dict(lib=os.path.basename(path), score_ms=float(st[2]), step_ms=a.elapsed_time(b) / 50, best=[int(idx[0]), int(cnt[0])])), flush=True)
+    print(json.dumps(dict(lib=os.path.basename(path), hypgen_ms=float(st[1]), score_ms=float(st[2]), step_ms=a.elapsed_time(b) / 50, best=[int(idx[0]), int(cnt[0])])), flush=True)
 else:
-    libs = [os.path.join(ROOT, "cuda-sfm_b200", "libsfmb200.so")] + sorted(glob.glob(os.path.join(ROOT, "tools", "proto", "libs", "*.so")))
+    libs = [os.path.join(ROOT, "cuda-sfm_b200", "libsfmb200.so")] + sorted(glob.glob(os.path.join(ROOT, "tools", "proto", "explibs", "*.so")))
     for l in libs + libs[:1]:
         subprocess.run([sys.executable, __file__, "--one", l])
