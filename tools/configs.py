@@ -45,6 +45,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the configs (tests)")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--variant", type=int, default=-1, help="scoring kernel variant (-1 = auto)")
+    ap.add_argument("--exchange", choices=["nccl", "p2p"], default="nccl",
+                    help="c3: exchange of the packed winners by all_reduce(MAX) or by the library's peer-memory push (csrc/mg.cu)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -68,10 +70,14 @@ def main():
         h.set_option(2, args.variant)
         h.set_points_xy(d_px)
 
+        if args.exchange == "p2p":
+            pkg.sharding.connect_peers(h, rank, world)
+
         def step():
-            pkg.sharding.estimate_e_sharded(h, H, 1237, THR, rank, world)
-            if world == 1:
-                pass
+            if args.exchange == "p2p":
+                pkg.sharding.estimate_e_p2p(h, H, 1237, THR)
+            else:
+                pkg.sharding.estimate_e_sharded(h, H, 1237, THR, rank, world)
         step()
         ms = timed(step, args.reps, world)
         idx, cnt = h.get_best()
@@ -82,7 +88,9 @@ def main():
             assert all(torch.equal(Es[0], e) for e in Es), "ranks disagree on the selected E"
         t = min(ms)
         emit(config="c3", n_gpus=world, n=n, H=H, sharding="hypotheses", ms=t, ms_all=ms, evals_per_s=n * H / (t * 1e-3),
-             best_index=int(idx[0]), inliers=int(cnt[0]), collective="one all_reduce(MAX) of 8 bytes", plan=h.score_plan())
+             best_index=int(idx[0]), inliers=int(cnt[0]),
+             collective="one all_reduce(MAX) of 8 bytes" if args.exchange == "nccl" else "none: keys pushed into peer memory (NVLink P2P atomics)",
+             plan=h.score_plan())
         h.close()
 
     if "c4" in args.which:
