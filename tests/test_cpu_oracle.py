@@ -241,3 +241,35 @@ def test_chain_restatement_on_exact_reconstructions(O):
     assert np.allclose(G, Gt, atol=1e-9)
     cloud, cnt = O.chain_merge(Xs, valids, G, S)
     assert np.all(cnt == views - 1) and np.allclose(cloud[:3].T, sc["X"] / sc["baselines"][0], atol=1e-9)
+
+
+def test_bundle_adjust_restatement_converges_from_a_perturbed_pose(O):
+    """The fp64 restatement of the two-view bundle adjustment (the checker of csrc/bundle.cu): from a perturbed
+    camera and DLT points it lowers the cost monotonically, lands near the true pose, keeps |t| = 1 and R in SO(3)."""
+    K, Kinv = O.reference_K()
+    n = 400
+    sc = O.synthetic_pair(n, outlier_frac=0.0, noise_px=0.3, seed=8)
+    x = O.normalise_points(sc["px"], Kinv).astype(np.float64)
+    R, t = sc["R"], sc["t"] / np.linalg.norm(sc["t"])
+    w = np.array([0.004, -0.006, 0.003])
+    M = np.eye(4)
+    M[:3, :3] = O._rodrigues(w) @ R
+    tp = t + np.array([0.0, 0.02, -0.03])
+    M[:3, 3] = tp / np.linalg.norm(tp)
+    X = O.triangulate(x, M)
+    act = O.ba_active(x, M, X, np.ones(n, bool))
+    assert act.sum() > 0.9 * n
+    r10 = O.bundle_adjust(x, M, X, act, 10)
+    r60 = O.bundle_adjust(x, M, X, act, 60)
+    assert r60["cost"] <= r10["cost"] <= r10["cost0"] and r60["accepted"] >= r10["accepted"] >= 1
+    Mo = r60["M"]
+    assert abs(np.linalg.norm(Mo[:3, 3]) - 1) < 1e-12 and np.abs(Mo[:3, :3] @ Mo[:3, :3].T - np.eye(3)).max() < 1e-9
+    e0 = np.linalg.norm(M[:3, :3] - R) + np.linalg.norm(M[:3, 3] - t)
+    e1 = np.linalg.norm(Mo[:3, :3] - R) + np.linalg.norm(Mo[:3, 3] - t)
+    assert e1 < 0.5 * e0
+    # reprojection RMS at the optimum is of the order of the noise (0.3 px in both views)
+    rms_px = np.sqrt(r60["cost"] / (4 * r60["n_active"])) * 2360
+    assert 0.1 < rms_px < 0.4
+    # the outer loop with E from the adjusted pose keeps every true inlier
+    out = O.bundle_adjust_rounds(x, M, O.essential_from_pose(M), 1e-6, 2, 30)
+    assert out["inliers"] >= 0.95 * n and np.allclose(np.linalg.svd(out["E"])[1], [1, 1, 0], atol=1e-9)
