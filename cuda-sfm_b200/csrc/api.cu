@@ -468,7 +468,7 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
         CKL();
         launch_score(s, h->plan, Hr, (int)lo, thr, h->stream);
         CKL();
-        launch_adaptive_decide(s, h->adapt, (int)hi, log1mp, hi >= H_max, h->stream);
+        launch_adaptive_decide(s, h->adapt, (int)lo, (int)hi, log1mp, hi >= H_max, h->stream);
         CKL();
         h->launches += 3;
         rounds++;
@@ -477,9 +477,7 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
         lo = hi;
         hi *= growth;
     }
-    launch_regen_best(h->s, d_idx, (long long)H_max * 8, seed, h->hyp_solver, h->stream);
-    CKL();
-    h->launches++;
+    // the decide kernel of each round publishes the running winner (E, index, count) from that round's arena
     h->thr = thr;
     h->have_candidates = false;   // the candidate arena holds whichever round ran last, not [0, used)
     h->have_E = true;

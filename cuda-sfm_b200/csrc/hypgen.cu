@@ -118,14 +118,31 @@ __global__ void regen_best_kernel(DeviceState s, const int32_t* __restrict__ d_i
 // when done_after >= needed for ALL pairs of the batch (or this is the last round) the flag is
 // raised, the remaining rounds' kernels return immediately and adapt[1] records the
 // hypotheses actually used.  One block; the host never synchronises between rounds.
-__global__ void adaptive_decide_kernel(DeviceState s, int* adapt, int done_after, double log1mp, int last) {
+__global__ void adaptive_decide_kernel(DeviceState s, int* adapt, int round_begin, int done_after, double log1mp, int last) {
     if (adapt[0] != 0) return;
     __shared__ int unsatisfied;
     if (threadIdx.x == 0) unsatisfied = 0;
     __syncthreads();
     int mine = 0;
     for (int b = threadIdx.x; b < s.B; b += blockDim.x) {
-        double w = (double)(int)(s.best[b] >> 32) / (double)s.n;
+        const unsigned long long packed = s.best[b];
+        const int cnt = (int)(packed >> 32);
+        // the running winner lives in this round's candidate arena iff its index falls in [round_begin, done_after):
+        // publish it now, so no hypothesis has to be regenerated after the last round
+        const unsigned int hg = 0xFFFFFFFFu - (unsigned int)(packed & 0xFFFFFFFFull);
+        const int local = (int)hg - round_begin;
+        if (packed != 0ull && local >= 0 && (int)hg < done_after) {
+            const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
+#pragma unroll
+            for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = Eb[(size_t)k * s.h_stride + local];
+        }
+        if (packed == 0ull && round_begin == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = 0.0f;
+        }
+        s.best_idx[b] = (int)hg;
+        s.best_count[b] = cnt;
+        double w = (double)cnt / (double)s.n;
         double w2 = w * w, w4 = w2 * w2, w8 = w4 * w4;
         bool ok = w8 >= 1.0 || (w8 > 0.0 && (double)done_after >= log1mp / log1p(-w8));
         mine += ok ? 0 : 1;
@@ -139,8 +156,9 @@ __global__ void adaptive_decide_kernel(DeviceState s, int* adapt, int done_after
         adapt[0] = 1;
     }
 }
-void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int done_after, double log1mp, int last, cudaStream_t st) {
-    adaptive_decide_kernel<<<1, 128, 0, st>>>(s, d_adapt, done_after, log1mp, last);
+void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int round_begin, int done_after, double log1mp, int last,
+                            cudaStream_t st) {
+    adaptive_decide_kernel<<<1, 128, 0, st>>>(s, d_adapt, round_begin, done_after, log1mp, last);
 }
 
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, unsigned long long seed,

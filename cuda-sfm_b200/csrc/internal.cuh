@@ -115,7 +115,8 @@ void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cud
 void launch_rescale_points(const DeviceState& s, cudaStream_t st);   // corr -> corr_s, corr_dup with s.pt_scale
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
                    unsigned long long seed, int solver, cudaStream_t st, int keep_best = 0);
-void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int done_after, double log1mp, int last, cudaStream_t st);
+void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int round_begin, int done_after, double log1mp, int last,
+                            cudaStream_t st);
 ScorePlan make_score_plan(int B, int n, int H, int variant_override);
 int score_num_variants();
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
