@@ -497,7 +497,7 @@ int sfmb200_mg_init(sfmb200_t* h, int rank, int world, void* h_handle_out) {
     if (!h || !h_handle_out) return fail(SFMB200_ERR_ARG, "null argument%s");
     if (world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world) return fail(SFMB200_ERR_ARG, "bad rank / world (at most 16 ranks)%s");
     if (h->mg_local) return fail(SFMB200_ERR_STATE, "mg_init called twice%s");
-    const size_t bytes = 2 * (size_t)h->s.B * sizeof(unsigned long long) + 64;
+    const size_t bytes = mg_buffer_bytes(h->s.B, world);
     CK(cudaMalloc(&h->mg_local, bytes));
     CK(cudaMemset(h->mg_local, 0, bytes));
     CK(cudaMalloc((void**)&h->mg_status, sizeof(int)));
@@ -559,12 +559,10 @@ int sfmb200_estimate_e_mg(sfmb200_t* h, const int32_t* d_idx, int H_total, uint6
     const long long lo = rank * base + (rank < rem ? rank : rem), cnt = base + (rank < rem ? 1 : 0);
     int rc = sfmb200_estimate_e_slice(h, d_idx, H_total, (int)lo, (int)cnt, seed, thr);
     if (rc) return rc;
-    launch_mg_exchange(h->s, h->mg, (int)(h->mg_calls & 1), h->mg_timeout_cycles, h->mg_status, h->stream);
+    launch_mg_exchange(h->s, h->mg, (int)(h->mg_calls & 1), H_total, h->mg_timeout_cycles, h->mg_status, h->stream);
     CKL();
     h->mg_calls++;
-    launch_regen_best(h->s, d_idx, (long long)H_total * 8, seed, h->hyp_solver, h->stream);
-    CKL();
-    h->launches += 3;
+    h->launches += 2;
     h->have_candidates = false;        // the candidate arena holds this rank's slice only
     return SFMB200_OK;
 }

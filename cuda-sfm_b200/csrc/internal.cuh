@@ -82,14 +82,15 @@ struct BAState {
     int max_blocks;
 };
 // Peer exchange buffers of the hypothesis-sharded multi-GPU estimate (mg.cu): base[r] = rank r's buffer
-// (keys[2][B] uint64, then arrive[2] uint32), mapped into this process through CUDA IPC.
+// (keys[2][B] uint64, arrive[2] uint32, E[2][world][B][9] float), mapped into this process through CUDA IPC.
 constexpr int MG_MAX_WORLD = 16;
 struct MgPeers {
     unsigned long long* base[MG_MAX_WORLD];
     int rank, world;
 };
-void launch_mg_exchange(const DeviceState& s, const MgPeers& peers, int parity, long long timeout_cycles, int* d_status,
-                        cudaStream_t st);
+void launch_mg_exchange(const DeviceState& s, const MgPeers& peers, int parity, int H_total, long long timeout_cycles,
+                        int* d_status, cudaStream_t st);
+size_t mg_buffer_bytes(int B, int world);
 
 // Scratch and results of the N-view chaining stage (chain.cu); allocated on first use.
 struct ChainState {
