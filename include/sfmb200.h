@@ -113,7 +113,8 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
 /* ---- multi-GPU without a collective library on the data path (one process per GPU, one NVLink box) ----
  * The exchange step of the hypothesis-sharded estimate is one 8-byte key per pair.  Instead of an
  * all-reduce every rank pushes its key into every peer's exchange buffer with a system-scope atomicMax over
- * peer memory, counts arrivals, and regenerates the winner locally.  Set-up: every rank calls sfmb200_mg_init
+ * peer memory together with the E of its local winner, counts arrivals, and reads the global winner's E from
+ * the slot of the rank that owns the winning index (nothing is regenerated, nothing returns to the host).  Set-up: every rank calls sfmb200_mg_init
  * (which returns an opaque handle of sfmb200_mg_handle_bytes() bytes: a CUDA IPC memory handle), the ranks
  * exchange those handles by any means (the Python mirror uses torch.distributed.all_gather, once), and every
  * rank calls sfmb200_mg_connect with the world x bytes table indexed by rank.  Then sfmb200_estimate_e_mg,
