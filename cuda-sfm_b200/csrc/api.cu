@@ -134,6 +134,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_pi = carve(B * sizeof(int));
     size_t o_pts = carve(B * 4 * (size_t)s.n_stride * sizeof(float));
     size_t o_tc = carve(B * sizeof(int));
+    size_t o_vote = carve(B * 8 * sizeof(int));
     size_t o_fs = carve(((size_t)max_points / 256 + 2) * sizeof(int));
     size_t o_ph = carve(B * 32 * sizeof(float));
     size_t o_pp = carve(B * 4 * (size_t)max_points * sizeof(float));
@@ -149,6 +150,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_bpart = carve(B * ba_blocks * 34 * sizeof(double));
     size_t o_bpart2 = carve(B * ba_blocks * 2 * sizeof(double));
     size_t o_bs = carve(B * 8 * sizeof(float));
+    size_t o_bcand = carve(B * 32 * sizeof(float));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
     size_t o_rT = carve(B * 8 * sizeof(float));
@@ -178,6 +180,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     s.P_ind = (int*)(base + o_pi);
     s.points = (float*)(base + o_pts);
     s.tri_count = (int*)(base + o_tc);
+    s.vote = (int*)(base + o_vote);
     h->filter_scratch = (int*)(base + o_fs);
     h->pack_header = (float*)(base + o_ph);
     h->pack_points = (float*)(base + o_pp);
@@ -192,6 +195,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->ba.part2 = (double*)(base + o_bpart2);
     h->ba.persistent = 1;
     h->ba.stats = (float*)(base + o_bs);
+    h->ba.cand = (float*)(base + o_bcand);
     h->ba.max_blocks = ba_blocks;
     h->refit.cand = (float*)(base + o_rc);
     h->refit.T = (float*)(base + o_rT);

@@ -138,7 +138,7 @@ __device__ void ba_apply_camera(const float* cam, const double* dc, float* out) 
 }
 
 // ---- state layout (BAState, internal.cuh) ----
-// ctl_i [B][8]: 0 cur buffer, 1 ticket A, 2 ticket B, 3 active points, 4 accepted steps, 5 solve ok, 6 inliers of refined E, 7 ticket C
+// ctl_i [B][8]: 0 cur buffer, 1 ticket A, 2 ticket B, 3 active points, 4 accepted steps, 5 solve ok, 6 inliers of the adjusted E, 7 committed
 // ctl_f [B][8]: 0 lambda, 1 cost (current), 2 cost at entry of this round, 3 spare
 
 // Start of an outer round: camera from P[P_ind], active set = inliers of the current E whose
@@ -516,6 +516,7 @@ __global__ void ba_finalise_kernel(DeviceState s, BAState ba, float* stats_out) 
     int* ci = ba.ctl_i + b * 8;
     float* cf = ba.ctl_f + b * 8;
     ci[6] = 0;
+    ci[7] = 0;
     if (ci[3] >= 8) {
         const float* cam = ba.cam + (size_t)b * 24 + 12 * ci[0];
         float R[9], t[3];
@@ -530,8 +531,8 @@ __global__ void ba_finalise_kernel(DeviceState s, BAState ba, float* stats_out) 
         const float nt = sqrtf(fmaf(t[0], t[0], fmaf(t[1], t[1], t[2] * t[2])));
         const float sc = nt > 0.0f ? 1.0f / nt : 1.0f;
         cf[3] = sc;
-        float* M = s.P + (size_t)b * 64 + 16 * s.P_ind[b];
-        for (int i = 0; i < 3; i++) {
+        float* M = ba.cand + (size_t)b * 32;         // candidate camera (16) and essential matrix (9): committed by
+        for (int i = 0; i < 3; i++) {                // ba_commit_kernel only if it does not lose inliers
             for (int j = 0; j < 3; j++) M[4 * i + j] = R[3 * i + j];
             M[4 * i + 3] = t[i] * sc;
         }
@@ -540,7 +541,7 @@ __global__ void ba_finalise_kernel(DeviceState s, BAState ba, float* stats_out) 
         float F[9];
         mul33(tx, R, F);
         for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) s.E[(size_t)b * 9 + 3 * i + j] = F[3 * j + i];
+            for (int j = 0; j < 3; j++) M[16 + 3 * i + j] = F[3 * j + i];
     } else {
         cf[3] = 1.0f;
     }
@@ -555,15 +556,14 @@ __global__ void ba_finalise_kernel(DeviceState s, BAState ba, float* stats_out) 
     }
 }
 
-// End of an outer round, point side (after the cloud has been re-triangulated with the refined
-// camera): the adjusted points, in the |t| = 1 gauge, replace the DLT points of the active
-// correspondences; the inliers of the refined E are counted into best_count.
-__global__ void __launch_bounds__(BA_THREADS) ba_scatter_kernel(DeviceState s, BAState ba, float thr) {
+// Inliers of the candidate E of each pair (same fp32 test as everywhere) -> ctl_i[6].
+__global__ void __launch_bounds__(BA_THREADS) ba_count_kernel(DeviceState s, BAState ba, float thr) {
     const int b = blockIdx.y;
     int* ci = ba.ctl_i + b * 8;
+    if (ci[3] < 8) return;
     __shared__ float sE[9];
     __shared__ int s_cnt;
-    if (threadIdx.x < 9) sE[threadIdx.x] = s.E[(size_t)b * 9 + threadIdx.x];
+    if (threadIdx.x < 9) sE[threadIdx.x] = ba.cand[(size_t)b * 32 + 16 + threadIdx.x];
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const int i = blockIdx.x * BA_THREADS + threadIdx.x;
@@ -571,14 +571,6 @@ __global__ void __launch_bounds__(BA_THREADS) ba_scatter_kernel(DeviceState s, B
     if (i < s.n) {
         const float4 p = s.corr[(size_t)b * s.n_stride + i];
         inl = sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f;
-        if (ci[3] >= 8 && ba.active[(size_t)b * s.n_stride + i]) {
-            const float sc = ba.ctl_f[b * 8 + 3];
-            const float* pts = ba.pts + ((size_t)b * 2 + ci[0]) * 3 * s.n_stride;
-            float* out = s.points + (size_t)b * 4 * s.n_stride;
-            out[i] = pts[i] * sc;
-            out[(size_t)s.n_stride + i] = pts[(size_t)s.n_stride + i] * sc;
-            out[(size_t)2 * s.n_stride + i] = pts[(size_t)2 * s.n_stride + i] * sc;
-        }
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, inl);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
@@ -586,14 +578,48 @@ __global__ void __launch_bounds__(BA_THREADS) ba_scatter_kernel(DeviceState s, B
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&ci[6], s_cnt);
 }
 
-// best_count <- inliers of the refined E; ticket counters back to zero for the next round.
-__global__ void ba_publish_kernel(DeviceState s, BAState ba, float* stats_out) {
+// "Never worse": the adjusted camera replaces P[pose_index], E and the best count only if its essential matrix
+// explains at least as many correspondences as the incumbent (the rule the refit stage uses too).
+__global__ void ba_commit_kernel(DeviceState s, BAState ba, float* stats_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= s.B) return;
     int* ci = ba.ctl_i + b * 8;
-    if (ci[3] >= 8) s.best_count[b] = ci[6];
-    if (stats_out) stats_out[(size_t)b * 8 + 6] = (float)ci[6];
-    ci[3] = 0;
+    const bool commit = ci[3] >= 8 && ci[6] >= s.best_count[b];
+    if (commit) {
+        const float* c = ba.cand + (size_t)b * 32;
+        float* M = s.P + (size_t)b * 64 + 16 * s.P_ind[b];
+        for (int i = 0; i < 16; i++) M[i] = c[i];
+        for (int i = 0; i < 9; i++) s.E[(size_t)b * 9 + i] = c[16 + i];
+        s.best_count[b] = ci[6];
+        ci[7] = 1;
+    }
+    if (stats_out) {
+        stats_out[(size_t)b * 8 + 6] = (float)ci[6];      // inliers of the adjusted model
+        stats_out[(size_t)b * 8 + 7] = commit ? 1.0f : 0.0f;
+    }
+}
+
+// End of an outer round, point side (after the cloud has been re-triangulated with the camera now in
+// P[pose_index]): when the adjusted model was committed, its points, in the |t| = 1 gauge, replace the DLT
+// points of the active correspondences.  Also clears the per-round state.
+__global__ void __launch_bounds__(BA_THREADS) ba_scatter_kernel(DeviceState s, BAState ba) {
+    const int b = blockIdx.y;
+    const int* ci = ba.ctl_i + b * 8;
+    const int i = blockIdx.x * BA_THREADS + threadIdx.x;
+    if (i < s.n && ci[7] != 0 && ba.active[(size_t)b * s.n_stride + i]) {
+        const float sc = ba.ctl_f[b * 8 + 3];
+        const float* pts = ba.pts + ((size_t)b * 2 + ci[0]) * 3 * s.n_stride;
+        float* out = s.points + (size_t)b * 4 * s.n_stride;
+        out[i] = pts[i] * sc;
+        out[(size_t)s.n_stride + i] = pts[(size_t)s.n_stride + i] * sc;
+        out[(size_t)2 * s.n_stride + i] = pts[(size_t)2 * s.n_stride + i] * sc;
+    }
+}
+
+__global__ void ba_publish_kernel(DeviceState s, BAState ba) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    ba.ctl_i[b * 8 + 3] = 0;
 }
 
 // One outer round = re-triangulate, select the active set, `iterations` LM steps, write back.
@@ -630,10 +656,12 @@ int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int
         }
     }
     ba_finalise_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s, ba, d_stats);
-    launch_triangulate(s, tri_inliers_only, thr, st);   // whole cloud under the refined camera (and refined E)
-    ba_scatter_kernel<<<dim3(nb_all, s.B), BA_THREADS, 0, st>>>(s, ba, thr);
-    ba_publish_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s, ba, d_stats);
-    launches += 4;
+    ba_count_kernel<<<dim3(nb_all, s.B), BA_THREADS, 0, st>>>(s, ba, thr);
+    ba_commit_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s, ba, d_stats);
+    launch_triangulate(s, tri_inliers_only, thr, st);   // whole cloud under the camera (and E) now in place
+    ba_scatter_kernel<<<dim3(nb_all, s.B), BA_THREADS, 0, st>>>(s, ba);
+    ba_publish_kernel<<<(s.B + 63) / 64, 64, 0, st>>>(s, ba);
+    launches += 6;
     return launches;
 }
 

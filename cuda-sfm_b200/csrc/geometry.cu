@@ -349,25 +349,27 @@ void launch_select_pose_choose(const DeviceState& s, int h_offset, int compat, c
     select_pose_choose_kernel<<<(threads + 63) / 64, 64, 0, st>>>(s, h_offset, compat);
 }
 
+// compat = 0: every inlier of the selected E votes for the candidates that put it in front of both cameras.
+// Grid over the correspondences (one thread per point, null vector by inverse iteration like the triangulation),
+// integer vote counters per pair, the last CTA of a pair picks the arg-max (first on ties) and clears the scratch.
 __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, float thr) {
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     __shared__ float sP[64];
     __shared__ float sE[9];
-    __shared__ int votes[4];
+    __shared__ int s_last;
     if (threadIdx.x < 64) sP[threadIdx.x] = s.P[(size_t)b * 64 + threadIdx.x];
     if (threadIdx.x < 9) sE[threadIdx.x] = s.E[(size_t)b * 9 + threadIdx.x];
-    if (threadIdx.x < 4) votes[threadIdx.x] = 0;
     __syncthreads();
     int local[4] = {0, 0, 0, 0};
     const float4* corr = s.corr + (size_t)b * s.n_stride;
-    for (int i = threadIdx.x; i < s.n; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += gridDim.x * blockDim.x) {
         float4 p = corr[i];
         if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr) >= 0.0f) continue;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             float A[16], v[4];
             dlt_matrix(p.x, p.y, p.z, p.w, sP + 16 * c, A);
-            null4<5>(A, v);
+            if (!null4_inverse_iteration<5>(A, v)) null4<5>(A, v);
             float X, Y, Z;
             dehomogenise(v, X, Y, Z);
             const float* M = sP + 16 * c;
@@ -375,6 +377,7 @@ __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, fl
             local[c] += (Z > 0.0f && z2 > 0.0f) ? 1 : 0;
         }
     }
+    int* votes = s.vote + (size_t)b * 8;          // [0..3] votes, [4] ticket
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         int v = local[c];
@@ -382,19 +385,30 @@ __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, fl
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&votes[c], v);
     }
+    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int best = 0;
-        for (int c = 1; c < 4; c++)
-            if (votes[c] > votes[best]) best = c;
-        s.P_ind[b] = best;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&votes[4], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    int best = 0, vb = __ldcg(&votes[0]);
+    for (int c = 1; c < 4; c++) {
+        int vc = __ldcg(&votes[c]);
+        if (vc > vb) { vb = vc; best = c; }
     }
+    s.P_ind[b] = best;
+    for (int c = 0; c < 5; c++) votes[c] = 0;     // clean for the next call
 }
 void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_t st) {
     if (compat)
         choose_pose_compat_kernel<<<(4 * s.B + 63) / 64, 64, 0, st>>>(s);
     else
-        choose_pose_vote_kernel<<<s.B, 256, 0, st>>>(s, thr);
+    {
+        int nb = (s.n + 255) / 256;
+        int cap = (1184 + s.B - 1) / s.B;                  // ~8 CTAs per SM over the whole batch
+        if (nb > cap) nb = cap < 1 ? 1 : cap;
+        choose_pose_vote_kernel<<<dim3(nb, s.B), 256, 0, st>>>(s, thr);
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -51,6 +51,7 @@ struct DeviceState {
     int* P_ind;         // [B]
     float* points;      // [B][4][n_stride] SoA (x,y,z,1), the reference's d_final_points layout
     int* tri_count;     // [B] points triangulated in front of both cameras (diagnostic)
+    int* vote;          // [B][8] cheirality votes of the four candidates + ticket (choose_pose_vote_kernel)
     const int* skip;    // adaptive termination: when non-null and *skip != 0 the hypgen / score kernels of
                         // the remaining rounds return at once (set by adaptive_decide_kernel); else nullptr
 };
@@ -79,6 +80,7 @@ struct BAState {
     double* part2;          // [B][max_blocks][2]  per-CTA candidate cost / bad-point count
     int persistent;         // 1: one cooperative launch per round when the grid is resident (default); 0: two launches per iteration
     float* stats;           // [B][8] device copy of the statistics of the last round
+    float* cand;            // [B][32] adjusted camera (16) + its essential matrix (9), before the commit decision
     int max_blocks;
 };
 // Peer exchange buffers of the hypothesis-sharded multi-GPU estimate (mg.cu): base[r] = rank r's buffer

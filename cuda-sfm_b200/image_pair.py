@@ -150,7 +150,7 @@ class BatchedPairs:
         self.lib.call("sfmb200_get_refit_iterations", self._h, _hptr(out))
         return out
 
-    BA_STATS = ("active", "cost_entry", "cost", "accepted", "lambda", "gauge_scale", "inliers", "spare")
+    BA_STATS = ("active", "cost_entry", "cost", "accepted", "lambda", "gauge_scale", "inliers", "committed")
 
     def bundle_adjust(self, outer_rounds: int = 4, iterations: int = 40) -> np.ndarray:
         """Two-view bundle adjustment with inlier re-selection; returns the [pairs, 8] statistics of the last round (BA_STATS)."""

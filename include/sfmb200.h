@@ -157,13 +157,14 @@ int sfmb200_refine_e(sfmb200_t* h, int iterations);
  * Marquardt on the reprojection error in normalised coordinates; camera 1 stays [I|0], the
  * gauge is |t| = 1.  Each of the `outer_rounds` rounds: inliers of the current E (same test
  * and threshold as the estimate) that triangulate in front of both cameras -> `iterations`
- * LM steps (point blocks eliminated by a Schur complement, 6x6 camera system) -> the refined
- * camera replaces P[pose_index], E is replaced by the essential matrix of that camera, the
- * whole cloud is re-triangulated (adjusted points for the active correspondences) and the
- * inlier count of the new E replaces the best count.  Everything is enqueued on the handle's
- * stream.  h_stats: NULL or host float [pairs][8] of the LAST round (forces a synchronise):
- * active points, cost at entry, cost at exit (sum of squared residuals), accepted steps,
- * lambda, gauge scale, inliers of the refined E, spare. */
+ * LM steps (point blocks eliminated by a Schur complement, 6x6 camera system) -> the essential
+ * matrix of the adjusted camera is scored; if it explains at least as many correspondences as the
+ * incumbent ("never worse") the camera replaces P[pose_index], its E replaces E, the inlier count
+ * replaces the best count and the adjusted points replace the triangulated ones of the active
+ * correspondences; in either case the whole cloud is re-triangulated under the camera in place.
+ * Everything is enqueued on the handle's stream.  h_stats: NULL or host float [pairs][8] of the
+ * LAST round (forces a synchronise): active points, cost at entry, cost at exit (sum of squared
+ * residuals), accepted steps, lambda, gauge scale, inliers of the adjusted model, committed (1 / 0). */
 int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float* h_stats);
 /* N-view chaining (the reference shapes Image_pair for image_count views,
  * sfm.h:23,30-31, but handles two).  The handle's pairs are CONSECUTIVE view pairs - pair b =

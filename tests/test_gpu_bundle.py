@@ -64,7 +64,7 @@ def test_bundle_adjust_matches_oracle_and_ground_truth(pkg, O):
     assert O.e_distance(E1[None], O.essential_from_pose(M1)[None])[0] < 1e-5
     assert np.allclose(np.linalg.svd(E1)[1], [1, 1, 0], atol=1e-5)
     assert c1 == int(h.get_inlier_mask().sum()) == int(O.sampson_mask_f32(E1, x, THR).sum())
-    assert st[2] <= st[1] and st[6] == c1
+    assert st[2] <= st[1] and st[6] == c1 and st[7] == 1
     # adjusted points reproject onto their observations
     X = h.get_points_host(0).astype(np.float64)
     m = O.sampson_mask_f32(E1, x, THR).astype(bool) & (X[2] > 0)
@@ -132,7 +132,7 @@ def test_bundle_adjust_persistent_equals_two_kernel_path(pkg, O):
         (a, la), (b, lb) = run(1, pairs), run(0, pairs)
         for u, v in zip(a, b):
             assert np.array_equal(u, v)
-        assert la == 3 * 7 and lb == 3 * (6 + 2 * 12)
+        assert la == 3 * 9 and lb == 3 * (8 + 2 * 12)
         assert a[3][0, 3] >= 1 and a[3][0, 2] < a[3][0, 1]          # steps were accepted, the cost went down
 
 
