@@ -151,6 +151,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_bpart2 = carve(B * ba_blocks * 2 * sizeof(double));
     size_t o_bs = carve(B * 8 * sizeof(float));
     size_t o_bcand = carve(B * 32 * sizeof(float));
+    size_t o_bbase = carve(B * sizeof(int));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
     size_t o_rT = carve(B * 8 * sizeof(float));
@@ -196,6 +197,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->ba.persistent = 1;
     h->ba.stats = (float*)(base + o_bs);
     h->ba.cand = (float*)(base + o_bcand);
+    h->ba.base_count = (int*)(base + o_bbase);
     h->ba.max_blocks = ba_blocks;
     h->refit.cand = (float*)(base + o_rc);
     h->refit.T = (float*)(base + o_rT);
@@ -619,7 +621,7 @@ int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float*
         return fail(SFMB200_ERR_STATE, "bundle_adjust needs an essential matrix and a chosen pose%s");
     const float thr = h->thr > 0 ? h->thr : 1e-6f;
     for (int r = 0; r < outer_rounds; r++) {
-        h->launches += launch_bundle_adjust(h->s, h->ba, thr, iterations, 1e-3f, h->tri_inliers_only, h->ba.stats, h->stream);
+        h->launches += launch_bundle_adjust(h->s, h->ba, thr, iterations, 1e-3f, h->tri_inliers_only, r == 0, h->ba.stats, h->stream);
         CKL();
     }
     if (h_stats) {

@@ -143,7 +143,7 @@ __device__ void ba_apply_camera(const float* cam, const double* dc, float* out) 
 
 // Start of an outer round: camera from P[P_ind], active set = inliers of the current E whose
 // triangulated point is finite and in front of both cameras, points copied into buffer 0.
-__global__ void __launch_bounds__(BA_THREADS) ba_init_kernel(DeviceState s, BAState ba, float thr, float lambda0) {
+__global__ void __launch_bounds__(BA_THREADS) ba_init_kernel(DeviceState s, BAState ba, float thr, float lambda0, int first_round) {
     const int b = blockIdx.y;
     __shared__ float sM[12];
     __shared__ float sE[9];
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_init_kernel(DeviceState s, BASt
             ba.ctl_i[b * 8 + 0] = 0;
             ba.ctl_i[b * 8 + 4] = 0;
             ba.ctl_f[b * 8 + 0] = lambda0;
+            if (first_round) ba.base_count[b] = s.best_count[b];      // the consensus this call must not lose
         }
     }
     const int i = blockIdx.x * BA_THREADS + threadIdx.x;
@@ -578,13 +579,16 @@ __global__ void __launch_bounds__(BA_THREADS) ba_count_kernel(DeviceState s, BAS
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&ci[6], s_cnt);
 }
 
-// "Never worse": the adjusted camera replaces P[pose_index], E and the best count only if its essential matrix
-// explains at least as many correspondences as the incumbent (the rule the refit stage uses too).
+// Guard against losing the consensus: the adjusted camera replaces P[pose_index], E and the best count only if its
+// essential matrix still explains at least 95 % of the correspondences the model had when sfmb200_bundle_adjust was
+// called (the count may dip by a few borderline points while the pose moves along the rotation / translation
+// valley - a strict "never fewer" rule would freeze the adjustment there - but it must not collapse, which happens
+// when only a small part of the inliers triangulates in front of both cameras).
 __global__ void ba_commit_kernel(DeviceState s, BAState ba, float* stats_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= s.B) return;
     int* ci = ba.ctl_i + b * 8;
-    const bool commit = ci[3] >= 8 && ci[6] >= s.best_count[b];
+    const bool commit = ci[3] >= 8 && 20LL * ci[6] >= 19LL * ba.base_count[b];
     if (commit) {
         const float* c = ba.cand + (size_t)b * 32;
         float* M = s.P + (size_t)b * 64 + 16 * s.P_ind[b];
@@ -625,14 +629,14 @@ __global__ void ba_publish_kernel(DeviceState s, BAState ba) {
 // One outer round = re-triangulate, select the active set, `iterations` LM steps, write back.
 // Returns the number of kernel launches.
 int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int iterations, float lambda0,
-                         int tri_inliers_only, float* d_stats, cudaStream_t st) {
+                         int tri_inliers_only, int first_round, float* d_stats, cudaStream_t st) {
     int launches = 0;
     // init / scatter: one thread per correspondence; LM kernels: at most max_blocks CTAs per pair (about four
     // CTAs per SM over the whole batch, several correspondences per thread) so the per-CTA reductions stay cheap
     const int nb_all = (s.n + BA_THREADS - 1) / BA_THREADS;
     const int nb = nb_all < ba.max_blocks ? nb_all : ba.max_blocks;
     launch_triangulate(s, 1, thr, st);      // only inliers of the current E can become active
-    ba_init_kernel<<<dim3(nb_all, s.B), BA_THREADS, 0, st>>>(s, ba, thr, lambda0);
+    ba_init_kernel<<<dim3(nb_all, s.B), BA_THREADS, 0, st>>>(s, ba, thr, lambda0, first_round);
     launches += 2;
     // one cooperative launch for all iterations when the whole grid is resident, else two launches per iteration
     int resident_per_sm = 0, sms = 0, dev = 0;

@@ -80,6 +80,7 @@ struct BAState {
     double* part2;          // [B][max_blocks][2]  per-CTA candidate cost / bad-point count
     int persistent;         // 1: one cooperative launch per round when the grid is resident (default); 0: two launches per iteration
     float* stats;           // [B][8] device copy of the statistics of the last round
+    int* base_count;        // [B] inliers of the model when sfmb200_bundle_adjust was called (commit guard)
     float* cand;            // [B][32] adjusted camera (16) + its essential matrix (9), before the commit decision
     int max_blocks;
 };
@@ -108,7 +109,7 @@ struct ChainState {
 int launch_chain(const DeviceState& s, const ChainState& c, float thr, float* d_cloud, int* d_count, cudaStream_t st);
 
 int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int iterations, float lambda0,
-                         int tri_inliers_only, float* d_stats, cudaStream_t st);
+                         int tri_inliers_only, int first_round, float* d_stats, cudaStream_t st);
 
 void launch_ingest_sift(const DeviceState& s, const void* d_sift, int n, cudaStream_t st);
 void launch_ingest_sift_filtered(const DeviceState& s, const void* d_sift, int n, float min_score, float max_ambiguity,

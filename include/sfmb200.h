@@ -158,8 +158,8 @@ int sfmb200_refine_e(sfmb200_t* h, int iterations);
  * gauge is |t| = 1.  Each of the `outer_rounds` rounds: inliers of the current E (same test
  * and threshold as the estimate) that triangulate in front of both cameras -> `iterations`
  * LM steps (point blocks eliminated by a Schur complement, 6x6 camera system) -> the essential
- * matrix of the adjusted camera is scored; if it explains at least as many correspondences as the
- * incumbent ("never worse") the camera replaces P[pose_index], its E replaces E, the inlier count
+ * matrix of the adjusted camera is scored; if it still explains at least 95 % of the correspondences
+ * the model had when this function was called the camera replaces P[pose_index], its E replaces E, the inlier count
  * replaces the best count and the adjusted points replace the triangulated ones of the active
  * correspondences; in either case the whole cloud is re-triangulated under the camera in place.
  * Everything is enqueued on the handle's stream.  h_stats: NULL or host float [pairs][8] of the

@@ -570,10 +570,11 @@ def essential_from_pose(M: np.ndarray) -> np.ndarray:
 def bundle_adjust_rounds(x: np.ndarray, M: np.ndarray, E: np.ndarray, thr: float = 1e-6, outer_rounds: int = 3,
                          iterations: int = 10):
     """Outer loop of sfmb200_bundle_adjust: inliers of the current E -> LM -> E from the
-    refined camera -> recount -> commit unless inliers were lost.  Returns dict(M, E, X, inliers, rounds=[per-round results])."""
+    refined camera -> recount -> commit unless the consensus collapsed.  Returns dict(M, E, X, inliers, rounds=[per-round results])."""
     M, E = np.asarray(M, np.float64), np.asarray(E, np.float64)
     rounds = []
     X = None
+    base_count = int(sampson_mask_f32(E, x, thr).sum())
     for _ in range(outer_rounds):
         mask = sampson_mask_f32(E, x, thr)
         X0 = triangulate(x, M)
@@ -583,10 +584,11 @@ def bundle_adjust_rounds(x: np.ndarray, M: np.ndarray, E: np.ndarray, thr: float
             rounds.append(dict(M=M, X=X0, cost0=0.0, cost=0.0, accepted=0, n_active=int(act.sum())))
             continue
         r = bundle_adjust(x, M, X0, act, iterations)
-        # "never worse": the adjusted model replaces the incumbent only if its E explains at least as many correspondences
+        # commit guard: the adjusted model replaces the incumbent only if its E still explains >= 95 % of the
+        # correspondences the model had when the call started
         E_new = essential_from_pose(r["M"])
         r["inliers"] = int(sampson_mask_f32(E_new, x, thr).sum())
-        r["committed"] = r["inliers"] >= int(mask.sum())
+        r["committed"] = 20 * r["inliers"] >= 19 * base_count
         if r["committed"]:
             M, X, E = r["M"], r["X"], E_new
         else:

@@ -61,7 +61,7 @@ def test_facade_demo_matches_python_mirror(pkg, O, tmp_path):
     h.pose_candidates(); h.choose_pose(); h.triangulate()
     st = h.bundle_adjust(3, 10)[0]
     assert (info["adaptive_used"], info["refits"], info["inliers_refit"]) == (used, int(refits[0]), inl_refit)
-    assert info["inliers_ba"] == int(h.get_best()[1][0]) >= inl_refit          # never worse than the refit
+    assert info["inliers_ba"] == int(h.get_best()[1][0]) >= 0.95 * inl_refit   # the commit guard
     assert st[7] == 0 or int(st[6]) == info["inliers_ba"]                       # committed: the adjusted model's count
     assert info["ba_active"] == st[0] and np.float32(info["ba_cost"]) == st[2] and info["ba_cost"] <= info["ba_cost_entry"]
     assert np.array_equal(np.asarray(info["E_ba"], np.float32), h.get_E()[0].reshape(9))
