@@ -195,3 +195,37 @@ def test_shard_range_and_keys(pkg):
     assert sh.pack_key(10, 500) > sh.pack_key(9, 0)
     assert sh.pack_key(10, 3) > sh.pack_key(10, 4)
     assert sh.pack_key(2**31 - 1, 0) < 2**63
+
+
+def test_headers_are_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: include/*.h compile as strict C99, and a C program that includes them links
+    against the shared library with nothing but gcc (no CUDA headers, no C++)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "sfmb200.h"\n#include "sfmb200_la.h"\n'
+        "int main(void) {\n"
+        "    float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};\n"
+        "    sfmb200_t* h = NULL;\n"
+        "    int rc = sfmb200_create(K, K, 1, 64, 64, &h);\n"
+        '    printf("%d %d %s\\n", sfmb200_version(), rc, sfmb200_last_error());\n'
+        "    if (rc == 0) sfmb200_destroy(h);\n"
+        "    return 0;\n}\n")
+    libdir = os.path.join(ROOT, "cuda-sfm_b200")
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", libdir, "-lsfmb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    ver, rc, *msg = out.stdout.split()
+    assert int(ver) >= 100
+    # without a GPU the create call must fail with the "no CUDA device" status, never fall back
+    import torch
+    if not torch.cuda.is_available():
+        assert int(rc) != 0 and "no CUDA device" in out.stdout
