@@ -1,8 +1,8 @@
 """fp64 CPU restatement of the reference hot path (TEST INFRASTRUCTURE ONLY).
 
-Only tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference
-legs and the checker-side dev tools (tools/gpu_diag.py, tools/reference_baselines.py)
-may import this module.  The product path (cuda-sfm_b200/) never does: it fails
+Only tests/ (including the checker-side diagnostics under tests/diag/),
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product path (cuda-sfm_b200/) never does: it fails
 loudly when the CUDA library is missing.
 
 Reference: Black-Phoenix/CUDA-SfM, files under SfM/.  Each function cites the
