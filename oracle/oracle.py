@@ -14,10 +14,15 @@ ties) - see SURVEY.md section 2.3.
 
 PARITY PINNING: the reference ships no asserting tests and no golden vectors
 (SURVEY.md section 4), so the pins are (1) the literals of its print-only tests
-(tests/test_oracle_reference_literals.py), (2) the reference's own CUDA code
-rebuilt unmodified as oracle/_ref/libsfm_ref.so and run on the GPU box
-(tests/test_gpu_reference_parity.py).  Everything else is "pinned by fp64
-math".
+and its own host svd()/det() compiled from svd.h (tests/test_cpu_oracle.py,
+tests/test_cpu_hostlogic.py, tests/test_gpu_la_wrappers.py), (2) the reference's
+own CUDA code rebuilt unmodified as oracle/_ref/libsfm_ref.so and run stage by
+stage on the GPU box (tests/test_gpu_reference_parity.py), (3) the committed
+fixture of the reference's own image pair (tests/golden/dino_000_001.npz,
+tests/test_golden_dino.py).  What the reference cannot pin because its code is
+undefined behaviour there (inlier counts, arg-max) and everything it does not
+have (refit, adaptive termination, homography model, bundle adjustment,
+chaining) is pinned by fp64 math and ground truth only.
 """
 from __future__ import annotations
 
