@@ -74,3 +74,31 @@ def test_run_host_pinned_zero_copy_equals_staged(pkg, O):
     for k in ("E", "P", "pose_index", "inliers", "points"):
         assert np.array_equal(a[k], out2[k]), k
     h.close()
+
+
+def test_whole_path_is_cuda_graph_capturable(pkg, O):
+    """run_device only enqueues kernels on the handle's stream (no allocation, no synchronisation), so a caller can
+    capture it in a CUDA graph; replay gives the same bits (tools/graph_check.py: -19 % at config-1 sizes)."""
+    import numpy as np
+    import torch
+
+    K, Kinv = O.reference_K()
+    n, H = 2000, 250
+    d_px = torch.from_numpy(O.synthetic_pair(n, seed=5)["px"][None]).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        h = pkg.BatchedPairs(K, Kinv, 1, n, H)
+        for _ in range(2):
+            h.run_device(d_px, H, 7, 1e-6)
+        s.synchronize()
+        ref = (h.get_best()[0].copy(), h.get_E().copy(), h.get_points_host(0).copy())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            h.run_device(d_px, H, 7, 1e-6)
+        h.set_E(np.zeros((1, 9), np.float32))          # perturb the state, then let the replay restore it
+        for _ in range(3):
+            g.replay()
+        s.synchronize()
+        got = (h.get_best()[0], h.get_E(), h.get_points_host(0))
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+        h.close()
