@@ -783,13 +783,17 @@ int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t see
                      int32_t* h_pose_index, int32_t* h_inliers, float* h_points) {
     if (h) prof_next(h);
     if (h && thr > 0.0f) h->s.pt_scale = make_thr_scale(thr).ik;
-    const float* px_alias = (const float*)pinned_alias(h_px);
+    // zero copy pays where latency dominates (config-2-sized calls: 160 KB each way); bulk transfers (batched
+    // config 4: hundreds of MB) stay with the copy engines, which keep more PCIe requests in flight than a kernel
+    const size_t zero_copy_limit = 4u << 20;
+    const size_t in_bytes = h ? (size_t)h->s.B * (size_t)(n > 0 ? n : 0) * 4 * sizeof(float) : 0;
+    const float* px_alias = in_bytes <= zero_copy_limit ? (const float*)pinned_alias(h_px) : nullptr;
     int rc = px_alias ? sfmb200_set_points_xy(h, px_alias, n) : sfmb200_set_points_xy_host(h, h_px, n);
     if (rc) return rc;
     if ((rc = run_stages(h, H, seed, thr))) return rc;
     DeviceState& s = h->s;
     const size_t B = s.B;
-    float* pts_alias = (float*)pinned_alias(h_points);
+    float* pts_alias = B * 4 * (size_t)s.n * sizeof(float) <= zero_copy_limit ? (float*)pinned_alias(h_points) : nullptr;
     dim3 grid(h_points ? (s.n + 255) / 256 : 1, (unsigned)B);
     // header: always through the handle's own pinned buffer (device-visible under UVA); points: straight into the
     // caller's buffer when it is pinned, else into the device staging copy followed by one DMA
