@@ -191,8 +191,9 @@ int sfmb200_triangulate(sfmb200_t* h);
  * of E [pairs][9], P (selected pose) [pairs][16], pose index [pairs], inlier
  * count [pairs] and, if h_points != NULL, points [pairs][4][n].  One stream
  * synchronisation at the end. */
-/* Page-locked h_px / h_points (cudaHostAlloc, cudaHostRegister, torch pin_memory) are read and written by the
- * kernels directly through their device-visible aliases (no staging copies); pageable buffers are staged. */
+/* Page-locked h_px / h_points (cudaHostAlloc, cudaHostRegister, torch pin_memory) of up to 4 MB are read and
+ * written by the kernels directly through their device-visible aliases (no staging copies: the call is
+ * latency bound at those sizes); larger or pageable buffers go through the copy engines. */
 int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t seed, float thr, float* h_E, float* h_P,
                      int32_t* h_pose_index, int32_t* h_inliers, float* h_points);
 /* Same with device-resident input, no output copies (results stay on the device). */
