@@ -15,6 +15,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     px = pkg.synthetic.synthetic_pair(n, 0.3, 1.0, seed=1234)["px"]
     d_px = torch.from_numpy(px[None]).cuda()
     h = pkg.BatchedPairs(K, Kinv, 1, n, H, lib=pkg.load_library(path))
+    if os.environ.get("SFMB200_AB_VARIANT"):
+        h.set_option(2, int(os.environ["SFMB200_AB_VARIANT"]))
     h.set_option(4, 1)
     for _ in range(5):
         h.run_device(d_px, H, 1237, 1e-6)
