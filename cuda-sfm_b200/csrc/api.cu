@@ -38,6 +38,7 @@ struct sfmb200_handle {
     BAState ba;
     ChainState chain;
     void* chain_arena;     // lazily allocated by sfmb200_chain_views
+    void* ba_arena;        // lazily allocated by sfmb200_bundle_adjust (6 floats + 1 byte per correspondence)
     MgPeers mg;            // multi-GPU peer exchange (mg.cu); mg.world == 0 until sfmb200_mg_init
     void* mg_local;        // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
     bool mg_connected;
@@ -139,19 +140,6 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_ph = carve(B * 32 * sizeof(float));
     size_t o_pp = carve(B * 4 * (size_t)max_points * sizeof(float));
     size_t o_ad = carve(4 * sizeof(int));
-    int ba_blocks = (592 + pairs - 1) / pairs;      // LM kernels: ~4 CTAs per SM over the whole batch
-    ba_blocks = ba_blocks < 2 ? 2 : (ba_blocks > 296 ? 296 : ba_blocks);
-    size_t o_bp = carve(B * 2 * 3 * (size_t)s.n_stride * sizeof(float));
-    size_t o_ba = carve(B * (size_t)s.n_stride);
-    size_t o_bc2 = carve(B * 24 * sizeof(float));
-    size_t o_bd = carve(B * 6 * sizeof(double));
-    size_t o_bi2 = carve(B * 8 * sizeof(int));
-    size_t o_bf = carve(B * 8 * sizeof(float));
-    size_t o_bpart = carve(B * ba_blocks * 34 * sizeof(double));
-    size_t o_bpart2 = carve(B * ba_blocks * 2 * sizeof(double));
-    size_t o_bs = carve(B * 8 * sizeof(float));
-    size_t o_bcand = carve(B * 32 * sizeof(float));
-    size_t o_bbase = carve(B * sizeof(int));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
     size_t o_rT = carve(B * 8 * sizeof(float));
@@ -186,19 +174,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->pack_header = (float*)(base + o_ph);
     h->pack_points = (float*)(base + o_pp);
     h->adapt = (int*)(base + o_ad);
-    h->ba.pts = (float*)(base + o_bp);
-    h->ba.active = (unsigned char*)(base + o_ba);
-    h->ba.cam = (float*)(base + o_bc2);
-    h->ba.dc = (double*)(base + o_bd);
-    h->ba.ctl_i = (int*)(base + o_bi2);
-    h->ba.ctl_f = (float*)(base + o_bf);
-    h->ba.part = (double*)(base + o_bpart);
-    h->ba.part2 = (double*)(base + o_bpart2);
-    h->ba.persistent = 1;
-    h->ba.stats = (float*)(base + o_bs);
-    h->ba.cand = (float*)(base + o_bcand);
-    h->ba.base_count = (int*)(base + o_bbase);
-    h->ba.max_blocks = ba_blocks;
+    h->ba.persistent = 1;      // the bundle-adjustment scratch itself is allocated on first use (ensure_ba_arena)
     h->refit.cand = (float*)(base + o_rc);
     h->refit.T = (float*)(base + o_rT);
     h->refit.flags = (int*)(base + o_rf);
@@ -236,6 +212,7 @@ int sfmb200_destroy(sfmb200_t* h) {
     }
     cudaFree(h->arena);
     if (h->chain_arena) cudaFree(h->chain_arena);
+    if (h->ba_arena) cudaFree(h->ba_arena);
     sfmb200_mg_close(h);
     delete h;
     return SFMB200_OK;
@@ -608,6 +585,45 @@ int sfmb200_refine_e(sfmb200_t* h, int iterations) {
     h->have_pose = false;
     return SFMB200_OK;
 }
+// Scratch of the bundle adjustment: allocated on first use so that handles that never adjust (the batched
+// configs: thousands of pairs) do not carry 25 bytes per correspondence for it.
+static int ensure_ba_arena(sfmb200_handle* h) {
+    if (h->ba_arena) return SFMB200_OK;
+    const DeviceState& s = h->s;
+    const size_t B = s.B;
+    int ba_blocks = (592 + s.B - 1) / s.B;          // LM kernels: ~4 CTAs per SM over the whole batch
+    ba_blocks = ba_blocks < 2 ? 2 : (ba_blocks > 296 ? 296 : ba_blocks);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_bp = carve(B * 2 * 3 * (size_t)s.n_stride * sizeof(float));
+    size_t o_ba = carve(B * (size_t)s.n_stride);
+    size_t o_bc2 = carve(B * 24 * sizeof(float));
+    size_t o_bd = carve(B * 6 * sizeof(double));
+    size_t o_bi2 = carve(B * 8 * sizeof(int));
+    size_t o_bf = carve(B * 8 * sizeof(float));
+    size_t o_bpart = carve(B * ba_blocks * 34 * sizeof(double));
+    size_t o_bpart2 = carve(B * ba_blocks * 2 * sizeof(double));
+    size_t o_bs = carve(B * 8 * sizeof(float));
+    size_t o_bcand = carve(B * 32 * sizeof(float));
+    size_t o_bbase = carve(B * sizeof(int));
+    CK(cudaMalloc(&h->ba_arena, off));
+    CK(cudaMemsetAsync(h->ba_arena, 0, off, h->stream));
+    char* base = (char*)h->ba_arena;
+    h->ba.pts = (float*)(base + o_bp);
+    h->ba.active = (unsigned char*)(base + o_ba);
+    h->ba.cam = (float*)(base + o_bc2);
+    h->ba.dc = (double*)(base + o_bd);
+    h->ba.ctl_i = (int*)(base + o_bi2);
+    h->ba.ctl_f = (float*)(base + o_bf);
+    h->ba.part = (double*)(base + o_bpart);
+    h->ba.part2 = (double*)(base + o_bpart2);
+    h->ba.stats = (float*)(base + o_bs);
+    h->ba.cand = (float*)(base + o_bcand);
+    h->ba.base_count = (int*)(base + o_bbase);
+    h->ba.max_blocks = ba_blocks;
+    return SFMB200_OK;
+}
+
 // Bundle adjustment of the selected pose and the triangulated inliers with inlier re-selection
 // (bundle.cu).  Each outer round: inliers of the current E -> LM iterations -> refined camera,
 // E derived from it, cloud re-triangulated, inliers recounted.  h_stats (optional, host
@@ -620,6 +636,7 @@ int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float*
     if (!h->have_points || !h->have_E || !h->have_pose || h->model != 0)
         return fail(SFMB200_ERR_STATE, "bundle_adjust needs an essential matrix and a chosen pose%s");
     const float thr = h->thr > 0 ? h->thr : 1e-6f;
+    if (int rc = ensure_ba_arena(h)) return rc;
     for (int r = 0; r < outer_rounds; r++) {
         h->launches += launch_bundle_adjust(h->s, h->ba, thr, iterations, 1e-3f, h->tri_inliers_only, r == 0, h->ba.stats, h->stream);
         CKL();
