@@ -38,6 +38,8 @@ struct sfmb200_handle {
     BAState ba;
     ChainState chain;
     void* chain_arena;     // lazily allocated by sfmb200_chain_views
+    void* staging_in;      // lazily allocated: device copy of pageable host input
+    void* staging_out;     // lazily allocated: compact device copy of the points for host output
     void* ba_arena;        // lazily allocated by sfmb200_bundle_adjust (6 floats + 1 byte per correspondence)
     MgPeers mg;            // multi-GPU peer exchange (mg.cu); mg.world == 0 until sfmb200_mg_init
     void* mg_local;        // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
@@ -123,7 +125,6 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_corr = carve(B * s.n_stride * sizeof(float4));
     size_t o_cs = carve(B * s.n_stride * sizeof(float4));
     size_t o_dup = carve(B * s.n_stride * 2 * sizeof(float4));
-    size_t o_px = carve(B * s.n_stride * 4 * sizeof(float));
     size_t o_ec = carve(B * 9 * (size_t)s.h_stride * sizeof(float));
     size_t o_cnt = carve(B * (size_t)s.h_stride * sizeof(int));
     size_t o_td = carve(B * (size_t)s.tiles_max * sizeof(int));
@@ -138,7 +139,6 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     size_t o_vote = carve(B * 8 * sizeof(int));
     size_t o_fs = carve(((size_t)max_points / 256 + 2) * sizeof(int));
     size_t o_ph = carve(B * 32 * sizeof(float));
-    size_t o_pp = carve(B * 4 * (size_t)max_points * sizeof(float));
     size_t o_ad = carve(4 * sizeof(int));
     const int refit_blocks = 64;
     size_t o_rc = carve(B * 9 * sizeof(float));
@@ -157,7 +157,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     s.corr_s = (float4*)(base + o_cs);
     s.corr_dup = (float4*)(base + o_dup);
     s.pt_scale = make_thr_scale(1e-6f).ik;     // the reference's threshold literal (sfm.cu:220) until told otherwise
-    s.px = (float*)(base + o_px);
+    s.px = nullptr;            // staging for pageable host input: allocated on first use (ensure_staging)
     s.Ecand = (float*)(base + o_ec);
     s.counts = (int*)(base + o_cnt);
     s.tile_done = (int*)(base + o_td);
@@ -172,7 +172,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     s.vote = (int*)(base + o_vote);
     h->filter_scratch = (int*)(base + o_fs);
     h->pack_header = (float*)(base + o_ph);
-    h->pack_points = (float*)(base + o_pp);
+    h->pack_points = nullptr;  // staging for host output: allocated on first use (ensure_staging)
     h->adapt = (int*)(base + o_ad);
     h->ba.persistent = 1;      // the bundle-adjustment scratch itself is allocated on first use (ensure_ba_arena)
     h->refit.cand = (float*)(base + o_rc);
@@ -213,6 +213,8 @@ int sfmb200_destroy(sfmb200_t* h) {
     cudaFree(h->arena);
     if (h->chain_arena) cudaFree(h->chain_arena);
     if (h->ba_arena) cudaFree(h->ba_arena);
+    if (h->staging_in) cudaFree(h->staging_in);
+    if (h->staging_out) cudaFree(h->staging_out);
     sfmb200_mg_close(h);
     delete h;
     return SFMB200_OK;
@@ -315,9 +317,24 @@ int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n) {
     h->have_points = true;
     return SFMB200_OK;
 }
+// Device staging for host buffers that the kernels cannot reach directly (pageable, or larger than the zero-copy
+// limit): allocated on first use, so device-resident workflows (run_device, the batched configs) never pay for it.
+static int ensure_staging(sfmb200_handle* h, bool in, bool out) {
+    if (in && !h->staging_in) {
+        CK(cudaMalloc(&h->staging_in, (size_t)h->s.B * h->s.n_stride * 4 * sizeof(float)));
+        h->s.px = (float*)h->staging_in;
+    }
+    if (out && !h->staging_out) {
+        CK(cudaMalloc(&h->staging_out, (size_t)h->s.B * 4 * (size_t)h->s.n_max * sizeof(float)));
+        h->pack_points = (float*)h->staging_out;
+    }
+    return SFMB200_OK;
+}
+
 int sfmb200_set_points_xy_host(sfmb200_t* h, const float* h_px, int n) {
     int rc = check_n(h, h_px, n);
     if (rc) return rc;
+    if ((rc = ensure_staging(h, true, false))) return rc;
     CK(cudaMemcpyAsync(h->s.px, h_px, (size_t)h->s.B * n * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     return sfmb200_set_points_xy(h, h->s.px, n);
 }
@@ -811,6 +828,7 @@ int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t see
     DeviceState& s = h->s;
     const size_t B = s.B;
     float* pts_alias = B * 4 * (size_t)s.n * sizeof(float) <= zero_copy_limit ? (float*)pinned_alias(h_points) : nullptr;
+    if (h_points && !pts_alias && (rc = ensure_staging(h, false, true))) return rc;
     dim3 grid(h_points ? (s.n + 255) / 256 : 1, (unsigned)B);
     // header: always through the handle's own pinned buffer (device-visible under UVA); points: straight into the
     // caller's buffer when it is pinned, else into the device staging copy followed by one DMA
