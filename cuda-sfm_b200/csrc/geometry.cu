@@ -51,6 +51,7 @@ __global__ void ingest_sift_kernel(DeviceState s, const float* __restrict__ sift
     normalise_store(s, 0, i, a.x, a.y, u2, v2, k);
 }
 __global__ void ingest_xy_kernel(DeviceState s, const float4* __restrict__ px, int n, Mat9 k) {
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int b = blockIdx.y;
     if (i >= n) return;
@@ -309,6 +310,8 @@ __global__ void choose_pose_compat_kernel(DeviceState s) {
 // are each a few microseconds of latency-bound work, so as separate launches the
 // gaps cost more than the math.  4 lanes per pair.
 __global__ void select_pose_choose_kernel(DeviceState s, int h_offset, int compat) {
+    pdl_wait();
+    pdl_trigger();
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     int b = g >> 2, c = g & 3;
     bool active = b < s.B;
@@ -346,7 +349,7 @@ __global__ void select_pose_choose_kernel(DeviceState s, int h_offset, int compa
 }
 void launch_select_pose_choose(const DeviceState& s, int h_offset, int compat, cudaStream_t st) {
     int threads = 4 * s.B;
-    select_pose_choose_kernel<<<(threads + 63) / 64, 64, 0, st>>>(s, h_offset, compat);
+    launch_dep(select_pose_choose_kernel, dim3((threads + 63) / 64), dim3(64), 0, st, s, h_offset, compat);
 }
 
 // compat = 0: every inlier of the selected E votes for the candidates that put it in front of both cameras.
@@ -419,6 +422,7 @@ void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_
 // inliers_only: points failing the Sampson test of the selected E get (0,0,0,1).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inliers_only, float thr) {
+    pdl_wait();
     const int b = blockIdx.y;
     __shared__ float sM[16];
     __shared__ float sE[9];
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inl
 }
 void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st) {
     dim3 grid((s.n + 255) / 256, s.B);
-    triangulate_kernel<<<grid, 256, 0, st>>>(s, inliers_only, thr);
+    launch_dep(triangulate_kernel, grid, dim3(256), 0, st, s, inliers_only, thr);
 }
 
 // ---------------------------------------------------------------------------

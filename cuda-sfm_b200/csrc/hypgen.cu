@@ -48,6 +48,8 @@ template <int THREADS, int MINB, int SYNC, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB)
 hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride, int H, int h_offset,
               unsigned long long seed, int keep_best) {
+    pdl_wait();
+    pdl_trigger();
     if (s.skip != nullptr && *s.skip != 0) return;      // adaptive termination reached in an earlier round
     const int b = blockIdx.y;
     const int j = blockIdx.x * THREADS + threadIdx.x;   // local hypothesis slot
@@ -82,7 +84,7 @@ void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pai
     if (solver == 0)
         hypgen_kernel<128, 2, 0, 0><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
     else if (solver == 1)
-        hypgen_kernel<128, SFMB200_HYPGEN_MINB, 0, 1><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
+        launch_dep(hypgen_kernel<128, SFMB200_HYPGEN_MINB, 0, 1>, grid, dim3(128), 0, st, s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
     else
         hypgen_kernel<128, 4, 0, 2><<<grid, 128, 0, st>>>(s, d_idx, idx_pair_stride, H, h_offset, seed, keep_best);
 }

@@ -140,6 +140,36 @@ void launch_export_ecand(const DeviceState& s, int pair, int H, float* d_out_Hx9
 void launch_export_X(const DeviceState& s, int pair, int image, float* d_out_3xN, cudaStream_t st);
 void launch_inlier_mask(const DeviceState& s, int pair, float thr, int model, unsigned char* d_mask, cudaStream_t st);
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may become resident while its
+// predecessor in the stream drains; it must execute pdl_wait() before touching anything the predecessor wrote
+// (the wait returns once the predecessor grid has completed and its writes are visible).  pdl_trigger() lets the
+// successor of THIS kernel start launching early.  Compiled in with -DSFMB200_PDL (A/B: profiles/r01_modes.md).
+#ifdef SFMB200_PDL
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+template <typename... KArgs, typename... Args>
+inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    kernel<<<grid, block, smem, st>>>(KArgs(args)...);
+}
+#endif
+
 // FP32 pipe micro-benchmark (bench/roofline denominator): returns lane-FMAs issued.
 double launch_fma_probe(int mode, int iters, cudaStream_t st, float* d_sink);
 

@@ -222,6 +222,8 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
     __shared__ unsigned long long red[THREADS / 32];
     __shared__ int s_last;
 
+    pdl_wait();
+    pdl_trigger();
     if (s.skip != nullptr && *s.skip != 0) return;      // adaptive termination reached in an earlier round
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -482,7 +484,7 @@ constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 template <int HPT, bool PACKED, int THREADS, int MINB>
 static void launch_one(const DeviceState& s, int ctas, int H, int h_offset, int T, long long units, int n_units, float thr,
                        cudaStream_t st) {
-    score_kernel<HPT, PACKED, THREADS, MINB, 0><<<ctas, THREADS, 0, st>>>(s, H, h_offset, T, units, n_units, thr);
+    launch_dep(score_kernel<HPT, PACKED, THREADS, MINB, 0>, dim3(ctas), dim3(THREADS), 0, st, s, H, h_offset, T, units, n_units, thr);
 }
 template <int HPT, bool PACKED, int THREADS, int MINB>
 static int occupancy_one() {
