@@ -202,6 +202,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
 int sfmb200_destroy(sfmb200_t* h) {
     if (!h) return SFMB200_OK;
     cudaStreamSynchronize(h->stream);
+    sfmb200_mg_close(h);          // unmaps the peers' exchange buffers; needs the stream, so before it goes
     if (h->own_stream) cudaStreamDestroy(h->stream);
     if (h->host_header) cudaFreeHost(h->host_header);
     if (h->prof_ev) {
@@ -215,7 +216,6 @@ int sfmb200_destroy(sfmb200_t* h) {
     if (h->ba_arena) cudaFree(h->ba_arena);
     if (h->staging_in) cudaFree(h->staging_in);
     if (h->staging_out) cudaFree(h->staging_out);
-    sfmb200_mg_close(h);
     delete h;
     return SFMB200_OK;
 }
