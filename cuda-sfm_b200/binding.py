@@ -47,6 +47,7 @@ SIGNATURES = {
     "sfmb200_mg_connect": (C.c_int, [_vp, _vp]),
     "sfmb200_estimate_e_mg": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, C.c_float]),
     "sfmb200_mg_status": (C.c_int, [_vp, _vp]),
+    "sfmb200_mg_set_timeout_ms": (C.c_int, [_vp, C.c_int]),
     "sfmb200_mg_close": (C.c_int, [_vp]),
     "sfmb200_chain_views": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sfmb200_bundle_adjust": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -83,6 +84,7 @@ SIGNATURES = {
     "sfmb200_host_solve_hypothesis_projector": (None, [_f, _f]),
     "sfmb200_host_null4": (None, [_f, _f]),
     "sfmb200_host_null4_fast": (C.c_int, [_f, _f]),
+    "sfmb200_host_dlt_null": (C.c_int, [_f, _f]),
     "sfmb200_host_inv4": (C.c_int, [_f, _f]),
     "sfmb200_host_sample_indices": (None, [C.c_uint64, C.c_uint64, C.c_int, _i]),
     # kernels.h facade wrappers (la_wrappers.cu)

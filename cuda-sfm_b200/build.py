@@ -29,6 +29,32 @@ def _newer(target: str, deps: list[str]) -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+def build_variant(name: str, defines: list[str], sources: list[str] | None = None) -> str:
+    """Experimental build with extra -D flags into tools/proto/explibs/<name>.so (A/B runs on the GPU box: tools/lib_ab.py,
+    tools/tri_ab.py).  Only `sources` (default: all) are recompiled with the flags; the rest reuse the product objects."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    build()
+    outdir = os.path.join(ROOT, "tools", "proto", "explibs")
+    objdir = os.path.join(HERE, "build", "exp_" + name)
+    os.makedirs(outdir, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        if sources is None or src in sources:
+            obj = os.path.join(objdir, src + ".o")
+            r = subprocess.run([nvcc, *NVCC_FLAGS, *defines, "-c", "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        else:
+            obj = os.path.join(HERE, "build", src + ".o")
+        objs.append(obj)
+    out = os.path.join(outdir, name + ".so")
+    r = subprocess.run([nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

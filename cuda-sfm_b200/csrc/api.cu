@@ -45,11 +45,14 @@ struct sfmb200_handle {
     void* mg_local;        // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
     bool mg_connected;
     long long mg_calls;
-    int* mg_status;        // device counter of timed-out waits
+    int* mg_failed_host;   // sticky failure word of the exchange (pinned, mapped): calls that timed out; != 0 poisons it
+    int* mg_failed_dev;    // device alias of the same word
+    int mg_clock_khz;
     long long mg_timeout_cycles;
     cudaStream_t stream;
     bool own_stream;
     int device;
+    int sms;               // SM count of the handle's device (cached at create)
     int compat;
     int score_variant;
     int tri_inliers_only;
@@ -89,6 +92,28 @@ static inline void prof_next(sfmb200_handle* h) {
     h->prof_mask[h->prof_cur] = 0;
 }
 
+// Every entry point runs with the handle's device current, whatever the caller's current device is (a process
+// that drives several GPUs keeps one handle per GPU), and restores the caller's device on return.
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(const sfmb200_handle* h) {
+        if (!h) return;
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != h->device) {
+            err = cudaSetDevice(h->device);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceScope() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define ENTER(h)                                                                                          \
+    DeviceScope scope_(h);                                                                                \
+    if (scope_.err != cudaSuccess) return fail(SFMB200_ERR_CUDA, "cannot make the handle's device current: %s", cudaGetErrorString(scope_.err))
+
 extern "C" {
 
 const char* sfmb200_last_error(void) { return g_err; }
@@ -109,6 +134,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     if (!h) return fail(SFMB200_ERR_ARG, "out of host memory%s");
     memset(h, 0, sizeof(*h));
     CK(cudaGetDevice(&h->device));
+    CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
     DeviceState& s = h->s;
     s.B = pairs;
     s.n_max = max_points;
@@ -200,6 +226,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
 }
 
 int sfmb200_destroy(sfmb200_t* h) {
+    ENTER(h);
     if (!h) return SFMB200_OK;
     cudaStreamSynchronize(h->stream);
     sfmb200_mg_close(h);          // unmaps the peers' exchange buffers; needs the stream, so before it goes
@@ -221,6 +248,7 @@ int sfmb200_destroy(sfmb200_t* h) {
 }
 
 int sfmb200_set_option(sfmb200_t* h, int option, int value) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     switch (option) {
         case SFMB200_OPT_COMPAT: h->compat = value ? 1 : 0; break;
@@ -252,6 +280,7 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
 }
 
 int sfmb200_set_stream(sfmb200_t* h, void* stream) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (h->own_stream) {
         cudaStreamSynchronize(h->stream);
@@ -263,6 +292,7 @@ int sfmb200_set_stream(sfmb200_t* h, void* stream) {
 }
 
 int sfmb200_synchronize(sfmb200_t* h) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     CK(cudaStreamSynchronize(h->stream));
     return SFMB200_OK;
@@ -275,6 +305,7 @@ static int check_n(sfmb200_t* h, const void* p, int n) {
 }
 
 int sfmb200_set_points_sift(sfmb200_t* h, const void* d_sift, int n) {
+    ENTER(h);
     int rc = check_n(h, d_sift, n);
     if (rc) return rc;
     if (h->s.B != 1) return fail(SFMB200_ERR_ARG, "SiftPoint ingest needs pairs == 1%s");
@@ -287,6 +318,7 @@ int sfmb200_set_points_sift(sfmb200_t* h, const void* d_sift, int n) {
 }
 int sfmb200_set_points_sift_filtered(sfmb200_t* h, const void* d_sift, int n, float min_score, float max_ambiguity,
                                      int32_t* d_kept_index, int32_t* h_kept) {
+    ENTER(h);
     int rc = check_n(h, d_sift, n);
     if (rc) return rc;
     if (h->s.B != 1) return fail(SFMB200_ERR_ARG, "SiftPoint ingest needs pairs == 1%s");
@@ -305,10 +337,14 @@ int sfmb200_set_points_sift_filtered(sfmb200_t* h, const void* d_sift, int n, fl
     h->have_points = true;
     return SFMB200_OK;
 }
-int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n) {
+// `scale` > 0: the ingest also commits a new threshold scale for the scaled copies (run_device / run_host pass the
+// scale of their threshold).  It is committed only once the arguments are validated, right before the launch that
+// writes corr_s / corr_dup with it - a failed call leaves pt_scale describing what the buffers really hold.
+static int ingest_xy(sfmb200_t* h, const float* d_px, int n, float scale) {
     int rc = check_n(h, d_px, n);
     if (rc) return rc;
     h->s.n = n;
+    if (scale > 0.0f) h->s.pt_scale = scale;
     prof_mark(h, 0);
     launch_ingest_xy(h->s, d_px, n, h->stream);
     prof_mark(h, 1);
@@ -316,6 +352,10 @@ int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n) {
     h->launches++;
     h->have_points = true;
     return SFMB200_OK;
+}
+int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n) {
+    ENTER(h);
+    return ingest_xy(h, d_px, n, 0.0f);
 }
 // Device staging for host buffers that the kernels cannot reach directly (pageable, or larger than the zero-copy
 // limit): allocated on first use, so device-resident workflows (run_device, the batched configs) never pay for it.
@@ -331,14 +371,19 @@ static int ensure_staging(sfmb200_handle* h, bool in, bool out) {
     return SFMB200_OK;
 }
 
-int sfmb200_set_points_xy_host(sfmb200_t* h, const float* h_px, int n) {
+static int ingest_xy_host(sfmb200_t* h, const float* h_px, int n, float scale) {
     int rc = check_n(h, h_px, n);
     if (rc) return rc;
     if ((rc = ensure_staging(h, true, false))) return rc;
     CK(cudaMemcpyAsync(h->s.px, h_px, (size_t)h->s.B * n * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    return sfmb200_set_points_xy(h, h->s.px, n);
+    return ingest_xy(h, h->s.px, n, scale);
+}
+int sfmb200_set_points_xy_host(sfmb200_t* h, const float* h_px, int n) {
+    ENTER(h);
+    return ingest_xy_host(h, h_px, n, 0.0f);
 }
 int sfmb200_set_points_normalised(sfmb200_t* h, const float* d_x, int n) {
+    ENTER(h);
     int rc = check_n(h, d_x, n);
     if (rc) return rc;
     h->s.n = n;
@@ -363,6 +408,7 @@ static int ensure_scaled(sfmb200_handle* h, float scale) {
 
 int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, int h_begin, int H, uint64_t seed,
                              float thr) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_points) return fail(SFMB200_ERR_STATE, "estimate_e before set_points%s");
     if (H < 1 || H > h->s.h_max || h_begin < 0 || (long long)h_begin + H > (long long)H_total)
@@ -372,7 +418,7 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     h->h_begin = h_begin;
     h->thr = thr;
     if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;
-    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
+    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant, h->sms);
     launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->hyp_solver, h->stream);
     prof_mark(h, 2);
     CKL();
@@ -391,16 +437,28 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
 }
 
 int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh, float* h_H, int32_t* h_matches) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_points) return fail(SFMB200_ERR_STATE, "find_homography before set_points%s");
     if (loops < 1 || loops > h->s.h_max) return fail(SFMB200_ERR_ARG, "loops out of range / above max_hypotheses%s");
     if (!(thresh > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
-    const float thr2 = thresh * thresh;
+    // `thresh` is in PIXELS like CudaSift's (matching.cu:953-996 runs on pixel coordinates), but the handle holds
+    // K^-1-normalised coordinates.  For a camera with square pixels and no skew a pixel distance is exactly f times
+    // a normalised one, so the test runs in normalised units with thresh / f and the result is mapped back with
+    // H_px = K H K^-1.  Any other K would make the pixel metric anisotropic in normalised units: refused.
+    const float* Kc = h->s.K;
+    const float f = Kc[0];
+    const bool isotropic = f > 0.0f && fabsf(Kc[4] - f) <= 1e-6f * f && Kc[1] == 0.0f && Kc[3] == 0.0f && Kc[6] == 0.0f &&
+                           Kc[7] == 0.0f && Kc[8] == 1.0f;
+    if (!isotropic)
+        return fail(SFMB200_ERR_ARG, "find_homography needs K = [f 0 cx; 0 f cy; 0 0 1] (square pixels, no skew): the pixel threshold is applied as thresh / f%s");
+    const float thresh_n = thresh / f;
+    const float thr2 = thresh_n * thresh_n;
     if (int rc = ensure_scaled(h, 1.0f)) return rc;      // the transfer-error test works on the unscaled coordinates
     h->H = loops;
     h->h_begin = 0;
     h->thr = thr2;
-    h->plan = make_score_plan_homography(h->s.B, h->s.n, loops);
+    h->plan = make_score_plan_homography(h->s.B, h->s.n, loops, h->sms);
     launch_hypgen(h->s, nullptr, (long long)loops * 8, loops, 0, seed, 2, h->stream);
     CKL();
     launch_score_homography(h->s, h->plan, loops, 0, thr2, h->stream);
@@ -416,18 +474,31 @@ int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh
     if (h_matches) CK(cudaMemcpyAsync(h_matches, h->s.best_count, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (h_H || h_matches) CK(cudaStreamSynchronize(h->stream));
     if (h_H) {
-        // CudaSift returns h8 = 1 (matching.cu:907-948 solves for 8 parameters); do the same when h8 is not ~0
+        // back to pixel coordinates, H_px = K H K^-1 (fp64 on the host: 2 x 27 multiply-adds per pair), then h8 = 1
+        // like CudaSift (matching.cu:907-948 solves for 8 parameters) when h8 is not ~0
         for (int b = 0; b < h->s.B; b++) {
             float* Hm = h_H + 9 * b;
-            if (fabsf(Hm[8]) > 1e-12f) {
-                float inv = 1.0f / Hm[8];
-                for (int i = 0; i < 9; i++) Hm[i] *= inv;
-            }
+            double T[9], R[9];
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) {
+                    double a = 0.0;
+                    for (int k = 0; k < 3; k++) a += (double)Hm[3 * i + k] * (double)h->s.Kinv[3 * k + j];
+                    T[3 * i + j] = a;
+                }
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) {
+                    double a = 0.0;
+                    for (int k = 0; k < 3; k++) a += (double)h->s.K[3 * i + k] * T[3 * k + j];
+                    R[3 * i + j] = a;
+                }
+            const double inv = fabs(R[8]) > 1e-12 ? 1.0 / R[8] : 1.0;
+            for (int i = 0; i < 9; i++) Hm[i] = (float)(R[i] * inv);
         }
     }
     return SFMB200_OK;
 }
 int sfmb200_estimate_e(sfmb200_t* h, const int32_t* d_idx, int H, uint64_t seed, float thr) {
+    ENTER(h);
     return sfmb200_estimate_e_slice(h, d_idx, H, 0, H, seed, thr);
 }
 
@@ -438,6 +509,7 @@ int sfmb200_estimate_e(sfmb200_t* h, const int32_t* d_idx, int H, uint64_t seed,
 // (counter-based sampler) or when d_idx rows are the same prefix.
 int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, int first_round, int growth,
                                 uint64_t seed, float thr, float confidence, int32_t* h_used) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_points) return fail(SFMB200_ERR_STATE, "estimate_e before set_points%s");
     if (H_max < 1 || first_round < 1 || growth < 2) return fail(SFMB200_ERR_ARG, "H_max >= 1, first_round >= 1, growth >= 2 required%s");
@@ -463,7 +535,7 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
     while (lo < H_max) {
         if (hi > H_max) hi = H_max;
         const int Hr = (int)(hi - lo);
-        h->plan = make_score_plan(s.B, s.n, Hr, h->score_variant);
+        h->plan = make_score_plan(s.B, s.n, Hr, h->score_variant, h->sms);
         launch_hypgen(s, d_idx, (long long)H_max * 8, Hr, (int)lo, seed, h->hyp_solver, h->stream, rounds > 0);
         CKL();
         launch_score(s, h->plan, Hr, (int)lo, thr, h->stream);
@@ -491,20 +563,32 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
 }
 
 // ---- multi-GPU, hypothesis-sharded, peer-memory exchange (mg.cu) ----
-int sfmb200_mg_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+// Opaque per-rank blob exchanged at set-up: the CUDA IPC handle of the exchange buffer + the UUID of the device
+// that owns it (so a peer can check that it reaches that device with native P2P atomics).
+struct MgBlob {
+    cudaIpcMemHandle_t ipc;
+    unsigned char uuid[16];
+};
+int sfmb200_mg_handle_bytes(void) { return (int)sizeof(MgBlob); }
 
 int sfmb200_mg_init(sfmb200_t* h, int rank, int world, void* h_handle_out) {
+    ENTER(h);
     if (!h || !h_handle_out) return fail(SFMB200_ERR_ARG, "null argument%s");
     if (world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world) return fail(SFMB200_ERR_ARG, "bad rank / world (at most 16 ranks)%s");
     if (h->mg_local) return fail(SFMB200_ERR_STATE, "mg_init called twice%s");
     const size_t bytes = mg_buffer_bytes(h->s.B, world);
     CK(cudaMalloc(&h->mg_local, bytes));
     CK(cudaMemset(h->mg_local, 0, bytes));
-    CK(cudaMalloc((void**)&h->mg_status, sizeof(int)));
-    CK(cudaMemset(h->mg_status, 0, sizeof(int)));
-    cudaIpcMemHandle_t ipc;
-    CK(cudaIpcGetMemHandle(&ipc, h->mg_local));
-    memcpy(h_handle_out, &ipc, sizeof(ipc));
+    CK(cudaHostAlloc((void**)&h->mg_failed_host, sizeof(int), cudaHostAllocMapped));
+    *h->mg_failed_host = 0;
+    CK(cudaHostGetDevicePointer((void**)&h->mg_failed_dev, h->mg_failed_host, 0));
+    MgBlob blob;
+    memset(&blob, 0, sizeof(blob));
+    CK(cudaIpcGetMemHandle(&blob.ipc, h->mg_local));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    memcpy(blob.uuid, prop.uuid.bytes, 16);
+    memcpy(h_handle_out, &blob, sizeof(blob));
     memset(&h->mg, 0, sizeof(h->mg));
     h->mg.rank = rank;
     h->mg.world = world;
@@ -513,19 +597,45 @@ int sfmb200_mg_init(sfmb200_t* h, int rank, int world, void* h_handle_out) {
     h->mg_calls = 0;
     int clock_khz = 0;
     cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);      // slow query: once, not per call
-    h->mg_timeout_cycles = 2000LL * (clock_khz > 0 ? clock_khz : 1900000);    // ~2 s of SM clock
+    h->mg_clock_khz = clock_khz > 0 ? clock_khz : 1900000;
+    h->mg_timeout_cycles = 2000LL * h->mg_clock_khz;                          // ~2 s of SM clock
+    return SFMB200_OK;
+}
+
+int sfmb200_mg_set_timeout_ms(sfmb200_t* h, int ms) {
+    ENTER(h);
+    if (!h || ms < 1) return fail(SFMB200_ERR_ARG, "timeout must be >= 1 ms%s");
+    if (!h->mg_local) return fail(SFMB200_ERR_STATE, "mg_set_timeout_ms before mg_init%s");
+    h->mg_timeout_cycles = (long long)ms * h->mg_clock_khz;
     return SFMB200_OK;
 }
 
 int sfmb200_mg_connect(sfmb200_t* h, const void* h_handles) {
+    ENTER(h);
     if (!h || !h_handles) return fail(SFMB200_ERR_ARG, "null argument%s");
     if (!h->mg_local) return fail(SFMB200_ERR_STATE, "mg_connect before mg_init%s");
     if (h->mg_connected) return fail(SFMB200_ERR_STATE, "mg_connect called twice%s");
-    const cudaIpcMemHandle_t* all = (const cudaIpcMemHandle_t*)h_handles;
+    const MgBlob* all = (const MgBlob*)h_handles;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
     for (int r = 0; r < h->mg.world; r++) {
         if (r == h->mg.rank) continue;
+        // the exchange relies on system-scope atomics over the peer mapping: they are only atomic when the two
+        // devices support NATIVE P2P atomics (NVLink); refuse PCIe-only peers instead of racing silently
+        int peer_dev = -1;
+        for (int d = 0; d < ndev && peer_dev < 0; d++) {
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, d));
+            if (memcmp(prop.uuid.bytes, all[r].uuid, 16) == 0) peer_dev = d;
+        }
+        if (peer_dev < 0) return fail(SFMB200_ERR_ARG, "mg_connect: a peer's device is not visible to this process%s");
+        if (peer_dev != h->device) {
+            int native = 0;
+            CK(cudaDeviceGetP2PAttribute(&native, cudaDevP2PAttrNativeAtomicSupported, h->device, peer_dev));
+            if (!native) return fail(SFMB200_ERR_STATE, "mg_connect: no native P2P atomics between this device and a peer (not NVLink-connected)%s");
+        }
         void* p = nullptr;
-        CK(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&p, all[r].ipc, cudaIpcMemLazyEnablePeerAccess));
         h->mg.base[r] = (unsigned long long*)p;
     }
     h->mg_connected = true;
@@ -533,15 +643,17 @@ int sfmb200_mg_connect(sfmb200_t* h, const void* h_handles) {
 }
 
 int sfmb200_mg_close(sfmb200_t* h) {
+    ENTER(h);
     if (!h) return SFMB200_OK;
     if (h->mg_local) {
         cudaStreamSynchronize(h->stream);
         for (int r = 0; r < h->mg.world; r++)
             if (r != h->mg.rank && h->mg.base[r]) cudaIpcCloseMemHandle(h->mg.base[r]);
         cudaFree(h->mg_local);
-        cudaFree(h->mg_status);
+        cudaFreeHost(h->mg_failed_host);
         h->mg_local = nullptr;
-        h->mg_status = nullptr;
+        h->mg_failed_host = nullptr;
+        h->mg_failed_dev = nullptr;
         h->mg_connected = false;
         memset(&h->mg, 0, sizeof(h->mg));
     }
@@ -549,17 +661,23 @@ int sfmb200_mg_close(sfmb200_t* h) {
 }
 
 // Every rank calls this with the same arguments on the same correspondences: scores its own slice of the
-// H_total hypotheses, exchanges the packed winners through peer memory and regenerates the global winner.
+// H_total hypotheses, exchanges the packed winners through peer memory and takes the global winner's E.
 int sfmb200_estimate_e_mg(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed, float thr) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->mg_connected) return fail(SFMB200_ERR_STATE, "estimate_e_mg before mg_init / mg_connect%s");
+    if (*(volatile int*)h->mg_failed_host != 0) {
+        h->have_E = false;
+        h->have_candidates = false;
+        return fail(SFMB200_ERR_STATE, "the peer exchange timed out earlier (a rank is lost or late): sfmb200_mg_close + mg_init + mg_connect on every rank%s");
+    }
     const int world = h->mg.world, rank = h->mg.rank;
     if (H_total < world) return fail(SFMB200_ERR_ARG, "fewer hypotheses than ranks%s");
     const long long base = H_total / world, rem = H_total % world;
     const long long lo = rank * base + (rank < rem ? rank : rem), cnt = base + (rank < rem ? 1 : 0);
     int rc = sfmb200_estimate_e_slice(h, d_idx, H_total, (int)lo, (int)cnt, seed, thr);
     if (rc) return rc;
-    launch_mg_exchange(h->s, h->mg, (int)(h->mg_calls & 1), H_total, h->mg_timeout_cycles, h->mg_status, h->stream);
+    launch_mg_exchange(h->s, h->mg, h->mg_calls, H_total, h->mg_timeout_cycles, h->mg_failed_dev, h->stream);
     CKL();
     h->mg_calls++;
     h->launches += 2;
@@ -567,32 +685,43 @@ int sfmb200_estimate_e_mg(sfmb200_t* h, const int32_t* d_idx, int H_total, uint6
     return SFMB200_OK;
 }
 
+// Calls of sfmb200_estimate_e_mg on this rank that timed out and produced no result (0 in a healthy job).  Any
+// value != 0 is final until the exchange is reconnected.  Synchronises the stream so that every call enqueued so
+// far is accounted for.
 int sfmb200_mg_status(sfmb200_t* h, int32_t* h_timeouts) {
+    ENTER(h);
     if (!h || !h_timeouts) return fail(SFMB200_ERR_ARG, "null argument%s");
     *h_timeouts = 0;
-    if (!h->mg_status) return SFMB200_OK;
-    CK(cudaMemcpyAsync(h_timeouts, h->mg_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->mg_failed_host) return SFMB200_OK;
     CK(cudaStreamSynchronize(h->stream));
+    *h_timeouts = *(volatile int*)h->mg_failed_host;
+    if (*h_timeouts != 0) h->have_E = false;
     return SFMB200_OK;
 }
 
 int sfmb200_best_buffer(sfmb200_t* h, uint64_t** d_best) {
+    ENTER(h);
     if (!h || !d_best) return fail(SFMB200_ERR_ARG, "null argument%s");
     *d_best = (uint64_t*)h->s.best;
     return SFMB200_OK;
 }
 int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_points) return fail(SFMB200_ERR_STATE, "adopt_best before set_points%s");
+    if (h->model != 0 || !(h->thr > 0.0f))
+        return fail(SFMB200_ERR_STATE, "adopt_best follows an essential-matrix estimate (estimate_e / estimate_e_slice) on this handle%s");
     launch_regen_best(h->s, d_idx, (long long)H_total * 8, seed, h->hyp_solver, h->stream);
     CKL();
     h->launches++;
     h->have_E = true;
     h->have_pose = false;
+    h->model = 0;          // s.E is an essential matrix scored at h->thr (set by the slice estimate that preceded)
     return SFMB200_OK;
 }
 
 int sfmb200_refine_e(sfmb200_t* h, int iterations) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (iterations < 0 || iterations > 64) return fail(SFMB200_ERR_ARG, "iterations must be in [0, 64]%s");
     if (!h->have_E || !h->have_points) return fail(SFMB200_ERR_STATE, "refine_e before an essential matrix exists%s");
@@ -647,6 +776,7 @@ static int ensure_ba_arena(sfmb200_handle* h) {
 // [pairs][8]): active points, cost at entry, cost at exit, accepted steps, lambda, gauge scale,
 // inliers of the refined E, spare - of the LAST round.
 int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float* h_stats) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (outer_rounds < 1 || outer_rounds > 64 || iterations < 1 || iterations > 256)
         return fail(SFMB200_ERR_ARG, "outer_rounds in [1, 64] and iterations in [1, 256] required%s");
@@ -667,6 +797,7 @@ int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float*
 
 // N-view chaining (chain.cu): pairs of the handle = consecutive view pairs over index-aligned tracks.
 int sfmb200_chain_views(sfmb200_t* h, float* d_cloud, int32_t* d_count, float* h_cameras, float* h_scales, int32_t* h_used) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (h->s.B > 256) return fail(SFMB200_ERR_ARG, "chain_views handles at most 256 pairs (257 views)%s");
     if (!h->have_points || !h->have_E || !h->have_pose || h->model != 0)
@@ -700,6 +831,7 @@ int sfmb200_chain_views(sfmb200_t* h, float* d_cloud, int32_t* d_count, float* h
 }
 
 int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_iters) {
+    ENTER(h);
     if (!h || !h_iters) return fail(SFMB200_ERR_ARG, "null argument%s");
     CK(cudaMemcpyAsync(h_iters, h->refit.iters_done, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -707,6 +839,7 @@ int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_iters) {
 }
 
 int sfmb200_pose_candidates(sfmb200_t* h) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_E) return fail(SFMB200_ERR_STATE, "pose_candidates before an essential matrix exists%s");
     launch_pose_candidates(h->s, h->compat, h->stream);
@@ -717,6 +850,7 @@ int sfmb200_pose_candidates(sfmb200_t* h) {
     return SFMB200_OK;
 }
 int sfmb200_choose_pose(sfmb200_t* h) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_pose || !h->have_points) return fail(SFMB200_ERR_STATE, "choose_pose before pose_candidates%s");
     launch_choose_pose(h->s, h->compat, h->thr > 0 ? h->thr : 1e-6f, h->stream);
@@ -726,6 +860,7 @@ int sfmb200_choose_pose(sfmb200_t* h) {
     return SFMB200_OK;
 }
 int sfmb200_triangulate(sfmb200_t* h) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!h->have_pose || !h->have_points) return fail(SFMB200_ERR_STATE, "triangulate before pose_candidates%s");
     launch_triangulate(h->s, h->tri_inliers_only, h->thr > 0 ? h->thr : 1e-6f, h->stream);
@@ -746,7 +881,7 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
     h->h_begin = 0;
     h->thr = thr;
     if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;     // no-op after run_device / run_host's own ingest
-    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant);
+    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant, h->sms);
     launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->hyp_solver, h->stream);
     prof_mark(h, 2);
     CKL();
@@ -769,9 +904,11 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
 }
 
 int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t seed, float thr) {
-    if (h) prof_next(h);
-    if (h && thr > 0.0f) h->s.pt_scale = make_thr_scale(thr).ik;      // the ingest below writes the scaled copies for this threshold
-    int rc = sfmb200_set_points_xy(h, d_px, n);
+    ENTER(h);
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!(thr > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
+    prof_next(h);
+    int rc = ingest_xy(h, d_px, n, make_thr_scale(thr).ik);          // writes the scaled copies for this threshold
     if (rc) return rc;
     return run_stages(h, H, seed, thr);
 }
@@ -815,14 +952,17 @@ static void* pinned_alias(const void* host) {
 
 int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t seed, float thr, float* h_E, float* h_P,
                      int32_t* h_pose_index, int32_t* h_inliers, float* h_points) {
-    if (h) prof_next(h);
-    if (h && thr > 0.0f) h->s.pt_scale = make_thr_scale(thr).ik;
+    ENTER(h);
+    if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
+    if (!(thr > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
+    prof_next(h);
+    const float scale = make_thr_scale(thr).ik;
     // zero copy pays where latency dominates (config-2-sized calls: 160 KB each way); bulk transfers (batched
     // config 4: hundreds of MB) stay with the copy engines, which keep more PCIe requests in flight than a kernel
     const size_t zero_copy_limit = 4u << 20;
-    const size_t in_bytes = h ? (size_t)h->s.B * (size_t)(n > 0 ? n : 0) * 4 * sizeof(float) : 0;
+    const size_t in_bytes = (size_t)h->s.B * (size_t)(n > 0 ? n : 0) * 4 * sizeof(float);
     const float* px_alias = in_bytes <= zero_copy_limit ? (const float*)pinned_alias(h_px) : nullptr;
-    int rc = px_alias ? sfmb200_set_points_xy(h, px_alias, n) : sfmb200_set_points_xy_host(h, h_px, n);
+    int rc = px_alias ? ingest_xy(h, px_alias, n, scale) : ingest_xy_host(h, h_px, n, scale);
     if (rc) return rc;
     if ((rc = run_stages(h, H, seed, thr))) return rc;
     DeviceState& s = h->s;
@@ -849,6 +989,7 @@ int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t see
 }
 
 int sfmb200_copy_to_vbo(sfmb200_t* h, int pair, float* d_pos, float* d_col) {
+    ENTER(h);
     if (!h || pair < 0 || pair >= h->s.B) return fail(SFMB200_ERR_ARG, "bad handle / pair%s");
     launch_vbo(h->s, pair, d_pos, d_col, 1.0f, h->stream);
     CKL();
@@ -858,6 +999,7 @@ int sfmb200_copy_to_vbo(sfmb200_t* h, int pair, float* d_pos, float* d_col) {
 }
 
 int sfmb200_copy_to_vbo_coloured(sfmb200_t* h, int pair, float* d_pos, float* d_col, float scale, int mode, float z_near, float z_far) {
+    ENTER(h);
     if (!h || pair < 0 || pair >= h->s.B) return fail(SFMB200_ERR_ARG, "bad handle / pair%s");
     if (mode < 0 || mode > 2) return fail(SFMB200_ERR_ARG, "colour mode must be 0 (ones), 1 (inlier / outlier) or 2 (depth ramp)%s");
     if (mode == 1 && (!h->have_E || h->model != 0)) return fail(SFMB200_ERR_STATE, "inlier colouring needs an essential matrix%s");
@@ -869,12 +1011,14 @@ int sfmb200_copy_to_vbo_coloured(sfmb200_t* h, int pair, float* d_pos, float* d_
 }
 
 int sfmb200_get_E(sfmb200_t* h, float* h_E) {
+    ENTER(h);
     if (!h || !h_E) return fail(SFMB200_ERR_ARG, "null argument%s");
     CK(cudaMemcpyAsync(h_E, h->s.E, (size_t)h->s.B * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return SFMB200_OK;
 }
 int sfmb200_set_E(sfmb200_t* h, const float* h_E) {
+    ENTER(h);
     if (!h || !h_E) return fail(SFMB200_ERR_ARG, "null argument%s");
     CK(cudaMemcpyAsync(h->s.E, h_E, (size_t)h->s.B * 9 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -885,6 +1029,7 @@ int sfmb200_set_E(sfmb200_t* h, const float* h_E) {
     return SFMB200_OK;
 }
 int sfmb200_get_best(sfmb200_t* h, int32_t* h_index, int32_t* h_count) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null argument%s");
     if (h_index) CK(cudaMemcpyAsync(h_index, h->s.best_idx, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (h_count) CK(cudaMemcpyAsync(h_count, h->s.best_count, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -892,12 +1037,14 @@ int sfmb200_get_best(sfmb200_t* h, int32_t* h_index, int32_t* h_count) {
     return SFMB200_OK;
 }
 int sfmb200_get_poses(sfmb200_t* h, float* h_P) {
+    ENTER(h);
     if (!h || !h_P) return fail(SFMB200_ERR_ARG, "null argument%s");
     CK(cudaMemcpyAsync(h_P, h->s.P, (size_t)h->s.B * 64 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return SFMB200_OK;
 }
 int sfmb200_get_pose_index(sfmb200_t* h, int32_t* h_ind) {
+    ENTER(h);
     if (!h || !h_ind) return fail(SFMB200_ERR_ARG, "null argument%s");
     CK(cudaMemcpyAsync(h_ind, h->s.P_ind, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -909,6 +1056,7 @@ static int check_pair(sfmb200_t* h, int pair, const void* p) {
     return SFMB200_OK;
 }
 int sfmb200_get_points(sfmb200_t* h, int pair, float* d_points) {
+    ENTER(h);
     int rc = check_pair(h, pair, d_points);
     if (rc) return rc;
     const DeviceState& s = h->s;
@@ -918,6 +1066,7 @@ int sfmb200_get_points(sfmb200_t* h, int pair, float* d_points) {
     return SFMB200_OK;
 }
 int sfmb200_get_points_host(sfmb200_t* h, int pair, float* h_points) {
+    ENTER(h);
     int rc = check_pair(h, pair, h_points);
     if (rc) return rc;
     const DeviceState& s = h->s;
@@ -928,6 +1077,7 @@ int sfmb200_get_points_host(sfmb200_t* h, int pair, float* h_points) {
     return SFMB200_OK;
 }
 int sfmb200_get_inlier_counts(sfmb200_t* h, int pair, int32_t* d_counts) {
+    ENTER(h);
     int rc = check_pair(h, pair, d_counts);
     if (rc) return rc;
     if (!h->have_candidates) return fail(SFMB200_ERR_STATE, "no estimate yet%s");
@@ -936,6 +1086,7 @@ int sfmb200_get_inlier_counts(sfmb200_t* h, int pair, int32_t* d_counts) {
     return SFMB200_OK;
 }
 int sfmb200_get_E_candidates(sfmb200_t* h, int pair, float* d_E) {
+    ENTER(h);
     int rc = check_pair(h, pair, d_E);
     if (rc) return rc;
     if (!h->have_candidates) return fail(SFMB200_ERR_STATE, "no estimate yet%s");
@@ -945,6 +1096,7 @@ int sfmb200_get_E_candidates(sfmb200_t* h, int pair, float* d_E) {
     return SFMB200_OK;
 }
 int sfmb200_get_X(sfmb200_t* h, int pair, int image, float* d_X) {
+    ENTER(h);
     int rc = check_pair(h, pair, d_X);
     if (rc) return rc;
     if (image < 0 || image > 1) return fail(SFMB200_ERR_ARG, "image must be 0 or 1%s");
@@ -955,6 +1107,7 @@ int sfmb200_get_X(sfmb200_t* h, int pair, int image, float* d_X) {
     return SFMB200_OK;
 }
 int sfmb200_get_inlier_mask(sfmb200_t* h, int pair, uint8_t* d_mask) {
+    ENTER(h);
     int rc = check_pair(h, pair, d_mask);
     if (rc) return rc;
     if (!(h->have_E || h->model == 1) || !h->have_points) return fail(SFMB200_ERR_STATE, "no model yet%s");
@@ -965,6 +1118,7 @@ int sfmb200_get_inlier_mask(sfmb200_t* h, int pair, uint8_t* d_mask) {
 }
 int sfmb200_device_views(sfmb200_t* h, float** d_E, float** d_P, int32_t** d_pose_index, float** d_points,
                          int* point_stride) {
+    ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (d_E) *d_E = h->s.E;
     if (d_P) *d_P = h->s.P;
@@ -974,6 +1128,7 @@ int sfmb200_device_views(sfmb200_t* h, float** d_E, float** d_P, int32_t** d_pos
     return SFMB200_OK;
 }
 int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]) {
+    ENTER(h);
     if (!h || !out) return fail(SFMB200_ERR_ARG, "null argument%s");
     out[0] = h->plan.variant;
     out[1] = h->plan.tiles;
@@ -984,6 +1139,7 @@ int sfmb200_score_plan(sfmb200_t* h, int32_t out[4]) {
 int64_t sfmb200_launch_count(sfmb200_t* h) { return h ? h->launches : 0; }
 
 int sfmb200_stage_times(sfmb200_t* h, int max_sets, float* ms, int* sets) {
+    ENTER(h);
     if (!h || !ms || !sets) return fail(SFMB200_ERR_ARG, "null argument%s");
     *sets = 0;
     if (!h->prof_ev) return fail(SFMB200_ERR_STATE, "profiling was never enabled%s");

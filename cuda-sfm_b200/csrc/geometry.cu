@@ -258,7 +258,11 @@ __device__ __forceinline__ void dlt_matrix(float x1, float y1, float x2, float y
 // De-homogenise like normalize_pt_kernal (kernels.h:433-450): w == 0 -> origin.
 __device__ __forceinline__ void dehomogenise(const float* v, float& X, float& Y, float& Z) {
     if (v[3] == 0.0f) { X = 0.0f; Y = 0.0f; Z = 0.0f; return; }
+#if defined(__CUDA_ARCH__)
+    float iw = __fdividef(1.0f, v[3]);      // MUFU.RCP: 1 ulp, |v| = 1
+#else
     float iw = 1.0f / v[3];
+#endif
     X = v[0] * iw; Y = v[1] * iw; Z = v[2] * iw;
 }
 
@@ -276,7 +280,7 @@ __device__ __forceinline__ void dehomogenise(const float* v, float& X, float& Y,
 __device__ __forceinline__ bool cheirality_compat(const float4& c0, const float* M, float* Minv) {
     float A[16], v[4];
     dlt_matrix(c0.x, c0.y, c0.z, c0.w, M, A);
-    if (!null4_inverse_iteration<5>(A, v)) null4<5>(A, v);     // same solve as triangulate_kernel
+    if (!dlt_null_adjugate1(A, v)) null4<5>(A, v);     // same solve as triangulate_kernel
     float X, Y, Z;
     dehomogenise(v, X, Y, Z);
     inv4(M, Minv);
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, fl
         for (int c = 0; c < 4; c++) {
             float A[16], v[4];
             dlt_matrix(p.x, p.y, p.z, p.w, sP + 16 * c, A);
-            if (!null4_inverse_iteration<5>(A, v)) null4<5>(A, v);
+            if (!dlt_null_adjugate1(A, v)) null4<5>(A, v);
             float X, Y, Z;
             dehomogenise(v, X, Y, Z);
             const float* M = sP + 16 * c;
@@ -415,48 +419,84 @@ void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_
 }
 
 // ---------------------------------------------------------------------------
-// Linear triangulation (sfm.cu:309-344): one thread per correspondence, 4x4 DLT
-// null vector in registers (replaces the batched 4x4 cusolver gesvdj that writes
-// U, S and V for every point), de-homogenised into the reference's 4xN SoA.
-// HBM roofline: 16 B read + 16 B written per point.
-// inliers_only: points failing the Sampson test of the selected E get (0,0,0,1).
+// Linear triangulation (sfm.cu:309-344): 4x4 DLT null vector per correspondence in registers (replaces the
+// batched 4x4 cusolver gesvdj that writes U, S and V for every point), de-homogenised into the reference's
+// 4xN SoA.  HBM roofline: 16 B read + 16 B written per point.
+// One thread solves PTS points that lie THREADS apart (every load / store is warp-coalesced); the null vector
+// comes from the adjugate power iteration dlt_null_adjugate (smallmat.cuh), which exploits camera 1 = I4; the
+// pose and E are read through uniform __ldg (one L1 line for the whole CTA), so there is no shared memory and
+// no barrier.  inliers_only: points failing the Sampson test of the selected E get (0,0,0,1).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) triangulate_kernel(DeviceState s, int inliers_only, float thr) {
+#ifndef SFMB200_TRI_PTS
+#define SFMB200_TRI_PTS 2
+#endif
+#ifndef SFMB200_TRI_THREADS
+#define SFMB200_TRI_THREADS 128
+#endif
+constexpr int TRI_THREADS = SFMB200_TRI_THREADS;
+template <int PTS, bool INLIERS_ONLY>
+__global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(DeviceState s, float thr) {
     pdl_wait();
     const int b = blockIdx.y;
-    __shared__ float sM[16];
-    __shared__ float sE[9];
-    if (threadIdx.x < 16) sM[threadIdx.x] = s.P[(size_t)b * 64 + 16 * s.P_ind[b] + threadIdx.x];
-    if (threadIdx.x < 9) sE[threadIdx.x] = s.E[(size_t)b * 9 + threadIdx.x];
-    __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool inside = i < s.n;
-    float4 p = inside ? __ldg(s.corr + (size_t)b * s.n_stride + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float X = 0.0f, Y = 0.0f, Z = 0.0f;
-    const bool keep = inside && (!inliers_only || sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f);
-    {
-        // every lane makes the call (the adaptive iteration votes across the warp); lanes without a point are not live.
-        // Inverse iteration: cross-product start, up to 5 solves on one Cholesky factor, the warp stops once every live
-        // lane has converged (2 solves for inliers); Jacobi only for the rare point whose two smallest singular values
-        // nearly coincide.
-        float A[16], v[4];
-        dlt_matrix(p.x, p.y, p.z, p.w, sM, A);
-        const bool ok = null4_inverse_iteration<5, true>(A, v, keep);
-        if (keep) {
-            if (!ok) null4<5>(A, v);
-            dehomogenise(v, X, Y, Z);
+    const float* Mg = s.P + (size_t)b * 64 + 16 * __ldg(s.P_ind + b);
+    float M[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) M[k] = __ldg(Mg + k);
+    const int base = blockIdx.x * (TRI_THREADS * PTS) + threadIdx.x;
+    const float4* corr = s.corr + (size_t)b * s.n_stride;
+    float x1[PTS], y1[PTS], a[PTS][4], bb[PTS][4], v[PTS][4];
+    bool keep[PTS], ok[PTS];
+    float4 pt[PTS];
+#pragma unroll
+    for (int p = 0; p < PTS; p++) {
+        const int i = base + p * TRI_THREADS;
+        pt[p] = i < s.n ? __ldg(corr + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+#pragma unroll
+    for (int p = 0; p < PTS; p++) {
+        const int i = base + p * TRI_THREADS;
+        keep[p] = i < s.n;
+        if constexpr (INLIERS_ONLY) {
+            float e[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) e[k] = __ldg(s.E + (size_t)b * 9 + k);
+            keep[p] = keep[p] && sampson_d(e, pt[p].x, pt[p].y, pt[p].z, pt[p].w, -thr) < 0.0f;
+        }
+        x1[p] = pt[p].x; y1[p] = pt[p].y;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            a[p][c] = fmaf(pt[p].z, M[8 + c], -M[c]);           // compute_linear_triangulation_A, kernels.h:387-431
+            bb[p][c] = fmaf(pt[p].w, M[8 + c], -M[4 + c]);
         }
     }
-    if (!inside) return;
+    // every lane makes the call (the iteration votes across the warp to leave early); idle points are not live
+    dlt_null_adjugate<PTS>(x1, y1, a, bb, v, keep, ok);
     float* out = s.points + (size_t)b * 4 * s.n_stride;
-    out[i] = X;
-    out[(size_t)s.n_stride + i] = Y;
-    out[(size_t)2 * s.n_stride + i] = Z;
-    out[(size_t)3 * s.n_stride + i] = 1.0f;
+#pragma unroll
+    for (int p = 0; p < PTS; p++) {
+        const int i = base + p * TRI_THREADS;
+        if (i >= s.n) continue;
+        float X = 0.0f, Y = 0.0f, Z = 0.0f;
+        if (keep[p]) {
+            if (!ok[p]) {                                        // the two smallest singular values nearly coincide: Jacobi
+                float A[16];
+                dlt_matrix(pt[p].x, pt[p].y, pt[p].z, pt[p].w, M, A);
+                null4<5>(A, v[p]);
+            }
+            dehomogenise(v[p], X, Y, Z);
+        }
+        out[i] = X;
+        out[(size_t)s.n_stride + i] = Y;
+        out[(size_t)2 * s.n_stride + i] = Z;
+        out[(size_t)3 * s.n_stride + i] = 1.0f;
+    }
 }
 void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st) {
-    dim3 grid((s.n + 255) / 256, s.B);
-    launch_dep(triangulate_kernel, grid, dim3(256), 0, st, s, inliers_only, thr);
+    dim3 grid((s.n + TRI_THREADS * SFMB200_TRI_PTS - 1) / (TRI_THREADS * SFMB200_TRI_PTS), s.B);
+    if (inliers_only)
+        launch_dep(triangulate_kernel<SFMB200_TRI_PTS, true>, grid, dim3(TRI_THREADS), 0, st, s, thr);
+    else
+        launch_dep(triangulate_kernel<SFMB200_TRI_PTS, false>, grid, dim3(TRI_THREADS), 0, st, s, thr);
 }
 
 // ---------------------------------------------------------------------------

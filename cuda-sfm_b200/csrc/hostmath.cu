@@ -27,6 +27,8 @@ void sfmb200_host_null4(const float A[16], float x[4]) { null4<5>(A, x); }
 
 int sfmb200_host_null4_fast(const float A[16], float x[4]) { return null4_inverse_iteration<5>(A, x) ? 0 : 1; }
 
+int sfmb200_host_dlt_null(const float A[16], float x[4]) { return dlt_null_adjugate1(A, x) ? 0 : 1; }
+
 int sfmb200_host_inv4(const float m[16], float out[16]) { return inv4(m, out) ? 0 : -1; }
 
 void sfmb200_host_sample_indices(uint64_t seed, uint64_t h, int n, int32_t idx[8]) {

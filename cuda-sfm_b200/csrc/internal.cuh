@@ -85,14 +85,14 @@ struct BAState {
     int max_blocks;
 };
 // Peer exchange buffers of the hypothesis-sharded multi-GPU estimate (mg.cu): base[r] = rank r's buffer
-// (keys[2][B] uint64, arrive[2] uint32, E[2][world][B][9] float), mapped into this process through CUDA IPC.
+// (keys[2][B] uint64, arrive uint64 (monotone), E[2][world][B][9] float), mapped into this process through CUDA IPC.
 constexpr int MG_MAX_WORLD = 16;
 struct MgPeers {
     unsigned long long* base[MG_MAX_WORLD];
     int rank, world;
 };
-void launch_mg_exchange(const DeviceState& s, const MgPeers& peers, int parity, int H_total, long long timeout_cycles,
-                        int* d_status, cudaStream_t st);
+void launch_mg_exchange(const DeviceState& s, const MgPeers& peers, long long call, int H_total, long long timeout_cycles,
+                        int* d_failed, cudaStream_t st);
 size_t mg_buffer_bytes(int B, int world);
 
 // Scratch and results of the N-view chaining stage (chain.cu); allocated on first use.
@@ -121,11 +121,11 @@ void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pai
                    unsigned long long seed, int solver, cudaStream_t st, int keep_best = 0);
 void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int round_begin, int done_after, double log1mp, int last,
                             cudaStream_t st);
-ScorePlan make_score_plan(int B, int n, int H, int variant_override);
+ScorePlan make_score_plan(int B, int n, int H, int variant_override, int sms);
 int score_num_variants();
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
 void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st);
-ScorePlan make_score_plan_homography(int B, int n, int H);
+ScorePlan make_score_plan_homography(int B, int n, int H, int sms);
 void launch_select(const DeviceState& s, int h_offset, cudaStream_t st);
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride,
                        unsigned long long seed, int solver, cudaStream_t st);

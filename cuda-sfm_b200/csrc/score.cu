@@ -523,7 +523,7 @@ static int variant_occupancy(int v) {
 
 int score_num_variants() { return kNumVariants; }
 
-ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
+ScorePlan make_score_plan(int B, int n, int H, int variant_override, int sms) {
     ScorePlan p;
     if (variant_override >= 0 && variant_override < kNumVariants) {
         p.variant = variant_override;
@@ -538,11 +538,7 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
     p.hyp_per_cta = v.hpt * v.threads;
     p.tiles = (H + p.hyp_per_cta - 1) / p.hyp_per_cta;
     if (p.tiles < 1) p.tiles = 1;
-    int sms = 148;
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    if (sms < 1) sms = 148;          // the handle caches the SM count of ITS device at create (api.cu)
     p.n_units = (n + SCORE_GRAIN - 1) / SCORE_GRAIN;
     p.total_units = (long long)B * p.tiles * p.n_units;
     long long ctas = (long long)sms * variant_occupancy(p.variant);   // persistent: all CTAs co-resident
@@ -554,8 +550,8 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override) {
 
 // Homography model: the same kernel with the transfer-error test; three tile sizes are enough
 // (thr here is the SQUARED pixel / coordinate threshold).
-ScorePlan make_score_plan_homography(int B, int n, int H) {
-    return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9));     // tiles of 2048 / 512 / 256 hypotheses
+ScorePlan make_score_plan_homography(int B, int n, int H, int sms) {
+    return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9), sms);     // tiles of 2048 / 512 / 256 hypotheses
 }
 void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st) {
     const int v = plan.variant;

@@ -20,18 +20,31 @@ def _torch():
     return torch
 
 
-def _dptr(t) -> C.c_void_p:
-    """Device pointer of a torch CUDA tensor (or a raw int address)."""
+def _dptr(t, dtype: str | None = None, min_elems: int = 0) -> C.c_void_p:
+    """Device pointer of a torch CUDA tensor (or a raw int address, taken on trust).  dtype ("float32", "int32",
+    "uint8") and min_elems, when given, are checked: the C ABI reads / writes raw memory of that type and size."""
     if t is None:
         return C.c_void_p(0)
     if isinstance(t, int):
         return C.c_void_p(t)
-    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    if not (t.is_cuda and t.is_contiguous()):
+        raise ValueError("expected a contiguous CUDA tensor")
+    if dtype is not None and str(t.dtype) != "torch." + dtype:
+        raise TypeError(f"expected a {dtype} tensor, got {t.dtype}")
+    if t.numel() < min_elems:
+        raise ValueError(f"tensor too small: {t.numel()} elements, need {min_elems}")
     return C.c_void_p(t.data_ptr())
 
 
-def _hptr(a: np.ndarray) -> C.c_void_p:
-    assert a.flags["C_CONTIGUOUS"]
+def _hptr(a: np.ndarray, dtype=None, shape: tuple | None = None) -> C.c_void_p:
+    """Host pointer of a C-contiguous numpy array; dtype / exact shape are checked when given (the C ABI writes
+    raw float32 / int32 of a fixed size through it)."""
+    if not isinstance(a, np.ndarray) or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("expected a C-contiguous numpy array")
+    if dtype is not None and a.dtype != np.dtype(dtype):
+        raise TypeError(f"expected a {np.dtype(dtype)} array, got {a.dtype}")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
     return C.c_void_p(a.ctypes.data)
 
 
@@ -93,7 +106,7 @@ class BatchedPairs:
 
     def set_points_xy(self, d_px, n: int | None = None):
         n = n if n is not None else d_px.shape[-2]
-        self.lib.call("sfmb200_set_points_xy", self._h, _dptr(d_px), n)
+        self.lib.call("sfmb200_set_points_xy", self._h, _dptr(d_px, "float32", self.pairs * n * 4), n)
         self.n = n
 
     def set_points_xy_host(self, h_px: np.ndarray):
@@ -105,15 +118,16 @@ class BatchedPairs:
 
     def set_points_normalised(self, d_x, n: int | None = None):
         n = n if n is not None else d_x.shape[-2]
-        self.lib.call("sfmb200_set_points_normalised", self._h, _dptr(d_x), n)
+        self.lib.call("sfmb200_set_points_normalised", self._h, _dptr(d_x, "float32", self.pairs * n * 4), n)
         self.n = n
 
     # ---- stages ----
     def estimate_e(self, H: int, seed: int = 0, thr: float = 1e-6, d_idx=None, H_total: int | None = None, h_begin: int = 0):
+        idx = _dptr(d_idx, "int32", self.pairs * (H_total or H) * 8)
         if H_total is None:
-            self.lib.call("sfmb200_estimate_e", self._h, _dptr(d_idx), H, C.c_uint64(seed), C.c_float(thr))
+            self.lib.call("sfmb200_estimate_e", self._h, idx, H, C.c_uint64(seed), C.c_float(thr))
         else:
-            self.lib.call("sfmb200_estimate_e_slice", self._h, _dptr(d_idx), H_total, h_begin, H, C.c_uint64(seed), C.c_float(thr))
+            self.lib.call("sfmb200_estimate_e_slice", self._h, idx, H_total, h_begin, H, C.c_uint64(seed), C.c_float(thr))
         self.H = H
 
     def estimate_e_adaptive(self, H_max: int, seed: int = 0, thr: float = 1e-6, confidence: float = 0.99,
@@ -136,7 +150,8 @@ class BatchedPairs:
         self.lib.call("sfmb200_adopt_best", self._h, _dptr(d_idx), H_total, C.c_uint64(seed))
 
     def find_homography(self, loops: int, seed: int = 0, thresh: float = 5.0):
-        """CudaSift FindHomography semantics on this handle's correspondences; returns (H [pairs,3,3], matches [pairs])."""
+        """CudaSift FindHomography semantics on this handle's correspondences: `thresh` in PIXELS, H maps image-1 pixels
+        to image-2 pixels (needs K = [f 0 cx; 0 f cy; 0 0 1]); returns (H [pairs,3,3], matches [pairs])."""
         Hm = np.empty((self.pairs, 3, 3), np.float32)
         cnt = np.empty(self.pairs, np.int32)
         self.lib.call("sfmb200_find_homography", self._h, loops, C.c_uint64(seed), C.c_float(thresh), _hptr(Hm), _hptr(cnt))
@@ -181,23 +196,30 @@ class BatchedPairs:
 
     def run_device(self, d_px, H: int, seed: int = 0, thr: float = 1e-6, n: int | None = None):
         n = n if n is not None else d_px.shape[-2]
-        self.lib.call("sfmb200_run_device", self._h, _dptr(d_px), n, H, C.c_uint64(seed), C.c_float(thr))
+        self.lib.call("sfmb200_run_device", self._h, _dptr(d_px, "float32", self.pairs * n * 4), n, H, C.c_uint64(seed), C.c_float(thr))
         self.n, self.H = n, H
+
+    def _host_io(self, h_px: np.ndarray, want_points: bool, out: dict | None):
+        """Validated host buffers of the e2e call: h_px float32 [pairs][n][4] (coerced like set_points_xy_host unless it
+        already is - a pinned buffer is passed through untouched), out[...] float32 / int32 of the exact shapes."""
+        if not (isinstance(h_px, np.ndarray) and h_px.dtype == np.float32 and h_px.flags["C_CONTIGUOUS"]):
+            h_px = np.ascontiguousarray(h_px, dtype=np.float32)
+        if h_px.shape[-1] != 4 or h_px.size % 4 or h_px.size // 4 % self.pairs:
+            raise ValueError(f"h_px must be [pairs={self.pairs}][n][4], got {h_px.shape}")
+        n = h_px.size // 4 // self.pairs
+        B = self.pairs
+        if out is None:
+            out = {"E": np.empty((B, 9), np.float32), "P": np.empty((B, 16), np.float32), "pose_index": np.empty(B, np.int32),
+                   "inliers": np.empty(B, np.int32), "points": np.empty((B, 4, n), np.float32) if want_points else None}
+        pts = out.get("points")
+        ptrs = (_hptr(out["E"], np.float32, (B, 9)), _hptr(out["P"], np.float32, (B, 16)), _hptr(out["pose_index"], np.int32, (B,)),
+                _hptr(out["inliers"], np.int32, (B,)), _hptr(pts, np.float32, (B, 4, n)) if pts is not None else C.c_void_p(0))
+        return h_px, n, out, ptrs
 
     def run_host(self, h_px: np.ndarray, H: int, seed: int = 0, thr: float = 1e-6, want_points: bool = True, out: dict | None = None):
         """Whole path from host pixel correspondences to host results (the e2e call)."""
-        n = h_px.shape[-2]
-        B = self.pairs
-        if out is None:
-            out = {
-                "E": np.empty((B, 9), np.float32), "P": np.empty((B, 16), np.float32),
-                "pose_index": np.empty(B, np.int32), "inliers": np.empty(B, np.int32),
-                "points": np.empty((B, 4, n), np.float32) if want_points else None,
-            }
-        pts = out.get("points")
-        self.lib.call("sfmb200_run_host", self._h, _hptr(h_px), n, H, C.c_uint64(seed), C.c_float(thr), _hptr(out["E"]),
-                      _hptr(out["P"]), _hptr(out["pose_index"]), _hptr(out["inliers"]),
-                      _hptr(pts) if pts is not None else C.c_void_p(0))
+        h_px, n, out, ptrs = self._host_io(h_px, want_points, out)
+        self.lib.call("sfmb200_run_host", self._h, _hptr(h_px), n, H, C.c_uint64(seed), C.c_float(thr), *ptrs)
         self.n, self.H = n, H
         return out
 
@@ -205,14 +227,8 @@ class BatchedPairs:
         """run_host with the argument marshalling done once: returns (call, out); call() runs the whole path on the
         buffers captured here (a caller that processes a stream of pairs through the same buffers pays the ctypes
         conversions once, not ~10 us per call)."""
-        n = h_px.shape[-2]
-        B = self.pairs
-        if out is None:
-            out = {"E": np.empty((B, 9), np.float32), "P": np.empty((B, 16), np.float32), "pose_index": np.empty(B, np.int32),
-                   "inliers": np.empty(B, np.int32), "points": np.empty((B, 4, n), np.float32)}
-        pts = out.get("points")
-        args = (self._h, _hptr(h_px), n, H, C.c_uint64(seed), C.c_float(thr), _hptr(out["E"]), _hptr(out["P"]),
-                _hptr(out["pose_index"]), _hptr(out["inliers"]), _hptr(pts) if pts is not None else C.c_void_p(0))
+        h_px, n, out, ptrs = self._host_io(h_px, True, out)
+        args = (self._h, _hptr(h_px), n, H, C.c_uint64(seed), C.c_float(thr), *ptrs)
         fn = self.lib.raw("sfmb200_run_host")
         lib = self.lib
         self.n, self.H = n, H
@@ -221,6 +237,7 @@ class BatchedPairs:
             rc = fn(*args)
             if rc != 0:
                 raise SfmError(rc, lib.last_error())
+        call.keepalive = (h_px, out)          # the captured pointers must outlive the closure's users
         return call, out
 
     # ---- getters ----
@@ -290,11 +307,12 @@ class BatchedPairs:
         return out
 
     def copy_to_vbo(self, d_pos, d_col, pair: int = 0):
-        self.lib.call("sfmb200_copy_to_vbo", self._h, pair, _dptr(d_pos), _dptr(d_col))
+        self.lib.call("sfmb200_copy_to_vbo", self._h, pair, _dptr(d_pos, "float32", 4 * self.n), _dptr(d_col, "float32", 4 * self.n))
 
     def copy_to_vbo_coloured(self, d_pos, d_col, pair: int = 0, scale: float = 1.0, mode: int = 1, z_near: float = 0.0, z_far: float = 1.0):
         """mode 0 ones, 1 inlier green / outlier red, 2 depth ramp blue -> red between z_near and z_far."""
-        self.lib.call("sfmb200_copy_to_vbo_coloured", self._h, pair, _dptr(d_pos), _dptr(d_col), C.c_float(scale), mode,
+        self.lib.call("sfmb200_copy_to_vbo_coloured", self._h, pair, _dptr(d_pos, "float32", 4 * self.n), _dptr(d_col, "float32", 4 * self.n),
+                      C.c_float(scale), mode,
                       C.c_float(z_near), C.c_float(z_far))
 
     def score_plan(self) -> dict:

@@ -55,9 +55,11 @@ def estimate_e_sharded(handle, H_total: int, seed: int, thr: float, rank: int, w
     return lo, hi
 
 
-def connect_peers(handle, rank: int, world: int, group=None):
-    """One-time set-up of the peer-memory exchange (csrc/mg.cu): every rank exports the CUDA IPC handle of its
-    exchange buffer, the handles are all-gathered (plumbing, once) and every rank maps its peers' buffers."""
+def connect_peers(handle, rank: int, world: int, group=None, timeout_ms: int | None = None):
+    """One-time set-up of the peer-memory exchange (csrc/mg.cu): every rank exports an opaque blob (the CUDA IPC
+    handle of its exchange buffer + its device UUID), the blobs are all-gathered (plumbing, once; works over nccl
+    and gloo groups) and every rank maps its peers' buffers.  sfmb200_mg_connect refuses peers it cannot reach with
+    native P2P atomics."""
     import ctypes as C
 
     import torch
@@ -67,7 +69,10 @@ def connect_peers(handle, rank: int, world: int, group=None):
     nbytes = lib.raw("sfmb200_mg_handle_bytes")()
     mine = (C.c_ubyte * nbytes)()
     lib.call("sfmb200_mg_init", handle._h, rank, world, C.cast(mine, C.c_void_p))
-    t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device="cuda")
+    if timeout_ms is not None:
+        lib.call("sfmb200_mg_set_timeout_ms", handle._h, int(timeout_ms))
+    on_gpu = world > 1 and dist.get_backend(group) == "nccl"
+    t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device="cuda" if on_gpu else "cpu")
     table = [torch.empty_like(t) for _ in range(world)]
     if world > 1:
         dist.all_gather(table, t, group=group)
@@ -76,6 +81,11 @@ def connect_peers(handle, rank: int, world: int, group=None):
     blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in table)
     buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
     lib.call("sfmb200_mg_connect", handle._h, C.cast(buf, C.c_void_p))
+
+
+def disconnect_peers(handle):
+    """Unmaps the peers' buffers and frees this rank's (sfmb200_mg_close); connect_peers may be called again."""
+    handle.lib.call("sfmb200_mg_close", handle._h)
 
 
 def estimate_e_p2p(handle, H_total: int, seed: int, thr: float, d_idx=None):

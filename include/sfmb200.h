@@ -119,13 +119,19 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
  * exchange those handles by any means (the Python mirror uses torch.distributed.all_gather, once), and every
  * rank calls sfmb200_mg_connect with the world x bytes table indexed by rank.  Then sfmb200_estimate_e_mg,
  * called by every rank with the same arguments on the same correspondences, equals sfmb200_estimate_e over
- * all H_total hypotheses bit for bit.  Waits are bounded (~2 s): sfmb200_mg_status returns the number of
- * waits that timed out (0 in a healthy job). */
+ * all H_total hypotheses bit for bit.  The devices must support native P2P atomics with each other (NVLink):
+ * sfmb200_mg_connect checks cudaDevP2PAttrNativeAtomicSupported and refuses otherwise.  Waits are bounded (~2 s,
+ * sfmb200_mg_set_timeout_ms).  A wait that times out (lost or late peer) POISONS the exchange on that rank: the call
+ * publishes no result (inlier count 0, E = 0), the rank stops publishing (so its peers time out too), every later
+ * sfmb200_estimate_e_mg returns SFMB200_ERR_STATE, and sfmb200_mg_status returns the number of calls that timed out
+ * (0 in a healthy job) until every rank reconnects: sfmb200_mg_close + sfmb200_mg_init + sfmb200_mg_connect. */
 int sfmb200_mg_handle_bytes(void);
 int sfmb200_mg_init(sfmb200_t* h, int rank, int world, void* h_handle_out);
 int sfmb200_mg_connect(sfmb200_t* h, const void* h_handles);
 int sfmb200_estimate_e_mg(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t seed, float thr);
 int sfmb200_mg_status(sfmb200_t* h, int32_t* h_timeouts);
+/* bound of the exchange wait (default ~2000 ms) */
+int sfmb200_mg_set_timeout_ms(sfmb200_t* h, int ms);
 int sfmb200_mg_close(sfmb200_t* h);
 /* Device pointer to the per-pair packed winners, uint64 [pairs]:
  * (count << 32) | (0xFFFFFFFF - global hypothesis index).  Multi-GPU: all-reduce
@@ -138,10 +144,12 @@ int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t
  * matching.cu:1000-1087; the outlier pre-filter the reference's main.cpp:283-290 has commented out) on the
  * same hypothesis / scoring skeleton.  `loops` 4-point hypotheses per pair (device-drawn from `seed`), one-sided
  * transfer error of image-1 -> image-2 points under H below `thresh` (same division-free test as
- * TestHomographies, matching.cu:953-996), first maximum wins.  Coordinates and threshold are in whatever
- * units ingest produced: create the handle with K = Kinv = identity for CudaSift's pixel-space semantics.
- * h_H: host [pairs][9] row-major with h8 = 1 like CudaSift; h_matches: inlier counts.  Afterwards
- * get_inlier_mask / get_inlier_counts / get_best refer to the homography. */
+ * TestHomographies, matching.cu:953-996), first maximum wins.  `thresh` is in PIXELS and h_H maps image-1 PIXELS
+ * to image-2 pixels, like CudaSift's, whatever K the handle was created with: the test runs on the handle's
+ * normalised coordinates with thresh / f and the winner is returned as K H K^-1.  That is exact for
+ * K = [f 0 cx; 0 f cy; 0 0 1] (square pixels, no skew - the reference's K, main.cpp:292-294, and K = I); any
+ * other K returns SFMB200_ERR_ARG.  h_H: host [pairs][9] row-major with h8 = 1 like CudaSift; h_matches: inlier
+ * counts.  Afterwards get_inlier_mask / get_inlier_counts / get_best refer to the homography. */
 int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh, float* h_H, int32_t* h_matches);
 
 /* ---- local optimisation (not in the reference; its README.md:65-69 lists it as future work,
@@ -245,6 +253,9 @@ void sfmb200_host_solve_hypothesis_projector(const float pts[32], float E[9]);  
 void sfmb200_host_null4(const float A[16], float x[4]);
 /* inverse-iteration fast path of the same null vector; returns 1 when it did not converge (caller falls back) */
 int sfmb200_host_null4_fast(const float A[16], float x[4]);
+/* null vector of a two-view DLT matrix (rows 0, 1 = camera 1 = I4: (-1,0,x1,0), (0,-1,y1,0)) by the adjugate power
+ * iteration the triangulation kernel uses; returns 1 when it did not converge (caller falls back to null4) */
+int sfmb200_host_dlt_null(const float A[16], float x[4]);
 int sfmb200_host_inv4(const float m[16], float out[16]);
 void sfmb200_host_sample_indices(uint64_t seed, uint64_t h, int n, int32_t idx[8]);
 

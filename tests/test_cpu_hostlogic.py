@@ -181,6 +181,42 @@ def test_host_null4_fast_path_matches_jacobi_on_dlt_matrices(lib, O):
     assert f == 1 or abs(np.linalg.norm(A @ v)) < 2e-3
 
 
+def test_host_dlt_null_adjugate_matches_fp64_on_dlt_matrices(lib, O):
+    """The triangulation kernel's solve (adjugate power iteration exploiting camera 1 = I4, smallmat.cuh) vs the
+    fp64 SVD null vector on real DLT matrices: inliers and outliers, true and inverted pose."""
+    K, Kinv = O.reference_K()
+    sc = O.synthetic_pair(3000, seed=5, noise_px=2.0)
+    x = O.normalise_points(sc["px"], Kinv)
+    M = np.eye(4)
+    M[:3, :3], M[:3, 3] = sc["R"], sc["t"]
+    for MM in (M, np.linalg.inv(M)):
+        A = O.dlt_rows(x, MM).astype(np.float32)
+        ref = O.triangulate(x, MM)
+        out = np.zeros((len(x), 4), np.float32)
+        fails = 0
+        for i in range(len(x)):
+            f = lib.raw("sfmb200_host_dlt_null")(P(A[i]), P(out[i]))
+            fails += f
+            if f:
+                lib.raw("sfmb200_host_null4")(P(A[i]), P(out[i]))
+        X = out[:, :3] / out[:, 3:4]
+        rel = np.abs(X.T - ref[:3]).max(0) / np.maximum(np.abs(ref[:3]).max(0), 1e-3)
+        inl = ~sc["is_outlier"]
+        assert fails <= 3                       # the fallback exists for pathological geometry only
+        assert np.median(rel) < 1e-6 and np.percentile(rel[inl], 99) < 1e-5 and np.percentile(rel, 99) < 1e-4 and rel.max() < 5e-3
+    # pixel-sized coordinates (K = I): no overflow in the cofactors
+    A = O.dlt_rows(sc["px"], M).astype(np.float32)
+    v = np.zeros(4, np.float32)
+    ok = 0
+    for i in range(200):
+        f = lib.raw("sfmb200_host_dlt_null")(P(A[i]), P(v))
+        assert np.all(np.isfinite(v))
+        if not f:
+            t = np.linalg.svd(A[i].astype(np.float64))[2][-1]
+            ok += min(np.linalg.norm(t - v), np.linalg.norm(t + v)) < 1e-3
+    assert ok >= 150
+
+
 def test_shard_range_and_keys(pkg):
     sh = pkg.sharding
     for total in (0, 1, 7, 8, 65536, 1000003):
@@ -229,3 +265,28 @@ def test_headers_are_plain_c_and_a_c_program_links(tmp_path):
     import torch
     if not torch.cuda.is_available():
         assert int(rc) != 0 and "no CUDA device" in out.stdout
+
+
+def test_svd_h_facade_surface_host_and_device(tmp_path):
+    """SfM/svd.h facade: every name of the reference's header (svd.h:33-501), including its six internal steps, is there
+    with its meaning (tests/src/svd_surface_check.cpp asserts the maths on the host, g++), and all of it is
+    __host__ __device__ like the reference's: the same file compiles as CUDA with a kernel that calls it (nvcc -c)."""
+    import shutil
+    import subprocess
+
+    src = os.path.join(ROOT, "tests", "src", "svd_surface_check.cpp")
+    inc = os.path.join(ROOT, "cuda-sfm_b200", "SfM")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = tmp_path / "svdchk"
+    r = subprocess.run(["g++", "-O1", "-std=c++17", f"-I{cuda}/include", f"-I{inc}", "-o", str(exe), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "svd.h surface ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+    nvcc = os.path.join(cuda, "bin", "nvcc")
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    cu = tmp_path / "svdchk.cu"
+    shutil.copy(src, cu)
+    r = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", f"-I{inc}", "-c", "-o", str(tmp_path / "svdchk.o"), str(cu)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -81,3 +81,61 @@ def test_bundle_adjust_then_rest_of_the_api_still_consistent(pkg, O):
     M2 = h.get_poses()[0][int(h.get_pose_index()[0])]
     assert np.linalg.norm(M2[:3, :3] - M[:3, :3]) < 1e-3 and np.linalg.norm(M2[:3, 3] - M[:3, 3]) < 1e-3
     h.close()
+
+
+def test_failed_run_does_not_corrupt_the_threshold_scale(pkg, O):
+    """run_device / run_host used to commit the new threshold scale before the ingest was validated; a
+    failing call then left corr_s / corr_dup at the old scale while pt_scale claimed the new one, and the next
+    estimate at that threshold scored mis-scaled points."""
+    import torch
+
+    K, Kinv = O.reference_K()
+    n, H = 2000, 1024
+    px = O.synthetic_pair(n, seed=3)["px"]
+    d_px = torch.from_numpy(px).cuda()
+    h = pkg.BatchedPairs(K, Kinv, 1, n, H)
+    h.run_device(d_px, H, 7, 1e-6)
+    want = h.get_inlier_counts().cpu().numpy().copy()
+    fresh = pkg.BatchedPairs(K, Kinv, 1, n, H)
+    fresh.run_device(d_px, H, 7, 4e-6)
+    want4 = fresh.get_inlier_counts().cpu().numpy().copy()
+    big = torch.zeros((n + 100, 4), device="cuda")
+    with pytest.raises(pkg.SfmError):
+        h.run_device(big, H, 7, 4e-6)                       # n above max_points: must leave the handle untouched
+    with pytest.raises(pkg.SfmError):
+        h.lib.call("sfmb200_run_host", h._h, None, n, H, __import__("ctypes").c_uint64(7), __import__("ctypes").c_float(4e-6),
+                   None, None, None, None, None)            # null input
+    h.estimate_e(H, 7, 4e-6)                                # re-materialises the scaled copies for the new threshold
+    assert np.array_equal(h.get_inlier_counts().cpu().numpy(), want4)
+    h.estimate_e(H, 7, 1e-6)
+    assert np.array_equal(h.get_inlier_counts().cpu().numpy(), want)
+    h.close(); fresh.close()
+
+
+def test_python_mirror_validates_buffers(pkg, O):
+    """dtype / shape of every buffer whose raw pointer crosses the C ABI is checked first."""
+    import torch
+
+    K, Kinv = O.reference_K()
+    n, H = 1000, 256
+    px = O.synthetic_pair(n, seed=4)["px"]
+    h = pkg.BatchedPairs(K, Kinv, 1, n, H)
+    out = h.run_host(px.astype(np.float64), H, 1, 1e-6)      # float64 input is coerced, not reinterpreted
+    ref = h.run_host(px, H, 1, 1e-6)
+    assert np.array_equal(out["E"], ref["E"]) and np.array_equal(out["points"], ref["points"])
+    bad = {k: v.copy() if v is not None else None for k, v in ref.items()}
+    bad["points"] = np.empty((1, 4, n // 2), np.float32)
+    with pytest.raises(ValueError):
+        h.run_host(px, H, 1, 1e-6, out=bad)
+    bad["points"] = np.empty((1, 4, n), np.float64)
+    with pytest.raises(TypeError):
+        h.run_host(px, H, 1, 1e-6, out=bad)
+    with pytest.raises(TypeError):
+        h.prepare_run_host(px, H, 1, 1e-6, out=dict(ref, inliers=np.empty(1, np.int64)))
+    with pytest.raises(TypeError):
+        h.set_points_xy(torch.zeros((n, 4), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        h.set_points_xy(torch.zeros((n // 2, 4), device="cuda"), n)
+    with pytest.raises(TypeError):
+        h.estimate_e(H, 1, 1e-6, d_idx=torch.zeros((H, 8), dtype=torch.int64, device="cuda"))
+    h.close()

@@ -85,3 +85,44 @@ def test_homography_batched_and_deterministic(pkg, O):
     with pytest.raises(pkg.SfmError):
         hb.find_homography(loops, 5, 0.0)
     hb.close()
+
+
+def test_homography_pixel_semantics_with_real_intrinsics(pkg, O):
+    """CudaSift's FindHomography takes a PIXEL threshold and returns a pixel-to-pixel H.  A handle created with the
+    reference's K (as SfM::Image_pair always is) holds K^-1-normalised coordinates: the call must still mean pixels
+    (threshold thresh / f inside, K H K^-1 on return) and agree with a K = I handle fed the same pixel data."""
+    import torch
+
+    K, Kinv = O.reference_K()
+    sc = O.planar_pair(3000, outlier_frac=0.3, noise_px=0.5, seed=7)
+    n, loops, thresh, seed = len(sc["px"]), 2048, 3.0, 11
+    d_px = torch.from_numpy(sc["px"]).cuda()
+    hp = pkg.BatchedPairs(I3, I3, 1, n, loops)
+    hp.set_points_xy(d_px)
+    Hp, mp_ = hp.find_homography(loops, seed, thresh)
+    hk = pkg.BatchedPairs(K, Kinv, 1, n, loops)
+    hk.set_points_xy(d_px)
+    Hk, mk = hk.find_homography(loops, seed, thresh)
+    # same sample rows on both sides, same metric up to fp32 rounding of the normalisation: the consensus sets agree
+    # to a handful of borderline points, nowhere near "every match is an inlier" (a 5.0 threshold in normalised units)
+    assert abs(int(mk[0]) - int(mp_[0])) <= max(5, int(0.005 * n)), (mk, mp_)
+    assert mk[0] < 0.8 * n
+    mask_k = hk.get_inlier_mask().cpu().numpy().astype(bool)
+    mask_p = hp.get_inlier_mask().cpu().numpy().astype(bool)
+    assert mask_k.sum() == mk[0] and np.mean(mask_k != mask_p) < 0.01
+    assert np.mean(mask_k[~sc["is_outlier"]]) > 0.9 and np.mean(mask_k[sc["is_outlier"]]) < 0.05
+    # the returned H is in pixels: it transfers image-1 pixels like the true homography does
+    good = ~sc["is_outlier"]
+    x = sc["px"]
+    hom = np.stack([x[good, 0], x[good, 1], np.ones(good.sum())])
+    q, q_true = Hk[0].astype(np.float64) @ hom, sc["H"] @ hom
+    transfer = np.hypot(q[0] / q[2] - q_true[0] / q_true[2], q[1] / q[2] - q_true[1] / q_true[2])
+    assert np.median(transfer) < 1.5 and abs(Hk[0][2, 2] - 1) < 1e-6
+    # anisotropic pixels: refused, not silently mis-scaled
+    Kb = K.copy(); Kb[1, 1] *= 1.1
+    hb = pkg.BatchedPairs(Kb, np.linalg.inv(Kb).astype(np.float32), 1, n, loops)
+    hb.set_points_xy(d_px)
+    with pytest.raises(pkg.SfmError):
+        hb.find_homography(loops, seed, thresh)
+    for h in (hp, hk, hb):
+        h.close()

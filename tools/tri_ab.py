@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""A/B of triangulation builds (tools/proto/explibs/tri_*.so + the product build): 1M points (config 5), L2 flushed
+between launches, CUDA events around each launch on the handle's stream; median of 40.  Each build in its own process."""
+import glob, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if len(sys.argv) > 1 and sys.argv[1] == "--one":
+    path = sys.argv[2]
+    sys.path.insert(0, ROOT)
+    import numpy as np, torch
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    lib = pkg.load_library(path)
+    K, Kinv = pkg.synthetic.reference_K()
+    for n in (1 << 20, 10000):
+        H = 4096
+        px = pkg.synthetic.synthetic_pair(n, 0.3, 1.0, seed=77)["px"]
+        d_px = torch.from_numpy(px[None]).cuda()
+        h = pkg.BatchedPairs(K, Kinv, 1, n, H, lib=lib)
+        h.run_device(d_px, H, 1237, 1e-6)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        ms = []
+        for i in range(45):
+            flush.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); h.triangulate(); b.record(); torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        ms = sorted(ms[5:])
+        pts = h.get_points_host()
+        t = ms[len(ms) // 2]
+        print(json.dumps(dict(lib=os.path.basename(path), n=n, tri_ms_median=t, tri_ms_min=ms[0], gbs=32 * n / (t * 1e-3) / 1e9,
+                              frac_hbm=32 * n / (t * 1e-3) / 1e9 / 6543.7, checksum=float(np.nansum(np.abs(pts[:3]).clip(0, 1e3))),
+                              nonfinite=int((~np.isfinite(pts)).sum()))), flush=True)
+        h.close()
+else:
+    libs = [os.path.join(ROOT, "cuda-sfm_b200", "libsfmb200.so")] + sorted(glob.glob(os.path.join(ROOT, "tools", "proto", "explibs", "tri_*.so")))
+    for l in libs:
+        subprocess.run([sys.executable, __file__, "--one", l])
