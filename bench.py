@@ -13,6 +13,15 @@ already in HBM; `e2e` is the same through the C-ABI host entry point
 N > 1: one process per GPU (torchrun), pairs sharded across ranks, no data-path
 collective (weak scaling); the barrier + max over ranks follows the contract.
 
+The same JSON line also carries, each measured outside the headline region and
+bounded to a few seconds: `sustained` (config 2 back to back for >= 2 s with its
+own clock samples), `c1` (the reference's dino pair with its own CudaSift matches,
+tests/golden/dino_cudasift_000_001.npz), `c3` (1M x 1M, HYPOTHESES sharded over the
+N ranks, the (count, index) exchange once through NVLink peer memory -
+sfmb200_estimate_e_mg - and once through an NCCL all-reduce; strong scaling),
+`c4` (4,096 pairs x 4k x 4k, PAIRS sharded over the N ranks; strong scaling) and
+`c5` (full path with 1M triangulated points; the triangulation roofline).
+
 --impl reference times the reference's OWN implementation of the path, which is
 CUDA (it has no CPU path): its unmodified sources rebuilt for sm_100a as
 oracle/_ref/libsfm_ref.so, same config, rank 0 only.
@@ -40,6 +49,17 @@ FLOP_PER_EVAL = 34.0              # 15 FFMA x2 + 3 FMUL + 1 compar
 # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch at this config,
 # from the ncu --set full capture summarised in profiles/r01_ncu_summary.md
 SCORE_TRAFFIC_BYTES_NCU = 2_972_416
+
+
+def ncu_traffic():
+    """DRAM bytes per score_kernel launch from the committed ncu capture (profiles/ncu_traffic.json, written by
+    tools/make_profiles.py from the `ncu --set full` report of `python bench.py`); a profiler counter cannot be
+    read inside an unprofiled run, so the line names the capture it comes from."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return int(d["score_kernel_dram_bytes_per_launch"]), d.get("source", "profiles/ncu_traffic.json")
+    except Exception:
+        return SCORE_TRAFFIC_BYTES_NCU, "profiles/r01_ncu_summary.md"
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4
 
 
@@ -160,6 +180,173 @@ def cv2_baseline(scene, K) -> dict | None:
             "inliers": int(mask.sum())}
 
 
+def _timed(torch, dist, world, fn, reps):
+    """ms per call: barrier + synchronise, CUDA events on the launching stream around ONE call, max over ranks; min over reps."""
+    out = []
+    for _ in range(reps):
+        barrier(world)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append(float(t.item()))
+    return out
+
+
+def run_configs(pkg, torch, dist, rank, world, K, Kinv, args) -> dict:
+    """BASELINE configs 1, 3, 4, 5 (config 2 is the headline).  Bounded: a few launches each."""
+    S = pkg.synthetic
+    sh = pkg.sharding
+    res = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    scale = float(os.environ.get("SFMB200_BENCH_SCALE", "1.0"))        # < 1 shrinks configs 3-5 (CPU-side dry runs of this file)
+
+    # ---- c3: one pair, 1M correspondences x 1M hypotheses, hypotheses sharded over the ranks (strong scaling) ----
+    n3 = H3 = max(int((1 << 20) * scale), 4096)
+    sc3 = S.synthetic_pair(n3, seed=1234)                   # replicated: every rank builds the same pair
+    d_px3 = torch.from_numpy(sc3["px"]).cuda()
+    lo, hi = sh.shard_range(H3, rank, world)
+    h = pkg.BatchedPairs(K, Kinv, 1, n3, hi - lo)
+    h.set_points_xy(d_px3)
+    c3 = {"workload": f"1 pair, {n3} correspondences x {H3} hypotheses, hypotheses sharded over {world} GPU(s): rank r generates and scores "
+                      "its contiguous slice against the replicated correspondences; one 8-byte (count, index) key per pair is exchanged",
+          "n": n3, "H": H3, "scaling": "strong", "evals": n3 * H3}
+    winners = {}
+    for name in ("p2p", "nccl"):
+        try:
+            if name == "p2p":
+                sh.connect_peers(h, rank, world)
+                step = lambda: sh.estimate_e_p2p(h, H3, SEED, THR)          # noqa: E731
+            else:
+                step = lambda: sh.estimate_e_sharded(h, H3, SEED, THR, rank, world)   # noqa: E731
+            step()
+            ms = _timed(torch, dist, world, step, 2)
+            idx, cnt = h.get_best()
+            E = torch.from_numpy(h.get_E()).cuda()
+            same = True
+            if world > 1:                                   # every rank must hold the same winner and the same E bits
+                Es = [torch.empty_like(E) for _ in range(world)]
+                dist.all_gather(Es, E)
+                same = all(torch.equal(Es[0], e) for e in Es)
+            winners[name] = (int(idx[0]), int(cnt[0]))
+            c3[name] = {"ms": min(ms), "ms_all": ms, "evals_per_s": n3 * H3 / (min(ms) * 1e-3), "winner_index": int(idx[0]),
+                        "winner_inliers": int(cnt[0]), "all_ranks_same_E_bits": bool(same),
+                        "exchange": "keys + E pushed into every peer's buffer by system-scope atomics over NVLink peer memory (csrc/mg.cu), no collective call"
+                        if name == "p2p" else "dist.all_reduce(MAX) of the 8-byte packed key over NCCL, winner regenerated locally from its index",
+                        "timeouts": sh.p2p_timeouts(h) if name == "p2p" else None}
+        except Exception as e:  # noqa: BLE001
+            c3[name] = {"error": repr(e)}
+    c3["same_winner_both_exchanges"] = len(set(winners.values())) == 1 if len(winners) == 2 else None
+    c3["plan"] = h.score_plan()
+    res["c3"] = c3
+    h.close()
+
+    # ---- c5: full path on one pair with 1M correspondences, all triangulated (replicas: rank 0's number is reported) ----
+    H5 = 65536
+    h = pkg.BatchedPairs(K, Kinv, 1, n3, H5)
+    h.run_device(d_px3, H5, SEED, THR)
+    step_ms = _timed(torch, dist, world, lambda: h.run_device(d_px3, H5, SEED, THR), 3)
+    tri = []
+    for i in range(24):                                     # the triangulation launch alone, L2 flushed before each
+        flush.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        h.triangulate()
+        b.record()
+        torch.cuda.synchronize()
+        tri.append(a.elapsed_time(b))
+    tri = sorted(tri[4:])
+    tri_ms = tri[len(tri) // 2]
+    pts = h.get_points_host()
+    inl = h.get_inlier_mask().cpu().numpy().astype(bool)
+    res["c5"] = {"workload": f"full path, 1 pair, {n3} correspondences, {H5} hypotheses, all {n3} points triangulated", "n": n3, "H": H5,
+                 "ms_per_pair": min(step_ms), "tri_ms": tri_ms, "tri_ms_min": tri[0], "tri_points_per_s": n3 / (tri_ms * 1e-3),
+                 "tri_gbs": 32.0 * n3 / (tri_ms * 1e-3) / 1e9, "inliers": int(inl.sum()),
+                 "inliers_in_front_of_camera_1": float(np.mean(pts[2][inl] > 0)) if inl.any() else None}
+    h.close()
+    del d_px3
+
+    # ---- c4: 4,096 pairs x 4,096 correspondences x 4,096 hypotheses, pairs sharded over the ranks (strong scaling) ----
+    pairs, n4, H4 = max(int(4096 * scale), world), 4096, 4096
+    lo, hi = sh.shard_range(pairs, rank, world)
+    mine = hi - lo
+    base = [S.synthetic_pair(n4, seed=500 + i)["px"] for i in range(8)]
+    d_base = torch.from_numpy(np.stack(base)).cuda()
+    d_px4 = d_base[torch.arange(lo, hi, device="cuda") % 8].contiguous()        # pair p = scene p mod 8, its own sample seed
+    h = pkg.BatchedPairs(K, Kinv, mine, n4, H4)
+    step = lambda: h.run_device(d_px4, H4, 99 + lo, THR, n=n4)                  # noqa: E731
+    step()
+    ms = _timed(torch, dist, world, step, 3)
+    t = min(ms)
+    res["c4"] = {"workload": f"{pairs} pairs x {n4} correspondences x {H4} hypotheses, full path per pair, pairs sharded over {world} GPU(s), "
+                             "no data-path collective", "pairs": pairs, "n": n4, "H": H4, "scaling": "strong", "ms": t, "ms_all": ms,
+                 "pairs_per_s": pairs / (t * 1e-3), "evals_per_s": pairs * n4 * H4 / (t * 1e-3), "hypotheses_per_s_whole_path": pairs * H4 / (t * 1e-3),
+                 "inliers_first_pairs_rank0": [int(v) for v in h.get_best()[1][:4]], "plan": h.score_plan()}
+    h.close()
+    del d_px4, d_base
+
+    # ---- c1: the reference's dino pair with its own CudaSift matches (rank 0 only; ~2k correspondences, H = N/8) ----
+    fx = os.path.join(ROOT, "tests", "golden", "dino_cudasift_000_001.npz")
+    if rank == 0 and os.path.exists(fx):
+        g = np.load(fx)
+        px1 = np.ascontiguousarray(g["px"])
+        n1, H1 = len(px1), len(g["idx"])
+        K1, K1inv = S.reference_K(int(g["image_wh"][0]), int(g["image_wh"][1]))
+        d_px1 = torch.from_numpy(px1).cuda()
+        d_idx1 = torch.from_numpy(np.ascontiguousarray(g["idx"])).cuda()
+        h = pkg.BatchedPairs(K1, K1inv, 1, n1, H1)
+
+        def staged():                                       # the five calls main.cpp makes (src/main.cpp:298-307), exported rows
+            h.set_points_xy(d_px1)
+            h.estimate_e(H1, 0, THR, d_idx=d_idx1)
+            h.pose_candidates()
+            h.choose_pose()
+            h.triangulate()
+        dev = {}
+        for name, fn in (("staged_calls_fixture_rows", staged), ("run_device", lambda: h.run_device(d_px1, H1, SEED, THR))):
+            for _ in range(5):
+                fn()
+            ts = []
+            for i in range(40):
+                flush[: 1 << 20].fill_(i & 0xFF)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            dev[name] = sorted(ts)[len(ts) // 2]
+        staged()
+        bi, bc = h.get_best()
+        hp1 = torch.from_numpy(px1).pin_memory().numpy()
+        out1 = {"E": np.empty((1, 9), np.float32), "P": np.empty((1, 16), np.float32), "pose_index": np.empty(1, np.int32),
+                "inliers": np.empty(1, np.int32), "points": torch.empty((1, 4, n1), dtype=torch.float32).pin_memory().numpy()}
+        run1, _ = h.prepare_run_host(hp1, H1, SEED, THR, out=out1)
+        for _ in range(5):
+            run1()
+        ts = []
+        for _ in range(40):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run1()
+            ts.append(time.perf_counter() - t0)
+        ref_ms = [float(v) for v in g["ref_ms"]]
+        res["c1"] = {"workload": f"data/dino viff.000/001, the reference's own CudaSift matches: {n1} correspondences, {H1} hypotheses (N/8), 1 GPU",
+                     "n": n1, "H": H1, "device_ms_per_pair": dev, "e2e_ms_per_pair": 1e3 * sorted(ts)[len(ts) // 2],
+                     "winner": [int(bi[0]), int(bc[0])], "winner_fixture_fp64": [int(g["best"]), int(g["counts"].max())],
+                     "reference_rebuilt_b200_ms": {"estimateE": ref_ms[0], "computePosecandidates": ref_ms[1], "choosePose_first_call": ref_ms[2],
+                                                   "linear_triangulation": ref_ms[3], "source": "tests/golden/make_dino_cudasift_fixture.py (oracle/_ref/libsfm_ref.so on a B200)"},
+                     "reference_published_1080ti_ms": {"hot_path_total": 38.92, "estimateE": 24.12, "source": "BASELINE.md section 1"}}
+        h.close()
+    del flush
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -220,6 +407,7 @@ def run_ours(args):
     stage = h.stage_times()
     stage_ms = stage.mean(axis=0) if len(stage) else np.zeros(7)
     best_idx, best_cnt = h.get_best()
+    plan_main = h.score_plan()
     # hypothesis generation with the other null-vector solver (9x9 Jacobi eigensolve), outside the timed region
     h.set_option(5, 0)
     h.set_option(4, 1)
@@ -253,6 +441,39 @@ def run_ours(args):
     h2d = px.nbytes
     d2h = 9 * 4 + 16 * 4 + 4 + 4 + 4 * N_CORR * 4
 
+    h2d_pageable = None
+    if rank == 0:
+        # the same call with PAGEABLE caller buffers: staged through the copy engines (api.cu: ingest_xy_host + pack)
+        hp_pg = np.array(px, copy=True)
+        out_pg = {"E": np.empty((1, 9), np.float32), "P": np.empty((1, 16), np.float32), "pose_index": np.empty(1, np.int32),
+                  "inliers": np.empty(1, np.int32), "points": np.empty((1, 4, N_CORR), np.float32)}
+        run_pg, _ = h.prepare_run_host(hp_pg, N_HYP, SEED, THR, out=out_pg)
+        for _ in range(3):
+            run_pg()
+        ts = []
+        for i in range(min(args.steps, 50)):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run_pg()
+            ts.append(time.perf_counter() - t0)
+        h2d_pageable = 1e3 * sum(ts) / len(ts)
+
+    # ---- sustained: config 2 back to back for >= 2 s (same step, same flush, same events), its own clock samples ----
+    sus_steps = int(min(max(2000.0 / max(ms_per_step + 0.06, 1e-3), args.steps), 20000))
+    sus_sampler = ClockSampler(local)
+    sus_sampler.start()
+    sus_wall0 = time.perf_counter()
+    sus_ms = timed_region(sus_steps) / sus_steps
+    sus_wall = time.perf_counter() - sus_wall0
+    sus_clocks = sus_sampler.stop()
+    h.close()
+    del flush
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs (all ranks take part; rank 0 reports) ----
+    extra = run_configs(pkg, torch, dist, rank, world, K, Kinv, args)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -260,12 +481,14 @@ def run_ours(args):
         return
     # ---- rank 0: roofline, probes, CPU baselines, JSON line ----
     lib = pkg.load_library()
+    score_plan = plan_main
     probe = {}
     for mode, name in ((0, "ffma"), (1, "ffma2")):
         fmas, ms = C.c_double(), C.c_float()
         lib.call("sfmb200_fma_probe", mode, 2000, C.byref(fmas), C.byref(ms))
         probe[name + "_tflops"] = 2 * fmas.value / (ms.value * 1e-3) / 1e12
     peaks = measured_peaks()
+    traffic, traffic_src = ncu_traffic()
     score_ms = float(stage_ms[2])
     achieved = FLOP_PER_EVAL * N_HYP * N_CORR / (score_ms * 1e-3) / 1e12 if score_ms > 0 else None
     fp32_probe = max(probe.values())
@@ -278,18 +501,25 @@ def run_ours(args):
         "peak_measured_probe": fp32_probe, "frac_of_measured_probe": achieved / fp32_probe if achieved else None,
         "probe": probe, "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": N_HYP * N_CORR,
         "kernel_ms": score_ms, "kernel_share_of_step": score_ms / ms_per_step if ms_per_step else None, "evals_per_s_kernel": N_HYP * N_CORR / (score_ms * 1e-3) if score_ms > 0 else None,
-        "traffic": SCORE_TRAFFIC_BYTES_NCU, "traffic_unit": "bytes per launch (ncu r01 capture; algorithmic input 2.36 MB of E candidates + 0.32 MB of points)",
+        "traffic": traffic, "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full "
+                                             "capture of this command (" + traffic_src + "); algorithmic input 2.36 MB of E candidates + 0.32 MB of points",
     }
-    tri_ms = float(stage_ms[6])
     hbm = peaks.get("hbm_gbs", 6650.0)
-    tri = {"kernel": "triangulate_kernel", "bound": "hbm", "achieved": 32.0 * N_CORR / (tri_ms * 1e-3) / 1e9 if tri_ms > 0 else None,
+    c5 = extra.get("c5") or {}
+    tri_ms = c5.get("tri_ms")
+    tri = {"kernel": "triangulate_kernel", "bound": "hbm", "achieved": c5.get("tri_gbs"),
            "peak": hbm, "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback",
-           "bytes_per_point": 32, "kernel_ms": tri_ms,
-           "note": "10k points = 320 KB: launch-latency bound at this size; see profiles/ for the 1M-point run"}
+           "bytes_per_point": 32, "points_per_launch": c5.get("n"), "kernel_ms": tri_ms,
+           "note": "BASELINE config 5: 1,048,576 points per launch (32 MB of traffic), L2 flushed before every timed launch, CUDA events "
+                   "around the launch on its stream; the 10k-point launch inside a config-2 step is launch-latency bound "
+                   f"({float(stage_ms[6]) * 1e3:.1f} us)"}
     tri["frac"] = tri["achieved"] / hbm if tri["achieved"] else None
-    O = entry.load_oracle()              # cpu_baseline leg: the oracle port timed on the host cores
-    x = O.normalise_points(px, Kinv)
-    cpu = cpu_baseline(O, x)
+    cpu = cv2b = None
+    if world == 1:                       # CPU baselines: N = 1 only (at N > 1 the other ranks would idle behind them)
+        O = entry.load_oracle()          # cpu_baseline leg: the oracle port timed on the host cores
+        x = O.normalise_points(px, Kinv)
+        cpu = cpu_baseline(O, x)
+        cv2b = cv2_baseline(scene, K)
     line = {
         "metric": "RANSAC hyp*corr evals/s", "value": value, "unit": "hyp*corr evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -299,7 +529,7 @@ def run_ours(args):
                                "pose candidates, cheirality, triangulation)", "pairs_per_step_per_gpu": 1,
                    "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective",
                    "l2": "flushed between timed iterations (256 MiB write)", "threshold": THR, "seed": SEED,
-                   "score_plan": h.score_plan()},
+                   "score_plan": score_plan},
         "e2e": {"value": world * N_HYP * N_CORR / (e2e_ms * 1e-3), "unit": "hyp*corr evals/s", "ms_per_pair": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "sfmb200_run_host (C ABI), pinned host buffers (read and written by the kernels through their "
@@ -315,9 +545,14 @@ def run_ours(args):
         "e_estimate_ms_per_pair": float(stage_ms[1] + stage_ms[2] + stage_ms[3]),
         "pairs_per_s": world / (ms_per_step * 1e-3),
         "result": {"best_hypothesis": int(best_idx[0]), "inliers": int(best_cnt[0]), "pose_index": int(out["pose_index"][0])},
-        "roofline": roofline, "roofline_triangulation": tri, "cpu_baseline": cpu, "cv2_baseline": cv2_baseline(scene, K),
+        "roofline": roofline, "roofline_triangulation": tri, "cpu_baseline": cpu, "cv2_baseline": cv2b,
         "clocks": clocks, "wall_s_timed_region": wall,
+        "sustained": {"what": "the same config-2 step back to back (L2 flushed between steps, CUDA events per step, max over ranks)",
+                      "steps": sus_steps, "ms_per_step": sus_ms, "value": world * N_HYP * N_CORR / (sus_ms * 1e-3), "unit": "hyp*corr evals/s",
+                      "wall_s": sus_wall, "clocks": sus_clocks},
+        **extra,
     }
+    line["e2e"]["ms_per_pair_pageable_buffers"] = h2d_pageable
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

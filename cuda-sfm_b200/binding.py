@@ -80,6 +80,7 @@ SIGNATURES = {
     "sfmb200_stage_times": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_int)]),
     "sfmb200_fma_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "sfmb200_host_svd3": (None, [_f, _f, _f, _f]),
+    "sfmb200_host_svd3_reference_orientation": (None, [_f, _f, _f, _f]),
     "sfmb200_host_solve_hypothesis": (None, [_f, _f]),
     "sfmb200_host_solve_hypothesis_projector": (None, [_f, _f]),
     "sfmb200_host_null4": (None, [_f, _f]),

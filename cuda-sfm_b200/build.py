@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libsfmb200.so")
-SOURCES = ["api.cu", "hypgen.cu", "score.cu", "geometry.cu", "refit.cu", "bundle.cu", "chain.cu", "mg.cu", "hostmath.cu", "la_wrappers.cu"]
+SOURCES = ["api.cu", "hypgen.cu", "score.cu", "geometry.cu", "small.cu", "refit.cu", "bundle.cu", "chain.cu", "mg.cu", "hostmath.cu", "la_wrappers.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-Wno-deprecated-gpu-targets",

@@ -57,6 +57,8 @@ struct sfmb200_handle {
     int score_variant;
     int tri_inliers_only;
     int hyp_solver;
+    int small_path;        // SFMB200_OPT_SMALL_PATH: -1 auto, 0 never, 1 whenever eligible
+    long long small_evals; // auto: use the fused single-launch path when n * H is at most this
     int model;             // what s.E holds: 0 essential matrix, 1 homography (find_homography)
     // state of the last estimate
     int H;            // hypotheses in the local slice
@@ -221,6 +223,8 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->hyp_solver = 1;     // Cholesky projector: same parity as the Jacobi eigensolve, 3.5-4.4x faster (profiles/)
     h->score_variant = -1;
     h->tri_inliers_only = 0;
+    h->small_path = -1;
+    h->small_evals = 6000000;      // crossover with the five-launch path on B200 (profiles/r02_small_path.md)
     *out = h;
     return SFMB200_OK;
 }
@@ -262,6 +266,14 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
             h->hyp_solver = value;
             break;
         case SFMB200_OPT_BA_PERSISTENT: h->ba.persistent = value ? 1 : 0; break;
+        case SFMB200_OPT_SMALL_PATH:
+            if (value < -1 || value > 1) return fail(SFMB200_ERR_ARG, "small path must be -1 (auto), 0 (never) or 1 (whenever eligible)%s");
+            h->small_path = value;
+            break;
+        case SFMB200_OPT_SMALL_PATH_EVALS:
+            if (value < 0) return fail(SFMB200_ERR_ARG, "evaluation limit must be >= 0%s");
+            h->small_evals = value;
+            break;
         case SFMB200_OPT_PROFILE:
             if (value && !h->prof_ev) {
                 h->prof_ev = new cudaEvent_t[PROF_RING][8];
@@ -406,6 +418,18 @@ static int ensure_scaled(sfmb200_handle* h, float scale) {
     return SFMB200_OK;
 }
 
+// The fused single-launch path (small.cu) serves essential-matrix estimates with the projector solver whose
+// hypotheses fit one cluster's shared memory; `pose`: the call also runs the pose stage, which the fused kernel
+// implements in reference (compat) semantics only.  Not used while per-stage events are being recorded.
+static bool small_path_ok(const sfmb200_handle* h, int H, bool pose) {
+    if (h->small_path == 0 || h->profile || h->hyp_solver != 1 || h->s.skip != nullptr) return false;
+    if (h->score_variant >= 0 && h->small_path != 1) return false;      // the caller asked for a specific scoring kernel
+    if (pose && !h->compat) return false;
+    if (H > small_path_max_hypotheses()) return false;
+    if (h->small_path == 1) return true;
+    return (long long)h->s.n * (long long)H <= h->small_evals;
+}
+
 int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, int h_begin, int H, uint64_t seed,
                              float thr) {
     ENTER(h);
@@ -418,17 +442,25 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     h->h_begin = h_begin;
     h->thr = thr;
     if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;
-    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant, h->sms);
-    launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->hyp_solver, h->stream);
-    prof_mark(h, 2);
-    CKL();
-    launch_score(h->s, h->plan, H, h_begin, thr, h->stream);
-    prof_mark(h, 3);
-    CKL();
-    launch_select(h->s, h_begin, h->stream);
-    prof_mark(h, 4);
-    CKL();
-    h->launches += 3;
+    if (small_path_ok(h, H, false)) {
+        // hypothesis generation + scoring + arg-max + selection in one cluster launch
+        CK(launch_small_path(h->s, nullptr, d_idx, (long long)H_total * 8, H, h_begin, seed, thr, h->compat, 0, SMALL_ESTIMATE, h->stream));
+        memset(&h->plan, 0, sizeof(h->plan));
+        h->plan.variant = -2;      // reported by sfmb200_score_plan: the fused path
+        h->launches += 1;
+    } else {
+        h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant, h->sms);
+        launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->hyp_solver, h->stream);
+        prof_mark(h, 2);
+        CKL();
+        launch_score(h->s, h->plan, H, h_begin, thr, h->stream);
+        prof_mark(h, 3);
+        CKL();
+        launch_select(h->s, h_begin, h->stream);
+        prof_mark(h, 4);
+        CKL();
+        h->launches += 3;
+    }
     h->have_candidates = true;
     h->have_E = true;
     h->have_pose = false;
@@ -903,11 +935,37 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
     return sfmb200_triangulate(h);
 }
 
+// Whole path in ONE launch when the problem is small (small.cu).  Returns 0 when the fused path does not apply (the
+// caller continues with the general path), 1 when it ran, < 0 on error.  d_px: device-readable pixel correspondences.
+static int run_small(sfmb200_t* h, const float* d_px, int n, int H, uint64_t seed, float thr) {
+    if (!d_px || n < 8 || n > h->s.n_max || H < 1 || H > h->s.h_max) return 0;       // let the general path report the error
+    const int n_before = h->s.n;
+    h->s.n = n;
+    const bool ok = small_path_ok(h, H, true);
+    h->s.n = n_before;
+    if (!ok) return 0;
+    h->s.n = n;
+    h->s.pt_scale = make_thr_scale(thr).ik;
+    cudaError_t e = launch_small_path(h->s, d_px, nullptr, (long long)H * 8, H, 0, seed, thr, h->compat, h->tri_inliers_only,
+                                      SMALL_INGEST | SMALL_ESTIMATE | SMALL_POSE | SMALL_TRI, h->stream);
+    if (e != cudaSuccess) return fail(SFMB200_ERR_CUDA, "fused small-problem launch: %s", cudaGetErrorString(e));
+    h->H = H;
+    h->h_begin = 0;
+    h->thr = thr;
+    h->model = 0;
+    memset(&h->plan, 0, sizeof(h->plan));
+    h->plan.variant = -2;
+    h->launches += 1;
+    h->have_points = h->have_candidates = h->have_E = h->have_pose = true;
+    return 1;
+}
+
 int sfmb200_run_device(sfmb200_t* h, const float* d_px, int n, int H, uint64_t seed, float thr) {
     ENTER(h);
     if (!h) return fail(SFMB200_ERR_ARG, "null handle%s");
     if (!(thr > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
     prof_next(h);
+    if (int rc = run_small(h, d_px, n, H, seed, thr)) return rc < 0 ? rc : SFMB200_OK;      // > 0: done by the fused path
     int rc = ingest_xy(h, d_px, n, make_thr_scale(thr).ik);          // writes the scaled copies for this threshold
     if (rc) return rc;
     return run_stages(h, H, seed, thr);
@@ -962,9 +1020,27 @@ int sfmb200_run_host(sfmb200_t* h, const float* h_px, int n, int H, uint64_t see
     const size_t zero_copy_limit = 4u << 20;
     const size_t in_bytes = (size_t)h->s.B * (size_t)(n > 0 ? n : 0) * 4 * sizeof(float);
     const float* px_alias = in_bytes <= zero_copy_limit ? (const float*)pinned_alias(h_px) : nullptr;
-    int rc = px_alias ? ingest_xy(h, px_alias, n, scale) : ingest_xy_host(h, h_px, n, scale);
-    if (rc) return rc;
-    if ((rc = run_stages(h, H, seed, thr))) return rc;
+    int rc = 0;
+    const bool small_shape = h_px && n >= 8 && n <= h->s.n_max && H >= 1 && H <= h->s.h_max;
+    if (px_alias) {
+        rc = run_small(h, px_alias, n, H, seed, thr);
+    } else if (small_shape) {
+        // pageable input: stage it, then the fused path reads the staged copy
+        if ((rc = ensure_staging(h, true, false))) return rc;
+        CK(cudaMemcpyAsync(h->s.px, h_px, (size_t)h->s.B * n * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        rc = run_small(h, h->s.px, n, H, seed, thr);
+        if (rc == 0) {                                          // not eligible: general path on the staged copy
+            if ((rc = ingest_xy(h, h->s.px, n, scale))) return rc;
+            if ((rc = run_stages(h, H, seed, thr))) return rc;
+            rc = 1;
+        }
+    }
+    if (rc < 0) return rc;
+    if (rc == 0) {
+        rc = px_alias ? ingest_xy(h, px_alias, n, scale) : ingest_xy_host(h, h_px, n, scale);
+        if (rc) return rc;
+        if ((rc = run_stages(h, H, seed, thr))) return rc;
+    }
     DeviceState& s = h->s;
     const size_t B = s.B;
     float* pts_alias = B * 4 * (size_t)s.n * sizeof(float) <= zero_copy_limit ? (float*)pinned_alias(h_points) : nullptr;

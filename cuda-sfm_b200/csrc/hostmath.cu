@@ -11,6 +11,10 @@ extern "C" {
 
 void sfmb200_host_svd3(const float a[9], float u[9], float s[9], float v[9]) { svd3<5>(a, u, s, v); }
 
+void sfmb200_host_svd3_reference_orientation(const float a[9], float u[9], float s[9], float v[9]) {
+    svd3_reference_orientation(a, u, s, v);
+}
+
 void sfmb200_host_solve_hypothesis(const float pts[32], float E[9]) {
     Corr c[8];
     for (int i = 0; i < 8; i++) c[i] = Corr{pts[4 * i], pts[4 * i + 1], pts[4 * i + 2], pts[4 * i + 3]};

@@ -47,9 +47,12 @@ SFM_HD void hartley(const float* x, const float* y, float& s, float& cx, float& 
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         float dx = x[i] - cx, dy = y[i] - cy;
-        d += sqrtf(fmaf(dx, dx, dy * dy));
+        d += sfm_sqrt_approx(fmaf(dx, dx, dy * dy));
     }
-    s = 11.3137085f / d;   // sqrt(2) / (d / 8)
+    // The similarity only conditions the solve: ANY scale is exact as long as normalisation and de-normalisation use the
+    // same one (they do), so hardware approximations (MUFU.RSQ / RCP, ~2 ulp) are free accuracy-wise and take ~150
+    // instructions and 18 slow-path branches out of every hypothesis.
+    s = 11.3137085f * sfm_rcp_approx(d);   // sqrt(2) / (d / 8)
 }
 
 // pts: the 8 sampled correspondences in normalised camera coordinates.
@@ -233,7 +236,9 @@ SFM_HD void chol8_factor(float k[8][8], Chol8& c) {
 #pragma unroll
         for (int m = 0; m < j; m++) d = fmaf(-c.l[j][m], c.l[j][m], d);
         c.ok = c.ok && (d > 0.0f);
-        float inv = 1.0f / sqrtf(fmaxf(d, 1e-30f));
+        // 2-ulp reciprocal square root: the factor only has to be a good preconditioner, the re-projections against the
+        // design rows in the callers remove what it leaves (same argument as for fp32 rounding in the factor itself)
+        float inv = sfm_rsqrt(fmaxf(d, 1e-30f));
         c.l[j][j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 8; i++) {
@@ -341,7 +346,7 @@ SFM_HD void solve_hypothesis_projector(const Corr* pts, float* E) {
         float n2 = e[0] * e[0];
 #pragma unroll
         for (int c = 1; c < 9; c++) n2 = fmaf(e[c], e[c], n2);
-        float inv = 1.0f / sqrtf(n2);
+        float inv = sfm_rsqrt(n2);          // keeps |e| ~ 1 between steps; the exact normalisation is project_essential's
 #pragma unroll
         for (int c = 0; c < 9; c++) e[c] *= inv;
     }
@@ -505,5 +510,39 @@ SFM_HD void sample_indices(unsigned long long seed, unsigned long long h, int n,
         idx[j] = cand;
     }
 }
+
+#if defined(__CUDACC__)
+// Loads the 8 sampled correspondences of hypothesis (pair b, global index hg).
+// A sample with an out-of-range or repeated index is degenerate: returns false.
+// COHERENT: the correspondences were written earlier in the SAME kernel (small.cu): read them through L2 (ld.global.cg)
+// instead of the non-coherent read-only path.
+template <bool COHERENT = false>
+__device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int n, const int32_t* __restrict__ idx_rows,
+                                            unsigned long long seed, long long hg, Corr* pts) {
+    int id[8];
+    if (idx_rows != nullptr) {
+        const int4* row = reinterpret_cast<const int4*>(idx_rows + 8 * hg);
+        int4 a = __ldg(row), b = __ldg(row + 1);
+        id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w;
+        id[4] = b.x; id[5] = b.y; id[6] = b.z; id[7] = b.w;
+    } else {
+        sample_indices(seed, (unsigned long long)hg, n, id);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        ok = ok && (id[i] >= 0) && (id[i] < n);
+#pragma unroll
+        for (int j = 0; j < i; j++) ok = ok && (id[i] != id[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int k = ok ? id[i] : 0;
+        float4 c = COHERENT ? __ldcg(corr + k) : __ldg(corr + k);
+        pts[i] = Corr{c.x, c.y, c.z, c.w};
+    }
+    return ok;
+}
+#endif
 
 }  // namespace sfmb200

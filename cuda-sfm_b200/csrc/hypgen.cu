@@ -15,35 +15,6 @@
 namespace sfmb200 {
 
 
-// Loads the 8 sampled correspondences of hypothesis (pair b, global index hg).
-// A sample with an out-of-range or repeated index is degenerate: returns false.
-__device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int n, const int32_t* __restrict__ idx_rows,
-                                            unsigned long long seed, long long hg, Corr* pts) {
-    int id[8];
-    if (idx_rows != nullptr) {
-        const int4* row = reinterpret_cast<const int4*>(idx_rows + 8 * hg);
-        int4 a = __ldg(row), b = __ldg(row + 1);
-        id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w;
-        id[4] = b.x; id[5] = b.y; id[6] = b.z; id[7] = b.w;
-    } else {
-        sample_indices(seed, (unsigned long long)hg, n, id);
-    }
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        ok = ok && (id[i] >= 0) && (id[i] < n);
-#pragma unroll
-        for (int j = 0; j < i; j++) ok = ok && (id[i] != id[j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        int k = ok ? id[i] : 0;
-        float4 c = __ldg(corr + k);
-        pts[i] = Corr{c.x, c.y, c.z, c.w};
-    }
-    return ok;
-}
-
 template <int THREADS, int MINB, int SYNC, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB)
 hypgen_kernel(DeviceState s, const int32_t* __restrict__ d_idx, long long idx_pair_stride, int H, int h_offset,

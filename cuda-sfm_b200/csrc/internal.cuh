@@ -140,6 +140,13 @@ void launch_export_ecand(const DeviceState& s, int pair, int H, float* d_out_Hx9
 void launch_export_X(const DeviceState& s, int pair, int image, float* d_out_3xN, cudaStream_t st);
 void launch_inlier_mask(const DeviceState& s, int pair, float thr, int model, unsigned char* d_mask, cudaStream_t st);
 
+// Fused single-launch path for small problems (small.cu): one thread-block cluster per pair.
+enum { SMALL_INGEST = 1, SMALL_ESTIMATE = 2, SMALL_POSE = 4, SMALL_TRI = 8 };
+int small_path_max_hypotheses();
+cudaError_t launch_small_path(const DeviceState& s, const float* d_px, const int32_t* d_idx, long long idx_pair_stride, int H,
+                              int h_offset, unsigned long long seed, float thr, int compat, int inliers_only, int mask,
+                              cudaStream_t st);
+
 // Programmatic dependent launch (sm_90+): a kernel launched with the attribute may become resident while its
 // predecessor in the stream drains; it must execute pdl_wait() before touching anything the predecessor wrote
 // (the wait returns once the predecessor grid has completed and its writes are visible).  pdl_trigger() lets the

@@ -1,0 +1,289 @@
+// Whole hot path of a SMALL problem in ONE launch: ingest -> hypothesis generation -> scoring + arg-max -> pose
+// candidates + cheirality -> triangulation, for pairs whose n x H is a few million evaluations or less - the
+// reference's real operating point (BASELINE config 1: the dino pair, ~2k correspondences, H = N/8 ~ 270).  At that
+// size the five stage kernels of the general path hold ~0.5 us of arithmetic and ~45 us of launch latency and
+// dependent-launch gaps (profiles/r01_dino_pipeline.md).
+//
+// One thread-block CLUSTER per pair (8 CTAs portable, 16 when the device allows it), 512 threads per CTA; the
+// stages are separated by hardware cluster barriers (barrier.cluster, sub-microsecond) instead of kernel
+// boundaries, and the data between stages (correspondences, candidates, counts: tens of KB) stays in L1 / L2.
+//   ingest    every thread normalises a strided share of the correspondences (same code as ingest_xy_kernel)
+//   hypgen    one hypothesis per thread, 32 per warp, warp k of the cluster = warp (k / C) of CTA (k % C): the first
+//             C warps sit on C different SMs, so at config-1 sizes every solve runs alone on its scheduler
+//             (the solve is a ~2k-instruction dependent chain: latency, not throughput)
+//   score     CTA r owns the hypotheses [r * Hc, (r + 1) * Hc); their scaled E sit in shared memory and are read as
+//             broadcasts, threads stride over the correspondences; counts by warp REDUX + shared atomics, the
+//             cluster's (count, ~index) key by one atomicMax per CTA
+//   pose      4 lanes of CTA 0: select + candidates + cheirality (same code as select_pose_choose_kernel)
+//   tri       every thread, strided (same solve as triangulate_kernel)
+// Every stage calls the SAME device functions as the general path (hyp_solver.cuh, sampson.cuh, geometry.cuh,
+// smallmat.cuh), so candidates, counts, winner, poses and points are bit-identical to it (tests/test_gpu_small.py).
+#include <cooperative_groups.h>
+
+#include "geometry.cuh"
+#include "hyp_solver.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sfmb200 {
+
+constexpr int SMALL_THREADS = 512;
+constexpr int SMALL_HC_MAX = 128;        // hypotheses per CTA kept in shared memory
+constexpr int SMALL_G = 4;               // hypotheses per register group in the scoring loop
+
+struct SmallArgs {
+    const float4* px;        // [B][n] pixel correspondences (SMALL_INGEST)
+    Mat9 kinv;
+    const int32_t* d_idx;    // sample rows or nullptr
+    long long idx_pair_stride;
+    unsigned long long seed;
+    int H, h_offset;
+    float thr;
+    int compat, inliers_only, mask;
+};
+
+__global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceState s, SmallArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = s.n, H = a.H;
+    const int stride = C * SMALL_THREADS;
+    __shared__ float sE[SMALL_HC_MAX][9];
+    __shared__ int sCnt[SMALL_HC_MAX];
+    __shared__ unsigned long long sKey;
+
+    if (rank == 0 && tid == 0 && (a.mask & SMALL_ESTIMATE)) s.best[b] = 0ull;
+
+    // ---- ingest ----
+    if (a.mask & SMALL_INGEST) {
+        for (int i = rank * SMALL_THREADS + tid; i < n; i += stride) {
+            const float4 p = __ldg(a.px + (size_t)b * n + i);
+            normalise_store(s, b, i, p.x, p.y, p.z, p.w, a.kinv);
+        }
+        cluster.sync();
+    }
+
+    if (a.mask & SMALL_ESTIMATE) {
+        // ---- hypothesis generation: block k of 32 hypotheses -> cluster warp k ----
+        const float4* corr = s.corr + (size_t)b * s.n_stride;
+        const int32_t* rows = a.d_idx ? a.d_idx + (size_t)b * a.idx_pair_stride : nullptr;
+        const int cluster_warps = C * (SMALL_THREADS / 32);
+        for (int k = warp * C + rank; k * 32 < H; k += cluster_warps) {
+            const int j = k * 32 + lane;
+            const bool live = j < H;
+            Corr pts[8];
+            float E[9];
+            const bool ok = load_sample<true>(corr, n, rows, a.seed + 0x632BE59BD9B4E019ull * (unsigned long long)b,
+                                        (long long)a.h_offset + (live ? j : 0), pts);
+            solve_hypothesis_projector(pts, E);
+            if (live) {
+                float* out = s.Ecand + (size_t)b * 9 * s.h_stride + j;
+#pragma unroll
+                for (int q = 0; q < 9; q++) out[(size_t)q * s.h_stride] = ok ? E[q] : 0.0f;
+            }
+        }
+        cluster.sync();
+
+        // ---- scoring: CTA `rank` owns hypotheses [h0, h1) ----
+        const int Hc = (H + C - 1) / C;
+        const int h0 = rank * Hc, h1 = min(H, h0 + Hc);
+        const int mine = max(h1 - h0, 0);
+        const ThrScale ts = make_thr_scale(a.thr);
+        const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
+        for (int t = tid; t < mine * 9; t += SMALL_THREADS) {
+            const int hh = t / 9, q = t - 9 * hh;
+            float v = __ldcg(Eb + (size_t)q * s.h_stride + h0 + hh);      // written by another SM before the barrier
+            if (q != 8) v *= thr_scale_factor(ts, q);                      // E~ = D E D (sampson.cuh), as score_kernel does
+            sE[hh][q] = v;
+        }
+        for (int t = tid; t < SMALL_HC_MAX; t += SMALL_THREADS) sCnt[t] = 0;
+        if (tid == 0) sKey = 0ull;
+        __syncthreads();
+        const float4* cs = s.corr_s + (size_t)b * s.n_stride;
+        for (int g0 = 0; g0 < mine; g0 += SMALL_G) {
+            float e[SMALL_G][9];
+            unsigned int cnt[SMALL_G];
+#pragma unroll
+            for (int g = 0; g < SMALL_G; g++) {
+                const int hh = min(g0 + g, mine - 1);
+#pragma unroll
+                for (int q = 0; q < 9; q++) e[g][q] = sE[hh][q];
+                cnt[g] = 0u;
+            }
+            for (int i = tid; i < n; i += SMALL_THREADS) {
+                const float4 p = __ldcg(cs + i);
+#pragma unroll
+                for (int g = 0; g < SMALL_G; g++) {
+                    const float d = sampson_unit_d(e[g], p.x, p.y, p.z, p.w);
+                    cnt[g] += __float_as_uint(d) >> 31;
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < SMALL_G; g++) {
+                const unsigned int w = __reduce_add_sync(0xFFFFFFFFu, cnt[g]);
+                if (lane == 0 && g0 + g < mine && w) atomicAdd(&sCnt[g0 + g], (int)w);
+            }
+        }
+        __syncthreads();
+        unsigned long long key = 0ull;
+        int* counts = s.counts + (size_t)b * s.h_stride;
+        for (int t = tid; t < mine; t += SMALL_THREADS) {
+            const int c = sCnt[t];
+            counts[h0 + t] = c;
+            const unsigned long long kk = ((unsigned long long)(unsigned)c << 32) |
+                                          (unsigned long long)(0xFFFFFFFFu - (unsigned)(a.h_offset + h0 + t));
+            key = kk > key ? kk : key;
+        }
+        if (mine > 0) {
+            if (key != 0ull) atomicMax(&sKey, key);
+            __syncthreads();
+            if (tid == 0 && sKey != 0ull) atomicMax(&s.best[b], sKey);
+        }
+        cluster.sync();
+    }
+
+    // ---- select (+ pose candidates + cheirality) : CTA 0, 4 lanes ----
+    if ((a.mask & (SMALL_ESTIMATE | SMALL_POSE)) && rank == 0 && warp == 0) {
+        const int c = lane;
+        bool pass = false;
+        if (c < 4) {
+            float E[9], P[16];
+            if (a.mask & SMALL_ESTIMATE) {
+                const unsigned long long packed = __ldcg(&s.best[b]);
+                const unsigned int hg = 0xFFFFFFFFu - (unsigned int)(packed & 0xFFFFFFFFull);
+                const int local = (int)hg - a.h_offset;
+                const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
+#pragma unroll
+                for (int k = 0; k < 9; k++) E[k] = (local >= 0 && local < s.h_stride) ? __ldcg(Eb + (size_t)k * s.h_stride + local) : 0.0f;
+                if (c == 0) {
+                    s.best_idx[b] = (int)hg;
+                    s.best_count[b] = (int)(packed >> 32);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = E[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; k++) E[k] = s.E[(size_t)b * 9 + k];
+            }
+            if (a.mask & SMALL_POSE) {
+                pose_candidate(E, c, a.compat, P);
+                if (a.compat) {
+                    const float4 c0 = __ldcg(s.corr + (size_t)b * s.n_stride);
+                    float Minv[16];
+                    pass = cheirality_compat(c0, P, Minv);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) P[i] = Minv[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) s.P[(size_t)b * 64 + 16 * c + i] = P[i];
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass) & 0xFu;
+        if (lane == 0 && (a.mask & SMALL_POSE) && a.compat) s.P_ind[b] = m ? 31 - __clz(m) : 0;      // last passing index (sfm.cu:284-297)
+    }
+    if (!(a.mask & SMALL_TRI)) return;
+    cluster.sync();
+
+    // ---- triangulation: same solve as triangulate_kernel ----
+    {
+        const float* Mg = s.P + (size_t)b * 64 + 16 * __ldcg(s.P_ind + b);
+        float M[12], e[9];
+#pragma unroll
+        for (int k = 0; k < 12; k++) M[k] = __ldcg(Mg + k);
+#pragma unroll
+        for (int k = 0; k < 9; k++) e[k] = __ldcg(s.E + (size_t)b * 9 + k);
+        const float4* corr = s.corr + (size_t)b * s.n_stride;
+        float* out = s.points + (size_t)b * 4 * s.n_stride;
+        const int rounds = (n + stride - 1) / stride;
+        for (int r = 0; r < rounds; r++) {
+            const int i = r * stride + rank * SMALL_THREADS + tid;
+            const bool inside = i < n;
+            const float4 pt = inside ? __ldcg(corr + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            bool keep[1] = {inside};
+            if (a.inliers_only) keep[0] = keep[0] && sampson_d(e, pt.x, pt.y, pt.z, pt.w, -a.thr) < 0.0f;
+            float x1[1] = {pt.x}, y1[1] = {pt.y}, aa[1][4], bb[1][4], v[1][4];
+            bool ok[1];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                aa[0][c] = fmaf(pt.z, M[8 + c], -M[c]);
+                bb[0][c] = fmaf(pt.w, M[8 + c], -M[4 + c]);
+            }
+            dlt_null_adjugate<1>(x1, y1, aa, bb, v, keep, ok);         // every lane calls (warp vote inside)
+            if (!inside) continue;
+            float X = 0.0f, Y = 0.0f, Z = 0.0f;
+            if (keep[0]) {
+                if (!ok[0]) {
+                    float A[16];
+                    dlt_matrix(pt.x, pt.y, pt.z, pt.w, M, A);
+                    null4<5>(A, v[0]);
+                }
+                dehomogenise(v[0], X, Y, Z);
+            }
+            out[i] = X;
+            out[(size_t)s.n_stride + i] = Y;
+            out[(size_t)2 * s.n_stride + i] = Z;
+            out[(size_t)3 * s.n_stride + i] = 1.0f;
+        }
+    }
+}
+
+// Largest cluster the device can co-schedule for this kernel: 16 (non-portable) or 8.
+static int small_cluster_size() {
+    static int cached = 0;
+    if (cached) return cached;
+    cached = 8;
+    if (cudaFuncSetAttribute(small_path_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16, 1, 1);
+        cfg.blockDim = dim3(SMALL_THREADS, 1, 1);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 16;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, small_path_kernel, &cfg) == cudaSuccess && clusters >= 1) cached = 16;
+    }
+    cudaGetLastError();
+    return cached;
+}
+
+int small_path_max_hypotheses() { return SMALL_HC_MAX * small_cluster_size(); }
+
+// mask: SMALL_INGEST | SMALL_ESTIMATE | SMALL_POSE | SMALL_TRI.  Returns cudaSuccess or the launch error.
+cudaError_t launch_small_path(const DeviceState& s, const float* d_px, const int32_t* d_idx, long long idx_pair_stride, int H,
+                              int h_offset, unsigned long long seed, float thr, int compat, int inliers_only, int mask,
+                              cudaStream_t st) {
+    SmallArgs a;
+    a.px = (const float4*)d_px;
+    for (int i = 0; i < 9; i++) a.kinv.v[i] = s.Kinv[i];
+    a.d_idx = d_idx;
+    a.idx_pair_stride = idx_pair_stride;
+    a.seed = seed;
+    a.H = H;
+    a.h_offset = h_offset;
+    a.thr = thr;
+    a.compat = compat;
+    a.inliers_only = inliers_only;
+    a.mask = mask;
+    const int C = small_cluster_size();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, s.B, 1);
+    cfg.blockDim = dim3(SMALL_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, small_path_kernel, s, a);
+}
+
+}  // namespace sfmb200

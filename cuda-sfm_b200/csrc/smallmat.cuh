@@ -69,6 +69,23 @@ SFM_HD float sfm_rsqrt(float x) {
 #endif
 }
 
+// sqrt(x) and 1/x from MUFU.RSQ / MUFU.RCP on the device (x >= 0; 0 -> 0), exact on the host.  For quantities whose
+// exact value does not matter (conditioning scales).
+SFM_HD float sfm_sqrt_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    return x > 0.0f ? x * rsqrtf(x) : 0.0f;
+#else
+    return sqrtf(x);
+#endif
+}
+SFM_HD float sfm_rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
+}
+
 // Givens pair (c, s) with c*a + s*b = r >= 0 and -s*a + c*b = 0.
 SFM_HD void givens(float a, float b, float& c, float& s) {
     float r2 = fmaf(a, a, b * b);
@@ -193,6 +210,85 @@ SFM_HD void svd3(const float* a, float* u, float* s, float* v) {
         }
 }
 
+// Orientation of the null direction as the REFERENCE's svd() returns it (SfM/svd.h:311-335).  Under the contract
+// a = u s v^T with u, v proper rotations an SVD keeps one discrete freedom: negating (u1, v1, u3, v3) - equivalently
+// the sign of v3 - changes nothing in a, u v^T or det, but it swaps W <-> W^T and the sign of the translation in
+// candidate_kernels (kernels.h:357-385), i.e. it permutes the four pose candidates 0 <-> 3, 1 <-> 2, and with them
+// the index choosePose reports (sfm.cu:284-297).  Which sign the reference gets is decided by the rotation path of
+// its SVD algorithm (McAdams, Selle, Tamstorf, Teran, Sifakis: "Computing the singular value decomposition of 3x3
+// matrices with minimal branching and elementary floating point operations", 2011): cyclic Jacobi on a^T a from the
+// identity over the pairs (0,1), (1,2), (2,0), 4 sweeps, each rotation taken from the half-angle estimate
+// (ch, sh) ~ (2 (s_pp - s_qq), s_pq), replaced by the fixed angle pi/8 when gamma sh^2 >= ch^2 (svd.h:120-215), then the
+// columns ordered by decreasing |a v_i| with negating swaps (svd.h:217-241).  This function replays that path on plain
+// 3x3 matrices for the one bit it decides and returns the third column of the resulting V; the decomposition itself
+// comes from svd3() (the replayed path is a 4-sweep approximation and is not used for values).  Checked against the
+// reference's own host svd() on 4,000 essential matrices: same orientation every time (tests/test_cpu_oracle.py).
+SFM_HD void reference_null_direction(const float* a, float* v3) {
+    const float gamma = 5.828427124746190f, cstar = 0.923879532511287f, sstar = 0.382683432365090f;
+    float S[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    mul33_AtB(a, a, S);
+#pragma unroll 1
+    for (int sweep = 0; sweep < 4; sweep++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int p = k, q = (k + 1) % 3, r = (k + 2) % 3;
+            float ch = 2.0f * (S[4 * p] - S[4 * q]), sh = S[3 * p + q];
+            const bool inner = gamma * sh * sh < ch * ch;
+            const float w = 1.0f / sqrtf(ch * ch + sh * sh);
+            ch = inner ? w * ch : cstar;
+            sh = inner ? w * sh : sstar;
+            const float c = ch * ch - sh * sh, sn = 2.0f * sh * ch;       // rotation [c -sn; sn c] in the (p, q) plane
+            const float spp = S[4 * p], sqq = S[4 * q], spq = S[3 * p + q], spr = S[3 * p + r], sqr = S[3 * q + r];
+            const float npp = c * (c * spp + sn * spq) + sn * (c * spq + sn * sqq);
+            const float npq = c * (-sn * spp + c * spq) + sn * (-sn * spq + c * sqq);
+            const float nqq = -sn * (-sn * spp + c * spq) + c * (-sn * spq + c * sqq);
+            const float npr = c * spr + sn * sqr, nqr = -sn * spr + c * sqr;
+            S[4 * p] = npp; S[4 * q] = nqq;
+            S[3 * p + q] = npq; S[3 * q + p] = npq;
+            S[3 * p + r] = npr; S[3 * r + p] = npr;
+            S[3 * q + r] = nqr; S[3 * r + q] = nqr;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float vp = V[3 * i + p], vq = V[3 * i + q];
+                V[3 * i + p] = c * vp + sn * vq;
+                V[3 * i + q] = -sn * vp + c * vq;
+            }
+        }
+    }
+    float B[9], rho[3];
+    mul33(a, V, B);
+#pragma unroll
+    for (int j = 0; j < 3; j++) rho[j] = B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j];
+#define SFM_REFSORT(i, j)                                                              \
+    if (rho[i] < rho[j]) {                                                             \
+        const float t = rho[i]; rho[i] = rho[j]; rho[j] = t;                           \
+        _Pragma("unroll") for (int row = 0; row < 3; row++) {                          \
+            const float vi = V[3 * row + i];                                           \
+            V[3 * row + i] = V[3 * row + j]; V[3 * row + j] = -vi;                     \
+        }                                                                              \
+    }
+    SFM_REFSORT(0, 1)
+    SFM_REFSORT(0, 2)
+    SFM_REFSORT(1, 2)
+#undef SFM_REFSORT
+    v3[0] = V[2]; v3[1] = V[5]; v3[2] = V[8];
+}
+// svd3() with the discrete freedom fixed the way the reference's svd() fixes it (see reference_null_direction).
+SFM_HD void svd3_reference_orientation(const float* a, float* u, float* s, float* v) {
+    svd3<5>(a, u, s, v);
+    float r[3];
+    reference_null_direction(a, r);
+    if (r[0] * v[2] + r[1] * v[5] + r[2] * v[8] < 0.0f) {
+#pragma unroll
+        for (int row = 0; row < 3; row++) {
+            u[3 * row] = -u[3 * row]; u[3 * row + 2] = -u[3 * row + 2];
+            v[3 * row] = -v[3 * row]; v[3 * row + 2] = -v[3 * row + 2];
+        }
+        // s = u^T a v: negating columns 0 and 2 of both sides leaves the diagonal and flips s01, s10, s12, s21 (all ~0)
+        s[1] = -s[1]; s[3] = -s[3]; s[5] = -s[5]; s[7] = -s[7];
+    }
+}
+
 // Closest essential matrix in the reference's sense (SfM/kernels.h:281-295):
 // E <- U diag(1,1,0) V^T.  The reference leaves the QR residue of S
 // off-diagonals in (<= 1e-6 typical); we use the exact diag.
@@ -200,7 +296,7 @@ SFM_HD void project_essential(float* E) {
     float n = 0.0f;
 #pragma unroll
     for (int i = 0; i < 9; i++) n = fmaf(E[i], E[i], n);
-    float inv = n > 0.0f ? 1.0f / sqrtf(n) : 0.0f;
+    float inv = n > 0.0f ? sfm_rsqrt(n) : 0.0f;      // conditioning only: the result U diag(1,1,0) V^T does not depend on the scale
     float En[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) En[i] = E[i] * inv;

@@ -54,8 +54,14 @@ typedef enum {
                                       accuracy, 3.5-4.4x faster on B200 (see hyp_solver.cuh) */
     SFMB200_OPT_PROFILE = 4,       /* 1: record CUDA events between the stages of run_device / run_host
                                       (the reference's unused PerformanceTimer, common.h:48-132, done per stage) */
-    SFMB200_OPT_BA_PERSISTENT = 6  /* bundle adjustment: 1 (default) all LM iterations of a round in one cooperative
+    SFMB200_OPT_BA_PERSISTENT = 6, /* bundle adjustment: 1 (default) all LM iterations of a round in one cooperative
                                       launch when the grid is resident; 0: two launches per iteration (same bits) */
+    SFMB200_OPT_SMALL_PATH = 7,    /* fused single-launch path for small problems (one thread-block cluster per pair runs
+                                      ingest, hypothesis generation, scoring + arg-max, poses, cheirality and
+                                      triangulation; same bits as the five-launch path): -1 (default) when n * H is at most
+                                      SFMB200_OPT_SMALL_PATH_EVALS, 0 never, 1 whenever eligible (projector solver,
+                                      H <= 128 * cluster size, reference pose semantics, no per-stage profiling) */
+    SFMB200_OPT_SMALL_PATH_EVALS = 8  /* the n * H limit of the automatic choice (default 6,000,000) */
 } sfmb200_option;
 
 const char* sfmb200_last_error(void);
@@ -248,6 +254,9 @@ int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms);
 
 /* ---- host-side small-matrix entry points (no GPU): svd.h facade + CPU tests ---- */
 void sfmb200_host_svd3(const float a[9], float u[9], float s[9], float v[9]);
+/* same decomposition with the one discrete freedom of the contract (the sign of v3, which orders the four pose
+ * candidates) fixed the way the reference's own svd() (SfM/svd.h:311-335) fixes it; used by the compat pose stage */
+void sfmb200_host_svd3_reference_orientation(const float a[9], float u[9], float s[9], float v[9]);
 void sfmb200_host_solve_hypothesis(const float pts[32], float E[9]);            /* 9x9 Jacobi eigensolve */
 void sfmb200_host_solve_hypothesis_projector(const float pts[32], float E[9]);  /* 8x8 Cholesky projector */
 void sfmb200_host_null4(const float A[16], float x[4]);

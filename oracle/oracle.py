@@ -353,6 +353,50 @@ def svd_rot(E: np.ndarray):
     return U, S, V
 
 
+def reference_null_direction(E: np.ndarray) -> np.ndarray:
+    """Third column of V as the reference's svd() (svd.h:311-335) ORIENTS it.  The SO(3) contract leaves one
+    discrete freedom - the sign of v3 (together with u3 and one in-plane column) - which permutes the pose
+    candidates 0<->3, 1<->2.  The reference's choice is decided by the rotation path of its algorithm (McAdams et
+    al. 2011): cyclic Jacobi on E^T E from the identity over the pairs (0,1), (1,2), (2,0), 4 sweeps, half-angle
+    estimate (ch, sh) ~ (2 (s_pp - s_qq), s_pq) or the fixed angle pi/8 when gamma sh^2 >= ch^2 (svd.h:120-215),
+    then columns ordered by decreasing |E v_i| with negating swaps (svd.h:217-241).  Replayed here in fp32 on plain
+    matrices for that one bit only; pinned against the reference's own host svd() in tests/test_cpu_oracle.py."""
+    f = np.float32
+    gamma, cstar, sstar = f(5.828427124746190), f(0.923879532511287), f(0.382683432365090)
+    A = np.asarray(E, f).reshape(3, 3)
+    S = (A.T @ A).astype(f)
+    V = np.eye(3, dtype=f)
+    for _ in range(4):
+        for p, q in ((0, 1), (1, 2), (2, 0)):
+            ch, sh = f(2) * (S[p, p] - S[q, q]), S[p, q]
+            if gamma * sh * sh < ch * ch:
+                w = f(1) / np.sqrt(ch * ch + sh * sh)
+                ch, sh = w * ch, w * sh
+            else:
+                ch, sh = cstar, sstar
+            c, sn = ch * ch - sh * sh, f(2) * sh * ch
+            Q = np.eye(3, dtype=f)
+            Q[p, p], Q[q, q], Q[p, q], Q[q, p] = c, c, -sn, sn
+            S = (Q.T @ S @ Q).astype(f)
+            V = (V @ Q).astype(f)
+    rho = list(((A @ V) ** 2).sum(axis=0))
+    for i, j in ((0, 1), (0, 2), (1, 2)):
+        if rho[i] < rho[j]:
+            rho[i], rho[j] = rho[j], rho[i]
+            vi = V[:, i].copy()
+            V[:, i], V[:, j] = V[:, j], -vi
+    return V[:, 2].astype(np.float64)
+
+
+def svd_reference_orientation(E: np.ndarray):
+    """svd_rot with v3 (and u3, and column 0 of both) oriented as the reference's svd() orients them."""
+    U, S, V = svd_rot(E)
+    if reference_null_direction(E) @ V[:, 2] < 0:
+        U[:, [0, 2]] = -U[:, [0, 2]]
+        V[:, [0, 2]] = -V[:, [0, 2]]
+    return U, S, V
+
+
 def det_reference_typo(a: np.ndarray) -> float:
     """det() exactly as written at svd.h:337-341 (third term a0*a3*a8)."""
     a = a.reshape(9)
@@ -364,8 +408,9 @@ def pose_candidates(E: np.ndarray, compat: bool = True) -> np.ndarray:
     (SURVEY Appendix A.4): P_i = [ (U W(^T) V^T)^T | +-u3 ; 0 0 0 1 ],
     W for i<2, W^T for i>=2, sign - for i in {0,2}, with the det-typo sign fix
     applied to V.  compat=False is textbook geometry for the x1^T E x2 = 0
-    convention: X2 = R X1 + t with E^T = [t]x R."""
-    U, _, V = svd_rot(E)
+    convention: X2 = R X1 + t with E^T = [t]x R.  In compat mode the candidates also come in the reference's ORDER
+    (svd_reference_orientation); match_candidates remains for comparing against arbitrary SVDs."""
+    U, _, V = svd_reference_orientation(E) if compat else svd_rot(E)
     W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], float)
     P = np.zeros((4, 4, 4))
     if compat:

@@ -113,7 +113,7 @@ def test_pose_candidates_compat_structure(O):
     rng = np.random.default_rng(0)
     E = O.project_essential(rng.normal(size=(3, 3)))
     Pc = O.pose_candidates(E, compat=True)
-    U, _, V = O.svd_rot(E)
+    U, _, V = O.svd_reference_orientation(E)
     for i in range(4):
         assert np.allclose(Pc[i][3], [0, 0, 0, 1])
         assert abs(abs(np.linalg.det(Pc[i][:3, :3])) - 1) < 1e-9
@@ -155,6 +155,51 @@ def test_reference_host_svd_contract(O, ref_lib):
         # Jacobi sweeps, hence the loose tolerance
         if sv[1] + sv[2] > 0.5:
             assert np.abs(U @ V.T - Uo @ Vo.T).max() < 2e-2
+
+
+def test_reference_svd_orientation_is_replayed(O, ref_lib, lib):
+    """The one discrete freedom of the reference's SVD contract - the sign of v3 / u3, which ORDERS the four pose
+    candidates - must come out as the reference's own host svd() (svd.h:311-335, compiled from the reference's
+    sources) produces it, in the oracle's restatement and in the library's compat SVD alike."""
+    rng = np.random.default_rng(3)
+    n, agree_o, agree_l = 3000, 0, 0
+    for t in range(n):
+        Q1, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        Q2, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        E = Q1 @ np.diag([1.0, 1.0, 0.0]) @ Q2.T                   # essential matrices, as normalizeE leaves them
+        if t % 3 == 1:
+            E = E + 1e-3 * rng.normal(size=(3, 3))
+        if t % 3 == 2:
+            E = rng.normal(size=(3, 3))
+        a = np.ascontiguousarray(E, np.float32).reshape(9)
+        ur, sr, vr, u, s, v = (np.zeros(9, np.float32) for _ in range(6))
+        ref_lib.ref_host_svd(P(a), P(ur), P(sr), P(vr))
+        Ur, Vr = ur.reshape(3, 3), vr.reshape(3, 3)
+        Uo, _, Vo = O.svd_reference_orientation(a.reshape(3, 3))
+        agree_o += bool(Vo[:, 2] @ Vr[:, 2] > 0 and Uo[:, 2] @ Ur[:, 2] > 0)
+        lib.raw("sfmb200_host_svd3_reference_orientation")(P(a), P(u), P(s), P(v))
+        U, S, V = u.reshape(3, 3), s.reshape(3, 3), v.reshape(3, 3)
+        agree_l += bool(V[:, 2] @ Vr[:, 2] > 0 and U[:, 2] @ Ur[:, 2] > 0)
+        assert np.abs(U @ S @ V.T - a.reshape(3, 3)).max() < 1e-5
+        assert abs(np.linalg.det(U.astype(np.float64)) - 1) < 1e-4 and abs(np.linalg.det(V.astype(np.float64)) - 1) < 1e-4
+    assert agree_o == n and agree_l == n, (agree_o, agree_l, n)
+    # ... and therefore the four candidates come in the reference's order: the oracle's candidates from the reference's
+    # own (U, V) equal the oracle's candidates from its own oriented SVD, index by index
+    for t in range(200):
+        Q1, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        Q2, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        a = np.ascontiguousarray(Q1 @ np.diag([1.0, 1.0, 0.0]) @ Q2.T, np.float32).reshape(9)
+        ur, sr, vr = (np.zeros(9, np.float32) for _ in range(3))
+        ref_lib.ref_host_svd(P(a), P(ur), P(sr), P(vr))
+        Ur, Vr = ur.reshape(3, 3).astype(np.float64), vr.reshape(3, 3).astype(np.float64)
+        if O.det_reference_typo(Ur @ Vr.T) < 0:
+            Vr = -Vr
+        W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], float)
+        Pm = O.pose_candidates(a.reshape(3, 3).astype(np.float64), compat=True)
+        for i in range(4):
+            Rm = Ur @ (W if i < 2 else W.T) @ Vr.T
+            sgn = -1.0 if i in (0, 2) else 1.0
+            assert np.abs(Pm[i, :3, :3] - Rm.T).max() < 5e-3 and np.abs(Pm[i, :3, 3] - sgn * Ur[:, 2]).max() < 5e-3, (t, i)
 
 
 def test_f32_mask_emulation_matches_c_port(O, oracle_c, scene_small):

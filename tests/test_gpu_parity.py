@@ -4,6 +4,8 @@ integer work -> bit-exact (counts: bit-exact against the fp32 port of the same
 fma tree, and inside the borderline band of the fp64 truth); floating-point
 stages carry their tolerance in the test."""
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import pytest
@@ -336,8 +338,10 @@ def test_error_paths(pkg, O, torch_cuda, scene_small):
     dpx = torch.from_numpy(scene_small["px"]).cuda()
     with pytest.raises(pkg.SfmError):
         h.set_points_xy(dpx, n=7)                    # fewer than 8 correspondences
+    with pytest.raises(ValueError):
+        h.set_points_xy(dpx, n=len(scene_small["px"]) + 1)   # tensor smaller than n says (caught by the Python mirror)
     with pytest.raises(pkg.SfmError):
-        h.set_points_xy(dpx, n=len(scene_small["px"]) + 1)   # above capacity
+        h.set_points_xy(torch.zeros((len(scene_small["px"]) + 1, 4), device="cuda"))   # above capacity (caught by the C ABI)
     h.set_points_xy(dpx)
     with pytest.raises(pkg.SfmError):
         h.estimate_e(101, 0, THR)                    # above max_hypotheses
@@ -352,7 +356,7 @@ def test_error_paths(pkg, O, torch_cuda, scene_small):
     h.close()
 
 
-def test_full_size_properties_config2(pkg, O, torch_cuda):
+def test_full_size_properties_config2(pkg, O, oracle_c, torch_cuda):
     """BASELINE config 2 (10k correspondences, 30 % outliers, 65,536 hypotheses):
     size-independent properties instead of an oracle run."""
     torch = torch_cuda
@@ -381,12 +385,29 @@ def test_full_size_properties_config2(pkg, O, torch_cuda):
     h.estimate_e(H, 1237, THR)
     c0 = h.get_inlier_counts()
     assert torch.equal(c, c0) and h.get_best()[0][0] == bi[0]
-    # a sampled sub-block against the fp32 port through torch (same fma tree not
-    # guaranteed in torch, so use the banded fp64 truth on 256 hypotheses)
-    x = O.normalise_points(sc["px"], Kinv)
-    sel = np.arange(0, H, 256)
-    cnt, amb = O.inlier_counts(E.cpu().numpy()[sel].astype(np.float64), x, THR, band=BAND)
-    assert np.all(np.abs(c.cpu().numpy()[sel] - cnt) <= amb)
+    # ALL 65,536 hypotheses: bit-exact against the fp32 port of the same fma tree, and against the fp64 truth inside
+    # the borderline band; how much of the band is actually used is recorded (profiles/r02_count_parity.md)
+    Enp, got = E.cpu().numpy(), c.cpu().numpy()
+    xg = gpu_x(h)
+    assert np.array_equal(got, counts_f32(oracle_c, Enp, xg))
+    c64, amb = counts_f64(oracle_c, Enp, xg)
+    diff = np.abs(got - c64)
+    assert np.all(diff <= amb)
+    rec = {"config": "BASELINE config 2: 10,000 correspondences x 65,536 hypotheses, seed 1237, thr 1e-6", "band_rel": BAND,
+           "hypotheses": int(H), "evaluations": int(H) * n, "sum_borderline": int(amb.sum()), "sum_abs_diff_vs_fp64": int(diff.sum()),
+           "max_abs_diff_vs_fp64": int(diff.max()), "hypotheses_with_any_diff": int((diff > 0).sum()),
+           "fp32_port_bit_exact": True, "winner_fp32": [int(bi[0]), int(bc[0])],
+           "winner_fp64": [int(np.argmax(c64)), int(c64.max())]}
+    for band in (1e-5, 1e-6):            # the band north_star's wording would imply: how many decisions fall outside it
+        cb, ab = np.zeros(H, np.int32), np.zeros(H, np.int32)
+        oracle_c.oracle_counts_f64(P(np.ascontiguousarray(Enp)), H, P(xg), n, C.c_double(THR), C.c_double(band), P(cb, ip), P(ab, ip))
+        rec[f"hypotheses_outside_band_{band:g}"] = int((np.abs(got - cb) > ab).sum())
+        rec[f"sum_borderline_band_{band:g}"] = int(ab.sum())
+    print("\ncount parity record:", json.dumps(rec))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "count_parity_config2.json"), "w") as f:
+        json.dump(rec, f, indent=1)
     h.close()
 
 
