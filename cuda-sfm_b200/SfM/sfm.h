@@ -47,6 +47,7 @@ namespace SfM {
 #define cuda_block_size 256
 class Image_pair {
     sfmb200_t* h_ = nullptr;
+    int sampler_ = 0;      // explicit-argument estimateE: 0 independent rows, 1 disjoint permutation
     int image_count;
     int num_points;
     static void check(int rc, const char* what) {
@@ -80,7 +81,18 @@ public:
     }
     // The reference draws H = N/8 disjoint samples from a std::shuffle seeded by
     // std::random_device (sfm.cu:95-104) and thresholds at 1e-6 (sfm.cu:220).
-    void estimateE() { estimateE(num_points / 8 > 0 ? num_points / 8 : 1, default_seed(), 1e-6f); }
+    // No arguments = exactly that: ONE permutation of the point indices cut into N/8 disjoint rows, drawn on the
+    // device (SFMB200_OPT_SAMPLER = 1), threshold 1e-6.  The overload below takes H, seed and threshold explicitly
+    // and samples every row independently unless setSampler(1) was called.
+    void estimateE() {
+        check(sfmb200_set_option(h_, SFMB200_OPT_SAMPLER, 1), "estimateE");
+        estimateE(num_points / 8 > 0 ? num_points / 8 : 1, default_seed(), 1e-6f);
+        check(sfmb200_set_option(h_, SFMB200_OPT_SAMPLER, sampler_), "estimateE");
+    }
+    void setSampler(int disjoint_permutation) {
+        sampler_ = disjoint_permutation ? 1 : 0;
+        check(sfmb200_set_option(h_, SFMB200_OPT_SAMPLER, sampler_), "setSampler");
+    }
     void computePosecandidates() {
         check(sfmb200_pose_candidates(h_), "computePosecandidates");
         check(sfmb200_synchronize(h_), "computePosecandidates");

@@ -86,8 +86,10 @@ SIGNATURES = {
     "sfmb200_host_null4": (None, [_f, _f]),
     "sfmb200_host_null4_fast": (C.c_int, [_f, _f]),
     "sfmb200_host_dlt_null": (C.c_int, [_f, _f]),
+    "sfmb200_host_dlt_null_power4": (None, [_f, _f]),
     "sfmb200_host_inv4": (C.c_int, [_f, _f]),
     "sfmb200_host_sample_indices": (None, [C.c_uint64, C.c_uint64, C.c_int, _i]),
+    "sfmb200_host_sample_indices_disjoint": (None, [C.c_uint64, C.c_uint64, C.c_int, _i]),
     # kernels.h facade wrappers (la_wrappers.cu)
     "sfmb200_la_mmul": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sfmb200_la_mmul_batched": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),

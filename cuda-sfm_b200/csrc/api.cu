@@ -266,6 +266,14 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
             h->hyp_solver = value;
             break;
         case SFMB200_OPT_BA_PERSISTENT: h->ba.persistent = value ? 1 : 0; break;
+        case SFMB200_OPT_SAMPLER:
+            if (value < 0 || value > 1) return fail(SFMB200_ERR_ARG, "sampler must be 0 (independent subsets) or 1 (disjoint permutation)%s");
+            h->s.sampler = value;
+            break;
+        case SFMB200_OPT_SCORE_METRIC:
+            if (value < 0 || value > 1) return fail(SFMB200_ERR_ARG, "score metric must be 0 (Sampson error) or 1 (symmetric epipolar distance)%s");
+            h->s.metric = value;
+            break;
         case SFMB200_OPT_SMALL_PATH:
             if (value < -1 || value > 1) return fail(SFMB200_ERR_ARG, "small path must be -1 (auto), 0 (never) or 1 (whenever eligible)%s");
             h->small_path = value;
@@ -418,11 +426,21 @@ static int ensure_scaled(sfmb200_handle* h, float scale) {
     return SFMB200_OK;
 }
 
+// Scoring launch of the essential-matrix model with the handle's metric: Sampson error (the tuned kernel family) or
+// symmetric epipolar distance (same kernel, MODEL = 2, in the three tile sizes).  h->plan must be set.
+static void score_essential(sfmb200_handle* h, const DeviceState& s, int H, int h_offset, float thr) {
+    if (s.metric == 0) launch_score(s, h->plan, H, h_offset, thr, h->stream);
+    else launch_score_symmetric(s, h->plan, H, h_offset, thr, h->stream);
+}
+static ScorePlan plan_essential(const sfmb200_handle* h, int n, int H) {
+    return h->s.metric == 0 ? make_score_plan(h->s.B, n, H, h->score_variant, h->sms) : make_score_plan_homography(h->s.B, n, H, h->sms);
+}
+
 // The fused single-launch path (small.cu) serves essential-matrix estimates with the projector solver whose
 // hypotheses fit one cluster's shared memory; `pose`: the call also runs the pose stage, which the fused kernel
 // implements in reference (compat) semantics only.  Not used while per-stage events are being recorded.
 static bool small_path_ok(const sfmb200_handle* h, int H, bool pose) {
-    if (h->small_path == 0 || h->profile || h->hyp_solver != 1 || h->s.skip != nullptr) return false;
+    if (h->small_path == 0 || h->profile || h->hyp_solver != 1 || h->s.skip != nullptr || h->s.metric != 0) return false;
     if (h->score_variant >= 0 && h->small_path != 1) return false;      // the caller asked for a specific scoring kernel
     if (pose && !h->compat) return false;
     if (H > small_path_max_hypotheses()) return false;
@@ -438,6 +456,8 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     if (H < 1 || H > h->s.h_max || h_begin < 0 || (long long)h_begin + H > (long long)H_total)
         return fail(SFMB200_ERR_ARG, "hypothesis slice out of range / above max_hypotheses%s");
     if (!(thr > 0.0f)) return fail(SFMB200_ERR_ARG, "threshold must be positive%s");
+    if (!d_idx && h->s.sampler == 1 && 8ll * H_total > (long long)h->s.n)
+        return fail(SFMB200_ERR_ARG, "the disjoint-permutation sampler needs 8 * H_total <= n (the reference uses H = N / 8)%s");
     h->H = H;
     h->h_begin = h_begin;
     h->thr = thr;
@@ -449,11 +469,11 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
         h->plan.variant = -2;      // reported by sfmb200_score_plan: the fused path
         h->launches += 1;
     } else {
-        h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant, h->sms);
+        h->plan = plan_essential(h, h->s.n, H);
         launch_hypgen(h->s, d_idx, (long long)H_total * 8, H, h_begin, seed, h->hyp_solver, h->stream);
         prof_mark(h, 2);
         CKL();
-        launch_score(h->s, h->plan, H, h_begin, thr, h->stream);
+        score_essential(h, h->s, H, h_begin, thr);
         prof_mark(h, 3);
         CKL();
         launch_select(h->s, h_begin, h->stream);
@@ -567,10 +587,10 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
     while (lo < H_max) {
         if (hi > H_max) hi = H_max;
         const int Hr = (int)(hi - lo);
-        h->plan = make_score_plan(s.B, s.n, Hr, h->score_variant, h->sms);
+        h->plan = plan_essential(h, s.n, Hr);
         launch_hypgen(s, d_idx, (long long)H_max * 8, Hr, (int)lo, seed, h->hyp_solver, h->stream, rounds > 0);
         CKL();
-        launch_score(s, h->plan, Hr, (int)lo, thr, h->stream);
+        score_essential(h, s, Hr, (int)lo, thr);
         CKL();
         launch_adaptive_decide(s, h->adapt, (int)lo, (int)hi, log1mp, hi >= H_max, h->stream);
         CKL();
@@ -913,11 +933,11 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
     h->h_begin = 0;
     h->thr = thr;
     if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;     // no-op after run_device / run_host's own ingest
-    h->plan = make_score_plan(h->s.B, h->s.n, H, h->score_variant, h->sms);
+    h->plan = plan_essential(h, h->s.n, H);
     launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->hyp_solver, h->stream);
     prof_mark(h, 2);
     CKL();
-    launch_score(h->s, h->plan, H, 0, thr, h->stream);
+    score_essential(h, h->s, H, 0, thr);
     prof_mark(h, 3);
     CKL();
     launch_select_pose_choose(h->s, 0, h->compat, h->stream);

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_init_kernel(DeviceState s, BASt
         const float* in = s.points + (size_t)b * 4 * s.n_stride;
         const float X = in[i], Y = in[(size_t)s.n_stride + i], Z = in[(size_t)2 * s.n_stride + i];
         const float z2 = fmaf(sM[8], X, fmaf(sM[9], Y, fmaf(sM[10], Z, sM[11])));
-        act = sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f && isfinite(X) && isfinite(Y) && isfinite(Z) && Z > 0.0f && z2 > 0.0f;
+        act = epipolar_d(s.metric, sE, p.x, p.y, p.z, p.w, -thr) < 0.0f && isfinite(X) && isfinite(Y) && isfinite(Z) && Z > 0.0f && z2 > 0.0f;
         float* out = ba.pts + (size_t)b * 6 * s.n_stride;
         out[i] = X;
         out[(size_t)s.n_stride + i] = Y;
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(BA_THREADS) ba_count_kernel(DeviceState s, BAS
     bool inl = false;
     if (i < s.n) {
         const float4 p = s.corr[(size_t)b * s.n_stride + i];
-        inl = sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f;
+        inl = epipolar_d(s.metric, sE, p.x, p.y, p.z, p.w, -thr) < 0.0f;
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, inl);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));

@@ -43,7 +43,7 @@ __device__ __forceinline__ bool track_in_pair(const DeviceState& s, int b, const
     const float* in = s.points + (size_t)b * 4 * s.n_stride;
     X[0] = in[i]; X[1] = in[(size_t)s.n_stride + i]; X[2] = in[(size_t)2 * s.n_stride + i];
     z2 = fmaf(v.M[8], X[0], fmaf(v.M[9], X[1], fmaf(v.M[10], X[2], v.M[11])));
-    return sampson_d(v.E, p.x, p.y, p.z, p.w, -thr) < 0.0f && isfinite(X[0]) && isfinite(X[1]) && isfinite(X[2]) &&
+    return epipolar_d(s.metric, v.E, p.x, p.y, p.z, p.w, -thr) < 0.0f && isfinite(X[0]) && isfinite(X[1]) && isfinite(X[2]) &&
            X[2] > 0.0f && z2 > 0.0f;
 }
 // log depth ratio of track i between pairs b-1 and b; false when the track does not link them

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) choose_pose_vote_kernel(DeviceState s, fl
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += gridDim.x * blockDim.x) {
         float4 p = corr[i];
-        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr) >= 0.0f) continue;
+        if (epipolar_d(s.metric, sE, p.x, p.y, p.z, p.w, -thr) >= 0.0f) continue;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             float A[16], v[4];
@@ -300,9 +300,10 @@ void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_
 // batched 4x4 cusolver gesvdj that writes U, S and V for every point), de-homogenised into the reference's
 // 4xN SoA.  HBM roofline: 16 B read + 16 B written per point.
 // One thread solves PTS points that lie THREADS apart (every load / store is warp-coalesced); the null vector
-// comes from the adjugate power iteration dlt_null_adjugate (smallmat.cuh), which exploits camera 1 = I4; the
-// pose and E are read through uniform __ldg (one L1 line for the whole CTA), so there is no shared memory and
-// no barrier.  inliers_only: points failing the Sampson test of the selected E get (0,0,0,1).
+// comes from four power-iteration steps on the adjugate (dlt_null_power4, smallmat.cuh), which exploits camera 1 = I4
+// and needs no convergence bookkeeping; the pose and E are read through uniform __ldg (one L1 line for the whole
+// CTA), so there is no shared memory and no barrier.  inliers_only: points failing the Sampson test of the selected E
+// get (0,0,0,1).
 // ---------------------------------------------------------------------------
 #ifndef SFMB200_TRI_PTS
 #define SFMB200_TRI_PTS 2
@@ -313,6 +314,7 @@ void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_
 constexpr int TRI_THREADS = SFMB200_TRI_THREADS;
 template <int PTS, bool INLIERS_ONLY>
 __global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(DeviceState s, float thr) {
+    static_assert(PTS == 1 || PTS == 2, "one point per thread, or two in packed f32x2 arithmetic");
     pdl_wait();
     const int b = blockIdx.y;
     const float* Mg = s.P + (size_t)b * 64 + 16 * __ldg(s.P_ind + b);
@@ -321,8 +323,8 @@ __global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(DeviceState s,
     for (int k = 0; k < 12; k++) M[k] = __ldg(Mg + k);
     const int base = blockIdx.x * (TRI_THREADS * PTS) + threadIdx.x;
     const float4* corr = s.corr + (size_t)b * s.n_stride;
-    float x1[PTS], y1[PTS], a[PTS][4], bb[PTS][4], v[PTS][4];
-    bool keep[PTS], ok[PTS];
+    float v[PTS][4];
+    bool keep[PTS];
     float4 pt[PTS];
 #pragma unroll
     for (int p = 0; p < PTS; p++) {
@@ -331,41 +333,44 @@ __global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(DeviceState s,
     }
 #pragma unroll
     for (int p = 0; p < PTS; p++) {
-        const int i = base + p * TRI_THREADS;
-        keep[p] = i < s.n;
+        keep[p] = base + p * TRI_THREADS < s.n;
         if constexpr (INLIERS_ONLY) {
             float e[9];
 #pragma unroll
             for (int k = 0; k < 9; k++) e[k] = __ldg(s.E + (size_t)b * 9 + k);
-            keep[p] = keep[p] && sampson_d(e, pt[p].x, pt[p].y, pt[p].z, pt[p].w, -thr) < 0.0f;
-        }
-        x1[p] = pt[p].x; y1[p] = pt[p].y;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            a[p][c] = fmaf(pt[p].z, M[8 + c], -M[c]);           // compute_linear_triangulation_A, kernels.h:387-431
-            bb[p][c] = fmaf(pt[p].w, M[8 + c], -M[4 + c]);
+            keep[p] = keep[p] && epipolar_d(s.metric, e, pt[p].x, pt[p].y, pt[p].z, pt[p].w, -thr) < 0.0f;
         }
     }
-    // every lane makes the call (the iteration votes across the warp to leave early); idle points are not live
-#ifdef SFMB200_TRI_ITERS      // experiment: <min, max> iterations of the null-vector solve
-    dlt_null_adjugate<PTS, true, SFMB200_TRI_ITERS>(x1, y1, a, bb, v, keep, ok);
-#else
-    dlt_null_adjugate<PTS>(x1, y1, a, bb, v, keep, ok);
-#endif
+    // rows 2, 3 of the DLT matrix (compute_linear_triangulation_A, kernels.h:387-431), then the null vector
+    if constexpr (PTS == 2) {
+        const float2 x1 = make_float2(pt[0].x, pt[1].x), y1 = make_float2(pt[0].y, pt[1].y);
+        const float2 x2 = make_float2(pt[0].z, pt[1].z), y2 = make_float2(pt[0].w, pt[1].w);
+        float2 a[4], bb[4], vv[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float2 m2 = make_float2(M[8 + c], M[8 + c]);
+            a[c] = __ffma2_rn(x2, m2, make_float2(-M[c], -M[c]));
+            bb[c] = __ffma2_rn(y2, m2, make_float2(-M[4 + c], -M[4 + c]));
+        }
+        dlt_null_power4_lanes<LaneF2>(x1, y1, a, bb, vv);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { v[0][c] = vv[c].x; v[1][c] = vv[c].y; }
+    } else {
+        float a[4], bb[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            a[c] = fmaf(pt[0].z, M[8 + c], -M[c]);
+            bb[c] = fmaf(pt[0].w, M[8 + c], -M[4 + c]);
+        }
+        dlt_null_power4_lanes<LaneF1>(pt[0].x, pt[0].y, a, bb, v[0]);
+    }
     float* out = s.points + (size_t)b * 4 * s.n_stride;
 #pragma unroll
     for (int p = 0; p < PTS; p++) {
         const int i = base + p * TRI_THREADS;
         if (i >= s.n) continue;
         float X = 0.0f, Y = 0.0f, Z = 0.0f;
-        if (keep[p]) {
-            if (!ok[p]) {                                        // the two smallest singular values nearly coincide: Jacobi
-                float A[16];
-                dlt_matrix(pt[p].x, pt[p].y, pt[p].z, pt[p].w, M, A);
-                null4<5>(A, v[p]);
-            }
-            dehomogenise(v[p], X, Y, Z);
-        }
+        if (keep[p]) dehomogenise(v[p], X, Y, Z);
         out[i] = X;
         out[(size_t)s.n_stride + i] = Y;
         out[(size_t)2 * s.n_stride + i] = Z;
@@ -408,7 +413,7 @@ __global__ void vbo_colour_kernel(DeviceState s, int pair, float4* pos, float4* 
 #pragma unroll
         for (int k = 0; k < 9; k++) e[k] = s.E[(size_t)pair * 9 + k];
         const float4 p = s.corr[(size_t)pair * s.n_stride + i];
-        const bool inl = sampson_d(e, p.x, p.y, p.z, p.w, -thr) < 0.0f;
+        const bool inl = epipolar_d(s.metric, e, p.x, p.y, p.z, p.w, -thr) < 0.0f;
         c = inl ? make_float4(0.0f, 1.0f, 0.0f, 1.0f) : make_float4(1.0f, 0.0f, 0.0f, 1.0f);
     } else if (mode == 2) {
         if (Z > 0.0f && z_far > z_near) {
@@ -462,7 +467,7 @@ __global__ void inlier_mask_kernel(DeviceState s, int pair, float thr, int model
 #pragma unroll
     for (int k = 0; k < 9; k++) e[k] = s.E[(size_t)pair * 9 + k];
     float4 p = s.corr[(size_t)pair * s.n_stride + i];
-    float d = model == 0 ? sampson_d(e, p.x, p.y, p.z, p.w, -thr) : homography_d(e, p.x, p.y, p.z, p.w, -thr);
+    float d = model == 0 ? epipolar_d(s.metric, e, p.x, p.y, p.z, p.w, -thr) : homography_d(e, p.x, p.y, p.z, p.w, -thr);
     mask[i] = d < 0.0f ? 1 : 0;
 }
 void launch_inlier_mask(const DeviceState& s, int pair, float thr, int model, unsigned char* d_mask, cudaStream_t st) {

@@ -33,11 +33,25 @@ int sfmb200_host_null4_fast(const float A[16], float x[4]) { return null4_invers
 
 int sfmb200_host_dlt_null(const float A[16], float x[4]) { return dlt_null_adjugate1(A, x) ? 0 : 1; }
 
+void sfmb200_host_dlt_null_power4(const float A[16], float x[4]) {
+    const float x1[1] = {A[2]}, y1[1] = {A[6]};
+    float a[1][4], b[1][4], out[1][4];
+    for (int c = 0; c < 4; c++) { a[0][c] = A[8 + c]; b[0][c] = A[12 + c]; }
+    dlt_null_power4<1>(x1, y1, a, b, out);
+    for (int c = 0; c < 4; c++) x[c] = out[0][c];
+}
+
 int sfmb200_host_inv4(const float m[16], float out[16]) { return inv4(m, out) ? 0 : -1; }
 
 void sfmb200_host_sample_indices(uint64_t seed, uint64_t h, int n, int32_t idx[8]) {
     int tmp[8];
     sample_indices(seed, h, n, tmp);
+    for (int i = 0; i < 8; i++) idx[i] = tmp[i];
+}
+
+void sfmb200_host_sample_indices_disjoint(uint64_t seed, uint64_t h, int n, int32_t idx[8]) {
+    int tmp[8];
+    sample_indices_disjoint(seed, h, n, tmp);
     for (int i = 0; i < 8; i++) idx[i] = tmp[i];
 }
 

@@ -511,6 +511,45 @@ SFM_HD void sample_indices(unsigned long long seed, unsigned long long h, int n,
     }
 }
 
+// The reference's sampling scheme (sfm.cu:95-104): ONE random permutation of the point indices cut into H = N / 8
+// DISJOINT groups of 8, so no correspondence is used by two hypotheses (SFMB200_OPT_SAMPLER = 1).  The reference
+// shuffles on the host (std::shuffle + std::random_device) and uploads the rows; here row h is computed where it is
+// needed from a keyed permutation of [0, n) - a 4-round Feistel network over 2 * half bits (2^(2 half) >= n) with cycle
+// walking - so any hypothesis slice regenerates on any GPU, and the oracle mirrors it bit for bit
+// (oracle.py: sample_indices_disjoint).  Needs 8 * H_total <= n.
+SFM_HD unsigned int perm_mix(unsigned int v, unsigned int key) {
+    v ^= key;
+    v *= 0x85EBCA6Bu;
+    v ^= v >> 13;
+    v *= 0xC2B2AE35u;
+    v ^= v >> 16;
+    return v;
+}
+SFM_HD void sample_indices_disjoint(unsigned long long seed, unsigned long long h, int n, int* idx) {
+    const unsigned long long k0 = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ull), k1 = splitmix64(k0);
+    const unsigned int key[4] = {(unsigned int)k0, (unsigned int)(k0 >> 32), (unsigned int)k1, (unsigned int)(k1 >> 32)};
+    int bits = 1;
+    while ((1ll << bits) < (long long)n) bits++;
+    const int half = (bits + 1) / 2;
+    const unsigned int mask = (1u << half) - 1u;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+        unsigned int x = (unsigned int)(8ull * h + (unsigned long long)j);
+        if (x >= (unsigned int)n) { idx[j] = -1; continue; }          // beyond the permutation: a degenerate row
+        do {
+            unsigned int L = x >> half, R = x & mask;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const unsigned int t = L ^ (perm_mix(R, key[r]) & mask);
+                L = R;
+                R = t;
+            }
+            x = (L << half) | R;
+        } while (x >= (unsigned int)n);
+        idx[j] = (int)x;
+    }
+}
+
 #if defined(__CUDACC__)
 // Loads the 8 sampled correspondences of hypothesis (pair b, global index hg).
 // A sample with an out-of-range or repeated index is degenerate: returns false.
@@ -518,13 +557,15 @@ SFM_HD void sample_indices(unsigned long long seed, unsigned long long h, int n,
 // instead of the non-coherent read-only path.
 template <bool COHERENT = false>
 __device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int n, const int32_t* __restrict__ idx_rows,
-                                            unsigned long long seed, long long hg, Corr* pts) {
+                                            unsigned long long seed, long long hg, Corr* pts, int sampler = 0) {
     int id[8];
     if (idx_rows != nullptr) {
         const int4* row = reinterpret_cast<const int4*>(idx_rows + 8 * hg);
         int4 a = __ldg(row), b = __ldg(row + 1);
         id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w;
         id[4] = b.x; id[5] = b.y; id[6] = b.z; id[7] = b.w;
+    } else if (sampler == 1) {
+        sample_indices_disjoint(seed, (unsigned long long)hg, n, id);
     } else {
         sample_indices(seed, (unsigned long long)hg, n, id);
     }

@@ -52,6 +52,9 @@ struct DeviceState {
     float* points;      // [B][4][n_stride] SoA (x,y,z,1), the reference's d_final_points layout
     int* tri_count;     // [B] points triangulated in front of both cameras (diagnostic)
     int* vote;          // [B][8] cheirality votes of the four candidates + ticket (choose_pose_vote_kernel)
+    int sampler;        // device-drawn sample rows: 0 independent 8-subsets per hypothesis, 1 one permutation cut into disjoint
+                        // groups of 8 (the reference's scheme, sfm.cu:95-104)
+    int metric;         // inlier test of the essential-matrix model: 0 Sampson error (default), 1 symmetric epipolar distance
     const int* skip;    // adaptive termination: when non-null and *skip != 0 the hypgen / score kernels of
                         // the remaining rounds return at once (set by adaptive_decide_kernel); else nullptr
 };
@@ -125,6 +128,7 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override, int sms);
 int score_num_variants();
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
 void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st);
+void launch_score_symmetric(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st);
 ScorePlan make_score_plan_homography(int B, int n, int H, int sms);
 void launch_select(const DeviceState& s, int h_offset, cudaStream_t st);
 void launch_regen_best(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride,

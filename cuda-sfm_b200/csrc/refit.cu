@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_eval_kernel(DeviceState s
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = blockIdx.x * REFIT_THREADS + threadIdx.x; i < s.n; i += gridDim.x * REFIT_THREADS) {
         float4 p = corr[i];
-        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr) < 0.0f) m[NMOM] += 1.0f;
-        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
+        if (epipolar_d(s.metric, sE, p.x, p.y, p.z, p.w, -thr) < 0.0f) m[NMOM] += 1.0f;
+        if (epipolar_d(s.metric, sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
             m[0] += 1.0f;
             m[1] += p.x; m[2] += p.y; m[3] += p.z; m[4] += p.w;
             m[5] += fmaf(p.x, p.x, p.y * p.y);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_solve_kernel(DeviceState 
     const float4* corr = s.corr + (size_t)b * s.n_stride;
     for (int i = blockIdx.x * REFIT_THREADS + threadIdx.x; i < s.n; i += gridDim.x * REFIT_THREADS) {
         float4 p = corr[i];
-        if (sampson_d(sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
+        if (epipolar_d(s.metric, sE, p.x, p.y, p.z, p.w, -thr_fit) < 0.0f) {
             float x1 = sT[0] * (p.x - sT[1]), y1 = sT[0] * (p.y - sT[2]);
             float x2 = sT[3] * (p.z - sT[4]), y2 = sT[3] * (p.w - sT[5]);
             float a[9] = {x1 * x2, x1 * y2, x1, y1 * x2, y1 * y2, y1, x2, y2, 1.0f};

@@ -282,7 +282,7 @@ score_kernel(DeviceState s, int H, int h_offset, int T, long long total_units, i
 #pragma unroll
                 for (int q = 0; q < 9; q++) {
                     float v = valid ? __ldg(Eb + (size_t)q * s.h_stride + h) : 0.0f;
-                    if (MODEL == 0 && q != 8) v *= thr_scale_factor(ts, q);      // E~ = D E D (sampson.cuh)
+                    if (MODEL != 1 && q != 8) v *= thr_scale_factor(ts, q);      // E~ = D E D (sampson.cuh)
                     if constexpr (PACKED) {
                         if (j & 1) e2[j / 2][q].y = v; else e2[j / 2][q].x = v;
                     } else {
@@ -378,7 +378,7 @@ score_const_kernel(DeviceState s, int b, int chunk, int last_np, int arrivals, i
 #pragma unroll
         for (int k = 0; k < 9; k++) {
             float v = valid ? __ldg(Eb + (size_t)k * s.h_stride + h) : 0.0f;
-            if (MODEL == 0 && k != 8) v *= thr_scale_factor(ts, k);      // E~ = D E D (sampson.cuh)
+            if (MODEL != 1 && k != 8) v *= thr_scale_factor(ts, k);      // E~ = D E D (sampson.cuh)
             e[j][k] = v;
         }
         cnt[j] = 0u;
@@ -553,20 +553,29 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override, int sms) {
 ScorePlan make_score_plan_homography(int B, int n, int H, int sms) {
     return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9), sms);     // tiles of 2048 / 512 / 256 hypotheses
 }
-void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st) {
+// The other two models (homography transfer error; symmetric epipolar distance) in the three tile sizes of
+// make_score_plan_homography.
+template <int MODEL>
+static void launch_score_model(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {
     const int v = plan.variant;
     if (v == kConstVariant) {
-        launch_score_const<1>(s, plan, H, h_offset, thr2, st);
+        launch_score_const<MODEL>(s, plan, H, h_offset, thr, st);
         return;
     }
     const bool big = kVariants[v].hpt * kVariants[v].threads >= 2048, mid = kVariants[v].hpt * kVariants[v].threads >= 512;
     if (big) {
-        score_kernel<8, true, 256, 1, 1><<<plan.ctas, 256, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr2);
+        score_kernel<8, true, 256, 1, MODEL><<<plan.ctas, 256, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr);
     } else if (mid) {
-        score_kernel<4, true, 128, 1, 1><<<plan.ctas, 128, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr2);
+        score_kernel<4, true, 128, 1, MODEL><<<plan.ctas, 128, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr);
     } else {
-        score_kernel<2, false, 128, 1, 1><<<plan.ctas, 128, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr2);
+        score_kernel<2, false, 128, 1, MODEL><<<plan.ctas, 128, 0, st>>>(s, H, h_offset, plan.tiles, plan.total_units, plan.n_units, thr);
     }
+}
+void launch_score_homography(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr2, cudaStream_t st) {
+    launch_score_model<1>(s, plan, H, h_offset, thr2, st);
+}
+void launch_score_symmetric(const DeviceState& s, ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {
+    launch_score_model<2>(s, plan, H, h_offset, thr, st);
 }
 
 void launch_score(const DeviceState& s, const ScorePlan& plan, int H, int h_offset, float thr, cudaStream_t st) {

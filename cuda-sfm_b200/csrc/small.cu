@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             Corr pts[8];
             float E[9];
             const bool ok = load_sample<true>(corr, n, rows, a.seed + 0x632BE59BD9B4E019ull * (unsigned long long)b,
-                                        (long long)a.h_offset + (live ? j : 0), pts);
+                                        (long long)a.h_offset + (live ? j : 0), pts, s.sampler);
             solve_hypothesis_projector(pts, E);
             if (live) {
                 float* out = s.Ecand + (size_t)b * 9 * s.h_stride + j;
@@ -202,25 +202,17 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             const bool inside = i < n;
             const float4 pt = inside ? __ldcg(corr + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             bool keep[1] = {inside};
-            if (a.inliers_only) keep[0] = keep[0] && sampson_d(e, pt.x, pt.y, pt.z, pt.w, -a.thr) < 0.0f;
+            if (a.inliers_only) keep[0] = keep[0] && epipolar_d(s.metric, e, pt.x, pt.y, pt.z, pt.w, -a.thr) < 0.0f;
             float x1[1] = {pt.x}, y1[1] = {pt.y}, aa[1][4], bb[1][4], v[1][4];
-            bool ok[1];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 aa[0][c] = fmaf(pt.z, M[8 + c], -M[c]);
                 bb[0][c] = fmaf(pt.w, M[8 + c], -M[4 + c]);
             }
-            dlt_null_adjugate<1>(x1, y1, aa, bb, v, keep, ok);         // every lane calls (warp vote inside)
+            dlt_null_power4<1>(x1, y1, aa, bb, v);
             if (!inside) continue;
             float X = 0.0f, Y = 0.0f, Z = 0.0f;
-            if (keep[0]) {
-                if (!ok[0]) {
-                    float A[16];
-                    dlt_matrix(pt.x, pt.y, pt.z, pt.w, M, A);
-                    null4<5>(A, v[0]);
-                }
-                dehomogenise(v[0], X, Y, Z);
-            }
+            if (keep[0]) dehomogenise(v[0], X, Y, Z);
             out[i] = X;
             out[(size_t)s.n_stride + i] = Y;
             out[(size_t)2 * s.n_stride + i] = Z;

@@ -577,6 +577,83 @@ SFM_HD void dlt_null_adjugate(const float* x1, const float* y1, const float (*a)
         ok[p] = diff2[p] < 1e-10f;      // false also for NaN
     }
 }
+// The same null vector for the triangulation kernel, where instruction count is everything (1M points, 32 B of HBM traffic
+// each: ~5 us of memory time): no convergence bookkeeping, no normalisation inside, no warp vote.  With the adjugate
+// columns k_j as above, S = sum_j k_j k_j^T / trace is formed once (10 entries, largest eigenvalue in [1/4, 1]) and
+//     v = S (S (S (S (k3 / |k|))))        = FOUR power-iteration steps from the start vector k3
+// costs 40 + 64 FMAs; only the direction of v matters (the caller de-homogenises), so nothing is normalised on the way.
+// Error after four steps: (sigma_4 / sigma_3)^8 of the start error - inliers are exact to fp32 rounding after the first,
+// 99.99 % of gross outliers are within 1e-3 (oracle comparison in tests/test_cpu_hostlogic.py); a point whose two smallest
+// singular values nearly coincide has no well-defined null vector in the reference's SVD either.  Degenerate input
+// (all cofactors zero or non-finite) gives v = 0, which de-homogenises to the reference's (0,0,0,1) (kernels.h:439).
+// Written once over a value type: float (one point), or float2 on the device = TWO points per thread in packed
+// FFMA2 / FMUL2 / FADD2 (sm_100): the kernel is bound by issue slots, not by the FMA pipe, and a packed instruction
+// does two points' worth of work in one slot.  Lane-wise the packed form is the scalar fma tree, bit for bit.
+struct LaneF1 {
+    typedef float T;
+    static SFM_HD T fma(T a, T b, T c) { return fmaf(a, b, c); }
+    static SFM_HD T mul(T a, T b) { return a * b; }
+    static SFM_HD T add(T a, T b) { return a + b; }
+    static SFM_HD T neg(T a) { return -a; }
+    static SFM_HD T rsqrt_scale(T tr) { return (tr > 0.0f && tr < 3.0e38f) ? sfm_rsqrt(tr) : 0.0f; }
+};
+#if defined(__CUDACC__)
+struct LaneF2 {
+    typedef float2 T;
+    static __device__ __forceinline__ T fma(T a, T b, T c) { return __ffma2_rn(a, b, c); }
+    static __device__ __forceinline__ T mul(T a, T b) { return __fmul2_rn(a, b); }
+    static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
+    static __device__ __forceinline__ T neg(T a) { return make_float2(-a.x, -a.y); }
+    static __device__ __forceinline__ T rsqrt_scale(T tr) { return make_float2(LaneF1::rsqrt_scale(tr.x), LaneF1::rsqrt_scale(tr.y)); }
+};
+#endif
+template <class L>
+SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const typename L::T* a, const typename L::T* b, typename L::T* v) {
+    typedef typename L::T T;
+    T k[4][4];
+    const T na3 = L::neg(a[3]), nb3 = L::neg(b[3]);
+    k[3][0] = L::mul(na3, x1); k[3][1] = L::mul(na3, y1); k[3][2] = na3; k[3][3] = L::fma(a[0], x1, L::fma(a[1], y1, a[2]));
+    k[2][0] = L::mul(nb3, x1); k[2][1] = L::mul(nb3, y1); k[2][2] = nb3; k[2][3] = L::fma(b[0], x1, L::fma(b[1], y1, b[2]));
+    const T m01 = L::fma(a[0], b[1], L::neg(L::mul(a[1], b[0]))), m02 = L::fma(a[0], b[2], L::neg(L::mul(a[2], b[0])));
+    const T m03 = L::fma(a[0], b[3], L::neg(L::mul(a[3], b[0]))), m12 = L::fma(a[1], b[2], L::neg(L::mul(a[2], b[1])));
+    const T m13 = L::fma(a[1], b[3], L::neg(L::mul(a[3], b[1]))), m23 = L::fma(a[2], b[3], L::neg(L::mul(a[3], b[2])));
+    k[0][0] = L::neg(L::fma(y1, m13, m23)); k[0][1] = L::mul(y1, m03); k[0][2] = m03; k[0][3] = L::neg(L::fma(y1, m01, m02));
+    k[1][0] = L::neg(L::mul(x1, m13)); k[1][1] = L::fma(x1, m03, m23); k[1][2] = L::neg(m13); k[1][3] = L::fma(L::neg(x1), m01, m12);
+    // S = sum_j k_j k_j^T, upper triangle, then / trace
+    T S[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = i; j < 4; j++)
+            S[i][j] = L::fma(k[3][i], k[3][j], L::fma(k[2][i], k[2][j], L::fma(k[1][i], k[1][j], L::mul(k[0][i], k[0][j]))));
+    const T r = L::rsqrt_scale(L::add(L::add(S[0][0], S[1][1]), L::add(S[2][2], S[3][3])));
+    const T it = L::mul(r, r);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = i; j < 4; j++) {
+            S[i][j] = L::mul(S[i][j], it);
+            S[j][i] = S[i][j];
+        }
+    T u[4], w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = L::mul(k[3][i], r);
+#pragma unroll
+    for (int step = 0; step < 2; step++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = L::fma(S[i][3], u[3], L::fma(S[i][2], u[2], L::fma(S[i][1], u[1], L::mul(S[i][0], u[0]))));
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = L::fma(S[i][3], w[3], L::fma(S[i][2], w[2], L::fma(S[i][1], w[1], L::mul(S[i][0], w[0]))));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = u[i];
+}
+template <int PTS = 1>
+SFM_HD void dlt_null_power4(const float* x1, const float* y1, const float (*a)[4], const float (*b)[4], float (*v)[4]) {
+#pragma unroll
+    for (int p = 0; p < PTS; p++) dlt_null_power4_lanes<LaneF1>(x1[p], y1[p], a[p], b[p], v[p]);
+}
+
 // one point; the matrix given row-major (rows 0 and 1 must be the camera-1 = I4 rows above)
 SFM_HD bool dlt_null_adjugate1(const float* A, float* v) {
     const float x1[1] = {A[2]}, y1[1] = {A[6]};

@@ -371,6 +371,15 @@ class ImagePair(BatchedPairs):
                                              max_ambiguity if max_ambiguity is not None else np.inf)
 
     def estimateE(self, H: int | None = None, seed: int = 0, thr: float = 1e-6, d_idx=None):
+        """No H and no rows = the reference's estimateE(): one permutation of the point indices cut into N/8 disjoint rows
+        (drawn on the device, option 10 = 1).  With H or rows: independent rows / the caller's rows."""
+        if H is None and d_idx is None:
+            self.set_option(10, 1)
+            try:
+                self.estimate_e(max(self.n // 8, 1), seed, thr)
+            finally:
+                self.set_option(10, 0)
+            return
         self.estimate_e(H or max(self.n // 8, 1), seed, thr, d_idx)
 
     def computePosecandidates(self):

@@ -61,7 +61,16 @@ typedef enum {
                                       triangulation; same bits as the five-launch path): -1 (default) when n * H is at most
                                       SFMB200_OPT_SMALL_PATH_EVALS, 0 never, 1 whenever eligible (projector solver,
                                       H <= 128 * cluster size, reference pose semantics, no per-stage profiling) */
-    SFMB200_OPT_SMALL_PATH_EVALS = 8  /* the n * H limit of the automatic choice (default 6,000,000) */
+    SFMB200_OPT_SMALL_PATH_EVALS = 8, /* the n * H limit of the automatic choice (default 6,000,000) */
+    SFMB200_OPT_SAMPLER = 10,      /* sample rows drawn on the device (d_idx == NULL): 0 (default) 8 distinct indices per hypothesis,
+                                      independent between hypotheses; 1 the reference's scheme (sfm.cu:95-104): ONE
+                                      permutation of the point indices cut into disjoint groups of 8, which needs
+                                      8 * H_total <= n (H = N / 8 is the reference's own choice) */
+    SFMB200_OPT_SCORE_METRIC = 9   /* inlier test of the essential-matrix model, used by scoring and by every later
+                                      classifier (mask, refit, cheirality vote, bundle adjustment, chaining): 0 (default)
+                                      Sampson error, what BASELINE's north_star mandates; 1 symmetric epipolar distance
+                                      n^2 (1/|(E x2)_01|^2 + 1/|(E^T x1)_01|^2) < thr, what the reference's calculateInliers was
+                                      written to compute (sfm.cu:155-221) */
 } sfmb200_option;
 
 const char* sfmb200_last_error(void);
@@ -265,8 +274,11 @@ int sfmb200_host_null4_fast(const float A[16], float x[4]);
 /* null vector of a two-view DLT matrix (rows 0, 1 = camera 1 = I4: (-1,0,x1,0), (0,-1,y1,0)) by the adjugate power
  * iteration the triangulation kernel uses; returns 1 when it did not converge (caller falls back to null4) */
 int sfmb200_host_dlt_null(const float A[16], float x[4]);
+/* the fixed four-step form the triangulation kernel uses (direction only, not normalised; zeros for degenerate input) */
+void sfmb200_host_dlt_null_power4(const float A[16], float x[4]);
 int sfmb200_host_inv4(const float m[16], float out[16]);
 void sfmb200_host_sample_indices(uint64_t seed, uint64_t h, int n, int32_t idx[8]);
+void sfmb200_host_sample_indices_disjoint(uint64_t seed, uint64_t h, int n, int32_t idx[8]);   /* SFMB200_OPT_SAMPLER = 1 */
 
 #ifdef __cplusplus
 }

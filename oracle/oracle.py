@@ -124,6 +124,39 @@ def sample_indices(seed: int, H: int, n: int, h0: int = 0) -> np.ndarray:
 # --------------------------------------------------------------------------
 # Hypothesis generation (K3-K7)
 # --------------------------------------------------------------------------
+def sample_indices_disjoint(seed: int, H: int, n: int, h0: int = 0) -> np.ndarray:
+    """The reference's sampling scheme (sfm.cu:95-104: one shuffle of the point indices cut into H = N/8 disjoint groups of
+    8), as the device draws it for SFMB200_OPT_SAMPLER = 1: row h = perm(8h .. 8h+7) with perm a keyed 4-round Feistel
+    permutation of [0, n) with cycle walking.  Bit-exact mirror of hyp_solver.cuh: sample_indices_disjoint."""
+    assert 8 * (h0 + H) <= n
+    k0 = _splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5)
+    k1 = _splitmix64(k0)
+    keys = [k0 & 0xFFFFFFFF, k0 >> 32, k1 & 0xFFFFFFFF, k1 >> 32]
+    bits = 1
+    while (1 << bits) < n:
+        bits += 1
+    half = (bits + 1) // 2
+    mask = np.uint32((1 << half) - 1)
+
+    def mix(v, key):
+        v = v ^ np.uint32(key)
+        v = (v * np.uint32(0x85EBCA6B)).astype(np.uint32)
+        v = v ^ (v >> np.uint32(13))
+        v = (v * np.uint32(0xC2B2AE35)).astype(np.uint32)
+        return v ^ (v >> np.uint32(16))
+
+    x = np.arange(8 * h0, 8 * (h0 + H), dtype=np.uint32)
+    todo = np.ones(len(x), bool)
+    with np.errstate(over="ignore"):
+        while todo.any():
+            L, R = x[todo] >> np.uint32(half), x[todo] & mask
+            for r in range(4):
+                L, R = R, L ^ (mix(R, keys[r]) & mask)
+            x[todo] = (L << np.uint32(half)) | R
+            todo = x >= n
+    return x.astype(np.int32).reshape(H, 8)
+
+
 def design_matrix(x: np.ndarray) -> np.ndarray:
     """kernels::kernels (SfM/kernels.h:247-257): row = kron((x1,y1,1),(x2,y2,1))
     so that the null vector reshaped row-major satisfies x1^T E x2 = 0."""
@@ -189,6 +222,27 @@ def inlier_counts(E: np.ndarray, x: np.ndarray, thr: float = 1e-6, band: float =
         d = n2 - thr * den
         cnt[s:s + chunk] = (d < 0).sum(1)
         amb[s:s + chunk] = (np.abs(d) <= band * thr * den + 1e-300).sum(1)
+    return cnt, amb
+
+
+def symmetric_counts(E: np.ndarray, x: np.ndarray, thr: float = 1e-6, band: float = 1e-4, chunk: int = 256):
+    """Symmetric epipolar distance, the stated intent of calculateInliers (sfm.cu:155-221):
+    n^2 / (l0^2 + l1^2) + n^2 / (m0^2 + m1^2) < thr with n = x1^T E x2, l = E x2, m = E^T x1, evaluated division-free as
+    n^2 (A + B) < thr A B.  Returns (counts, borderline) like inlier_counts."""
+    E = E.reshape(-1, 3, 3).astype(np.float64)
+    x1 = np.stack([x[:, 0], x[:, 1], np.ones(len(x))], 0).astype(np.float64)
+    x2 = np.stack([x[:, 2], x[:, 3], np.ones(len(x))], 0).astype(np.float64)
+    cnt = np.zeros(len(E), np.int64)
+    amb = np.zeros(len(E), np.int64)
+    for s in range(0, len(E), chunk):
+        Ec = E[s:s + chunk]
+        l = Ec @ x2
+        m = np.transpose(Ec, (0, 2, 1)) @ x1
+        num = (x1[None] * l).sum(1)
+        A, B = l[:, 0] ** 2 + l[:, 1] ** 2, m[:, 0] ** 2 + m[:, 1] ** 2
+        d = num * num * (A + B) - thr * A * B
+        cnt[s:s + chunk] = (d < 0).sum(1)
+        amb[s:s + chunk] = (np.abs(d) <= band * thr * A * B + 1e-300).sum(1)
     return cnt, amb
 
 

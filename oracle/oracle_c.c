@@ -170,6 +170,63 @@ void oracle_counts_f32(const float* E, int H, const float* x, int n, float thr, 
     free(xs);
 }
 
+/* Symmetric epipolar distance (SFMB200_OPT_SCORE_METRIC = 1; the intent of sfm.cu:155-221): mirrors
+ * sampson.cuh:symmetric_unit_d - same scaling, d = num~^2 (A + B) - A B, A = l0^2 + l1^2, B = m0^2 + m1^2. */
+static inline float symmetric_unit_d_f32(const float* s, float x1, float y1, float x2, float y2) {
+    float l0 = fmaf(s[0], x2, fmaf(s[1], y2, s[2]));
+    float l1 = fmaf(s[3], x2, fmaf(s[4], y2, s[5]));
+    float l2 = fmaf(s[6], x2, fmaf(s[7], y2, s[8]));
+    float num = fmaf(x1, l0, fmaf(y1, l1, l2));
+    float m0 = fmaf(s[0], x1, fmaf(s[3], y1, s[6]));
+    float m1 = fmaf(s[1], x1, fmaf(s[4], y1, s[7]));
+    float A = fmaf(l0, l0, l1 * l1);
+    float B = fmaf(m0, m0, m1 * m1);
+    return fmaf(num * num, A + B, -(A * B));
+}
+void oracle_counts_sym_f32(const float* E, int H, const float* x, int n, float thr, int32_t* counts) {
+    const float ik = 1.0f / sqrtf(thr);
+    float* xs = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    for (size_t i = 0; i < 4 * (size_t)n; i++) xs[i] = x[i] * ik;
+#pragma omp parallel for schedule(static)
+    for (int h = 0; h < H; h++) {
+        float s[9];
+        thr_scale_E(E + 9 * (size_t)h, thr, s);
+        int c = 0;
+        for (int i = 0; i < n; i++) {
+            const float* p = xs + 4 * (size_t)i;
+            float d = symmetric_unit_d_f32(s, p[0], p[1], p[2], p[3]);
+            uint32_t bits;
+            memcpy(&bits, &d, 4);
+            c += (int)(bits >> 31);
+        }
+        counts[h] = c;
+    }
+    free(xs);
+}
+/* fp64 truth: inlier <=> num^2 (A + B) < thr A B; borderline within band (relative to thr A B) */
+void oracle_counts_sym_f64(const float* E, int H, const float* x, int n, double thr, double band, int32_t* counts,
+                           int32_t* borderline) {
+#pragma omp parallel for schedule(static)
+    for (int h = 0; h < H; h++) {
+        double e[9];
+        for (int k = 0; k < 9; k++) e[k] = E[9 * (size_t)h + k];
+        int c = 0, bl = 0;
+        for (int i = 0; i < n; i++) {
+            const float* p = x + 4 * (size_t)i;
+            double x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3];
+            double l0 = e[0] * x2 + e[1] * y2 + e[2], l1 = e[3] * x2 + e[4] * y2 + e[5], l2 = e[6] * x2 + e[7] * y2 + e[8];
+            double num = x1 * l0 + y1 * l1 + l2;
+            double m0 = e[0] * x1 + e[3] * y1 + e[6], m1 = e[1] * x1 + e[4] * y1 + e[7];
+            double A = l0 * l0 + l1 * l1, B = m0 * m0 + m1 * m1;
+            double d = num * num * (A + B) - thr * A * B;
+            c += d < 0;
+            bl += fabs(d) <= band * thr * A * B + 1e-300;
+        }
+        counts[h] = c;
+        if (borderline) borderline[h] = bl;
+    }
+}
+
 /* fp64 truth on the same fp32 inputs; borderline[h] = #{i : |num^2 - thr*den| <= band*thr*den} */
 void oracle_counts_f64(const float* E, int H, const float* x, int n, double thr, double band, int32_t* counts,
                        int32_t* borderline) {

@@ -217,6 +217,25 @@ def test_host_dlt_null_adjugate_matches_fp64_on_dlt_matrices(lib, O):
     assert ok >= 150
 
 
+def test_disjoint_permutation_sampler_matches_oracle(lib, O):
+    """SFMB200_OPT_SAMPLER = 1 (the reference's scheme, sfm.cu:95-104: one permutation cut into disjoint groups of 8):
+    the device / host code and the oracle mirror agree bit for bit, rows are disjoint and cover distinct indices."""
+    for n, seed in ((2153, 5), (8, 0), (17, 3), (65536, 99), (1000003, 7)):
+        H = min(n // 8, 1500)
+        want = O.sample_indices_disjoint(seed, H, n)
+        got = np.zeros((H, 8), np.int32)
+        for h in range(H):
+            lib.raw("sfmb200_host_sample_indices_disjoint")(C.c_uint64(seed), C.c_uint64(h), n, got[h].ctypes.data_as(C.POINTER(C.c_int32)))
+        assert np.array_equal(want, got)
+        flat = want.reshape(-1)
+        assert len(set(flat.tolist())) == len(flat) and flat.min() >= 0 and flat.max() < n
+        # a slice regenerates without the rows before it
+        assert np.array_equal(O.sample_indices_disjoint(seed, H - H // 2, n, h0=H // 2), want[H // 2:])
+    # a full permutation when n is a multiple of 8
+    full = O.sample_indices_disjoint(11, 64, 512).reshape(-1)
+    assert sorted(full.tolist()) == list(range(512))
+
+
 def test_shard_range_and_keys(pkg):
     sh = pkg.sharding
     for total in (0, 1, 7, 8, 65536, 1000003):

@@ -472,3 +472,82 @@ def test_random_shapes_fuzz(pkg, O, oracle_c, torch_cuda):
             assert bc[b] == got.max() and bi[b] == int(np.argmax(got)), (trial, B, n, H, variant)
             assert np.array_equal(h.get_E()[b].reshape(9), Eg[bi[b]])
         h.close()
+
+
+@pytest.mark.parametrize("H", [200, 700, 3000])
+def test_symmetric_epipolar_metric(pkg, O, oracle_c, torch_cuda, scene_small, H):
+    """SFMB200_OPT_SCORE_METRIC = 1: the symmetric epipolar distance the reference's calculateInliers was written to compute
+    (sfm.cu:155-221), on the same kernel skeleton (three tile sizes), bit-exact against the fp32 port of its
+    fma tree, banded against fp64, and consistent through the later classifiers."""
+    torch = torch_cuda
+    x, n = scene_small["x"], len(scene_small["x"])
+    h = make_handle(pkg, scene_small, H)
+    h.set_option(9, 1)
+    h.set_points_xy(torch.from_numpy(scene_small["px"]).cuda())
+    h.estimate_e(H, 1237, THR)
+    assert h.score_plan()["variant"] >= 0                      # the fused small path is Sampson-only
+    Eg = h.get_E_candidates().cpu().numpy()
+    got = h.get_inlier_counts().cpu().numpy()
+    xg = gpu_x(h)
+    c32 = np.zeros(H, np.int32)
+    oracle_c.oracle_counts_sym_f32(P(np.ascontiguousarray(Eg)), H, P(xg), n, C.c_float(THR), P(c32, ip))
+    assert np.array_equal(got, c32)
+    c64, amb = np.zeros(H, np.int32), np.zeros(H, np.int32)
+    oracle_c.oracle_counts_sym_f64(P(np.ascontiguousarray(Eg)), H, P(xg), n, C.c_double(THR), C.c_double(BAND), P(c64, ip), P(amb, ip))
+    assert np.all(np.abs(got - c64) <= amb)
+    cpy, _ = O.symmetric_counts(Eg.astype(np.float64), xg, THR, band=BAND)
+    assert np.array_equal(cpy, c64)
+    bi, bc = h.get_best()
+    assert bc[0] == got.max() and bi[0] == int(np.argmax(got))
+    mask = h.get_inlier_mask().cpu().numpy().astype(bool)
+    assert mask.sum() == bc[0]
+    # d_sym = n^2 (1/A + 1/B) >= 4 n^2 / (A + B) = 4 x Sampson: an inlier of the symmetric test at thr is a Sampson inlier at
+    # thr / 4 (up to a borderline decision), let alone at thr
+    hs = make_handle(pkg, scene_small, H)
+    hs.set_points_xy(torch.from_numpy(scene_small["px"]).cuda())
+    hs.estimate_e(H, 1237, THR)
+    assert np.array_equal(hs.get_E_candidates().cpu().numpy(), Eg)
+    samp = hs.get_inlier_counts().cpu().numpy()
+    hs.estimate_e(H, 1237, THR / 4)
+    samp4 = hs.get_inlier_counts().cpu().numpy()
+    assert np.all(got <= samp) and np.all(got <= samp4 + 2) and got.sum() < samp.sum()
+    # downstream: inliers-only triangulation keeps exactly the metric's inliers
+    h.set_option(3, 1)
+    h.pose_candidates(); h.choose_pose(); h.triangulate()
+    pts = h.get_points_host()
+    assert np.all(pts[:3, ~mask] == 0) and np.all(pts[3] == 1)
+    with pytest.raises(pkg.SfmError):
+        h.set_option(9, 2)
+    h.close(); hs.close()
+
+
+def test_disjoint_permutation_sampler_on_device(pkg, O, torch_cuda, scene_small):
+    """estimateE() with no arguments means what sfm.cu:95-104 means: H = N/8 rows from ONE permutation, drawn on the device;
+    identical to feeding the oracle's rows explicitly, on the general and on the fused small path."""
+    torch = torch_cuda
+    n = len(scene_small["px"])
+    d_px = torch.from_numpy(scene_small["px"]).cuda()
+    H = n // 8
+    rows = O.sample_indices_disjoint(77, H, n)
+    for small in (0, 1):
+        a, b = make_handle(pkg, scene_small, H), make_handle(pkg, scene_small, H)
+        for h in (a, b):
+            h.set_option(7, small)
+            h.set_points_xy(d_px)
+        a.set_option(10, 1)
+        a.estimate_e(H, 77, THR)
+        b.estimate_e(H, 0, THR, d_idx=torch.from_numpy(rows).cuda())
+        assert np.array_equal(a.get_E_candidates().cpu().numpy(), b.get_E_candidates().cpu().numpy())
+        assert np.array_equal(a.get_inlier_counts().cpu().numpy(), b.get_inlier_counts().cpu().numpy())
+        assert np.array_equal(a.get_E(), b.get_E())
+        with pytest.raises(pkg.SfmError):
+            a.estimate_e(H + 1, 77, THR)                       # 8 H > n: not a permutation any more
+        a.close(); b.close()
+    ipair = pkg.ImagePair(scene_small["K"], scene_small["Kinv"], 2, n)
+    ipair.set_points_xy(d_px)
+    ipair.estimateE()                                          # the reference's call
+    ref = make_handle(pkg, scene_small, H)
+    ref.set_points_xy(d_px)
+    ref.estimate_e(H, 0, THR, d_idx=torch.from_numpy(O.sample_indices_disjoint(0, H, n)).cuda())
+    assert np.array_equal(ipair.get_E(), ref.get_E()) and ipair.H == H
+    ipair.close(); ref.close()
