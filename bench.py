@@ -481,6 +481,15 @@ def run_ours(args):
         return
     # ---- rank 0: roofline, probes, CPU baselines, JSON line ----
     lib = pkg.load_library()
+    build_info = lib.raw("sfmb200_build_info")().decode()
+    try:
+        import importlib.util as _ilu
+        _sp = _ilu.spec_from_file_location("sfmb200_build", os.path.join(ROOT, "cuda-sfm_b200", "build.py"))
+        _b = _ilu.module_from_spec(_sp)
+        _sp.loader.exec_module(_b)
+        tree_hash = _b.source_hash()
+    except Exception:
+        tree_hash = None
     score_plan = plan_main
     probe = {}
     for mode, name in ((0, "ffma"), (1, "ffma2")):
@@ -547,6 +556,8 @@ def run_ours(args):
         "result": {"best_hypothesis": int(best_idx[0]), "inliers": int(best_cnt[0]), "pose_index": int(out["pose_index"][0])},
         "roofline": roofline, "roofline_triangulation": tri, "cpu_baseline": cpu, "cv2_baseline": cv2b,
         "clocks": clocks, "wall_s_timed_region": wall,
+        "library": {"path": os.path.relpath(lib.path, ROOT), "build_info": build_info, "source_tree_hash": tree_hash,
+                    "built_from_this_tree": bool(tree_hash and tree_hash in build_info)},
         "sustained": {"what": "the same config-2 step back to back (L2 flushed between steps, CUDA events per step, max over ranks)",
                       "steps": sus_steps, "ms_per_step": sus_ms, "value": world * N_HYP * N_CORR / (sus_ms * 1e-3), "unit": "hyp*corr evals/s",
                       "wall_s": sus_wall, "clocks": sus_clocks},

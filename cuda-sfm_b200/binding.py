@@ -29,6 +29,8 @@ _vp = C.c_void_p
 SIGNATURES = {
     "sfmb200_last_error": (C.c_char_p, []),
     "sfmb200_version": (C.c_int, []),
+    "sfmb200_build_info": (C.c_char_p, []),
+    "sfmb200_small_path_debug": (C.c_int, [_vp]),
     "sfmb200_create": (C.c_int, [_f, _f, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "sfmb200_destroy": (C.c_int, [_vp]),
     "sfmb200_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),

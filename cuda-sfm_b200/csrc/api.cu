@@ -51,6 +51,10 @@ struct sfmb200_handle {
     long long mg_timeout_cycles;
     cudaStream_t stream;
     bool own_stream;
+    cudaStream_t aux_stream;       // side stream of the batched pipeline (hypothesis generation of later chunks runs under the
+    cudaEvent_t ev_fork;           // scoring of earlier ones); created on first use
+    cudaEvent_t ev_chunk[16];
+    int pipeline_chunks;           // SFMB200_OPT_BATCH_PIPELINE: -1 auto, 0 / 1 off, 2..16 chunks
     int device;
     int sms;               // SM count of the handle's device (cached at create)
     int compat;
@@ -223,6 +227,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->hyp_solver = 1;     // Cholesky projector: same parity as the Jacobi eigensolve, 3.5-4.4x faster (profiles/)
     h->score_variant = -1;
     h->tri_inliers_only = 0;
+    h->pipeline_chunks = -1;
     h->small_path = -1;
     h->small_evals = 6000000;      // crossover with the five-launch path on B200 (profiles/r02_small_path.md)
     *out = h;
@@ -234,6 +239,11 @@ int sfmb200_destroy(sfmb200_t* h) {
     if (!h) return SFMB200_OK;
     cudaStreamSynchronize(h->stream);
     sfmb200_mg_close(h);          // unmaps the peers' exchange buffers; needs the stream, so before it goes
+    if (h->aux_stream) {
+        cudaStreamDestroy(h->aux_stream);
+        cudaEventDestroy(h->ev_fork);
+        for (int i = 0; i < 16; i++) cudaEventDestroy(h->ev_chunk[i]);
+    }
     if (h->own_stream) cudaStreamDestroy(h->stream);
     if (h->host_header) cudaFreeHost(h->host_header);
     if (h->prof_ev) {
@@ -266,6 +276,10 @@ int sfmb200_set_option(sfmb200_t* h, int option, int value) {
             h->hyp_solver = value;
             break;
         case SFMB200_OPT_BA_PERSISTENT: h->ba.persistent = value ? 1 : 0; break;
+        case SFMB200_OPT_BATCH_PIPELINE:
+            if (value < -1 || value > 16) return fail(SFMB200_ERR_ARG, "batch pipeline chunks must be -1 (auto), 0 / 1 (off) or 2..16%s");
+            h->pipeline_chunks = value;
+            break;
         case SFMB200_OPT_SAMPLER:
             if (value < 0 || value > 1) return fail(SFMB200_ERR_ARG, "sampler must be 0 (independent subsets) or 1 (disjoint permutation)%s");
             h->s.sampler = value;
@@ -934,12 +948,48 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
     h->thr = thr;
     if (int rc = ensure_scaled(h, make_thr_scale(thr).ik)) return rc;     // no-op after run_device / run_host's own ingest
     h->plan = plan_essential(h, h->s.n, H);
-    launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->hyp_solver, h->stream);
-    prof_mark(h, 2);
-    CKL();
-    score_essential(h, h->s, H, 0, thr);
-    prof_mark(h, 3);
-    CKL();
+    int chunks = h->pipeline_chunks;
+    if (chunks < 0) chunks = 1;      // measured on B200 (profiles/r02_batch_pipeline.md): no gain at config 4, so off unless asked for
+    if (chunks > h->s.B) chunks = h->s.B;
+    if (chunks >= 2) {
+        // Batched pipeline: the batch is cut into chunks of pairs; hypothesis generation of ALL chunks is enqueued on a
+        // side stream, scoring of chunk c on the main stream waits only for generation of chunk c.  The persistent
+        // scoring grid holds one 256-thread CTA (42 K registers) per SM, which leaves room for one 128-thread generation
+        // CTA next to it: generation - a latency-bound kernel that keeps the FMA pipe 40 % busy on its own - runs in the
+        // issue slots scoring leaves idle instead of in front of it.  Same kernels, same per-pair seeds: same bits.
+        if (!h->aux_stream) {
+            CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+        const int per = (h->s.B + chunks - 1) / chunks;
+        int used = 0;
+        for (int c = 0, b0 = 0; b0 < h->s.B; c++, b0 += per, used++) {
+            const DeviceState v = sub_batch(h->s, b0, b0 + per <= h->s.B ? per : h->s.B - b0);
+            launch_hypgen(v, nullptr, (long long)H * 8, H, 0, seed, h->hyp_solver, h->aux_stream);
+            CKL();
+            CK(cudaEventRecord(h->ev_chunk[c], h->aux_stream));
+        }
+        for (int c = 0, b0 = 0; b0 < h->s.B; c++, b0 += per) {
+            const DeviceState v = sub_batch(h->s, b0, b0 + per <= h->s.B ? per : h->s.B - b0);
+            CK(cudaStreamWaitEvent(h->stream, h->ev_chunk[c], 0));
+            ScorePlan keep = h->plan;
+            h->plan = h->s.metric == 0 ? make_score_plan(v.B, v.n, H, h->score_variant, h->sms) : make_score_plan_homography(v.B, v.n, H, h->sms);
+            score_essential(h, v, H, 0, thr);
+            CKL();
+            h->plan = keep;
+        }
+        h->launches += 2 * used - 2;
+    } else {
+        launch_hypgen(h->s, nullptr, (long long)H * 8, H, 0, seed, h->hyp_solver, h->stream);
+        prof_mark(h, 2);
+        CKL();
+        score_essential(h, h->s, H, 0, thr);
+        prof_mark(h, 3);
+        CKL();
+    }
     launch_select_pose_choose(h->s, 0, h->compat, h->stream);
     prof_mark(h, 4);
     prof_mark(h, 5);
@@ -1248,6 +1298,11 @@ int sfmb200_stage_times(sfmb200_t* h, int max_sets, float* ms, int* sets) {
         for (int k = 0; k < 7; k++) CK(cudaEventElapsedTime(&ms[(size_t)(*sets) * 7 + k], h->prof_ev[i][k], h->prof_ev[i][k + 1]));
         (*sets)++;
     }
+    return SFMB200_OK;
+}
+
+int sfmb200_small_path_debug(int64_t* d_stamps) {
+    small_path_set_debug((long long*)d_stamps);
     return SFMB200_OK;
 }
 

@@ -312,73 +312,97 @@ void launch_choose_pose(const DeviceState& s, int compat, float thr, cudaStream_
 #define SFMB200_TRI_THREADS 128
 #endif
 constexpr int TRI_THREADS = SFMB200_TRI_THREADS;
+#ifndef SFMB200_TRI_MINB
+#define SFMB200_TRI_MINB 8      // resident CTAs per SM the kernel is compiled for (<= 64 registers at 128 threads)
+#endif
 template <int PTS, bool INLIERS_ONLY>
-__global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(DeviceState s, float thr) {
+__global__ void __launch_bounds__(TRI_THREADS, SFMB200_TRI_MINB) triangulate_kernel(DeviceState s, float thr) {
     static_assert(PTS == 1 || PTS == 2, "one point per thread, or two in packed f32x2 arithmetic");
     pdl_wait();
     const int b = blockIdx.y;
     const float* Mg = s.P + (size_t)b * 64 + 16 * __ldg(s.P_ind + b);
-    float M[12];
+    float M[12], e[9];
 #pragma unroll
     for (int k = 0; k < 12; k++) M[k] = __ldg(Mg + k);
-    const int base = blockIdx.x * (TRI_THREADS * PTS) + threadIdx.x;
+    if constexpr (INLIERS_ONLY) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) e[k] = __ldg(s.E + (size_t)b * 9 + k);
+    }
+    // persistent over the pair's points: grid.x CTAs stride through them, the next points are in flight while the current
+    // ones are solved (the loads are the only long-latency operation), the pose stays in registers
+    constexpr int CHUNK = TRI_THREADS * PTS;
+    const int step = gridDim.x * CHUNK, n = s.n;
     const float4* corr = s.corr + (size_t)b * s.n_stride;
-    float v[PTS][4];
-    bool keep[PTS];
-    float4 pt[PTS];
-#pragma unroll
-    for (int p = 0; p < PTS; p++) {
-        const int i = base + p * TRI_THREADS;
-        pt[p] = i < s.n ? __ldg(corr + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
-#pragma unroll
-    for (int p = 0; p < PTS; p++) {
-        keep[p] = base + p * TRI_THREADS < s.n;
-        if constexpr (INLIERS_ONLY) {
-            float e[9];
-#pragma unroll
-            for (int k = 0; k < 9; k++) e[k] = __ldg(s.E + (size_t)b * 9 + k);
-            keep[p] = keep[p] && epipolar_d(s.metric, e, pt[p].x, pt[p].y, pt[p].z, pt[p].w, -thr) < 0.0f;
-        }
-    }
-    // rows 2, 3 of the DLT matrix (compute_linear_triangulation_A, kernels.h:387-431), then the null vector
-    if constexpr (PTS == 2) {
-        const float2 x1 = make_float2(pt[0].x, pt[1].x), y1 = make_float2(pt[0].y, pt[1].y);
-        const float2 x2 = make_float2(pt[0].z, pt[1].z), y2 = make_float2(pt[0].w, pt[1].w);
-        float2 a[4], bb[4], vv[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const float2 m2 = make_float2(M[8 + c], M[8 + c]);
-            a[c] = __ffma2_rn(x2, m2, make_float2(-M[c], -M[c]));
-            bb[c] = __ffma2_rn(y2, m2, make_float2(-M[4 + c], -M[4 + c]));
-        }
-        dlt_null_power4_lanes<LaneF2>(x1, y1, a, bb, vv);
-#pragma unroll
-        for (int c = 0; c < 4; c++) { v[0][c] = vv[c].x; v[1][c] = vv[c].y; }
-    } else {
-        float a[4], bb[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            a[c] = fmaf(pt[0].z, M[8 + c], -M[c]);
-            bb[c] = fmaf(pt[0].w, M[8 + c], -M[4 + c]);
-        }
-        dlt_null_power4_lanes<LaneF1>(pt[0].x, pt[0].y, a, bb, v[0]);
-    }
     float* out = s.points + (size_t)b * 4 * s.n_stride;
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 nxt[PTS];
+    int i0 = blockIdx.x * CHUNK;
 #pragma unroll
     for (int p = 0; p < PTS; p++) {
-        const int i = base + p * TRI_THREADS;
-        if (i >= s.n) continue;
-        float X = 0.0f, Y = 0.0f, Z = 0.0f;
-        if (keep[p]) dehomogenise(v[p], X, Y, Z);
-        out[i] = X;
-        out[(size_t)s.n_stride + i] = Y;
-        out[(size_t)2 * s.n_stride + i] = Z;
-        out[(size_t)3 * s.n_stride + i] = 1.0f;
+        const int i = i0 + p * TRI_THREADS + threadIdx.x;
+        nxt[p] = i < n ? __ldg(corr + i) : zero4;
+    }
+    for (; i0 < n; i0 += step) {
+        float4 pt[PTS];
+#pragma unroll
+        for (int p = 0; p < PTS; p++) {
+            pt[p] = nxt[p];
+            const int i = i0 + step + p * TRI_THREADS + threadIdx.x;
+            nxt[p] = i < n ? __ldg(corr + i) : zero4;
+        }
+        float v[PTS][4];
+        bool keep[PTS];
+#pragma unroll
+        for (int p = 0; p < PTS; p++) {
+            keep[p] = true;
+            if constexpr (INLIERS_ONLY) keep[p] = epipolar_d(s.metric, e, pt[p].x, pt[p].y, pt[p].z, pt[p].w, -thr) < 0.0f;
+        }
+        // rows 2, 3 of the DLT matrix (compute_linear_triangulation_A, kernels.h:387-431), then the null vector
+        if constexpr (PTS == 2) {
+            const float2 x1 = make_float2(pt[0].x, pt[1].x), y1 = make_float2(pt[0].y, pt[1].y);
+            const float2 x2 = make_float2(pt[0].z, pt[1].z), y2 = make_float2(pt[0].w, pt[1].w);
+            float2 a[4], bb[4], vv[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float2 m2 = make_float2(M[8 + c], M[8 + c]);
+                a[c] = __ffma2_rn(x2, m2, make_float2(-M[c], -M[c]));
+                bb[c] = __ffma2_rn(y2, m2, make_float2(-M[4 + c], -M[4 + c]));
+            }
+            dlt_null_power4_lanes<LaneF2>(x1, y1, a, bb, vv);
+#pragma unroll
+            for (int c = 0; c < 4; c++) { v[0][c] = vv[c].x; v[1][c] = vv[c].y; }
+        } else {
+            float a[4], bb[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                a[c] = fmaf(pt[0].z, M[8 + c], -M[c]);
+                bb[c] = fmaf(pt[0].w, M[8 + c], -M[4 + c]);
+            }
+            dlt_null_power4_lanes<LaneF1>(pt[0].x, pt[0].y, a, bb, v[0]);
+        }
+#pragma unroll
+        for (int p = 0; p < PTS; p++) {
+            const int i = i0 + p * TRI_THREADS + threadIdx.x;
+            if (i >= n) continue;
+            float X = 0.0f, Y = 0.0f, Z = 0.0f;
+            if (keep[p]) dehomogenise(v[p], X, Y, Z);
+            out[i] = X;
+            out[(size_t)s.n_stride + i] = Y;
+            out[(size_t)2 * s.n_stride + i] = Z;
+            out[(size_t)3 * s.n_stride + i] = 1.0f;
+        }
     }
 }
+#ifndef SFMB200_TRI_CTAS_PER_SM
+#define SFMB200_TRI_CTAS_PER_SM 8
+#endif
 void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st) {
-    dim3 grid((s.n + TRI_THREADS * SFMB200_TRI_PTS - 1) / (TRI_THREADS * SFMB200_TRI_PTS), s.B);
+    constexpr int CHUNK = TRI_THREADS * SFMB200_TRI_PTS;
+    int gx = (s.n + CHUNK - 1) / CHUNK;
+    int cap = (148 * SFMB200_TRI_CTAS_PER_SM + s.B - 1) / s.B;          // resident CTAs over the whole batch
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+    dim3 grid(gx, s.B);
     if (inliers_only)
         launch_dep(triangulate_kernel<SFMB200_TRI_PTS, true>, grid, dim3(TRI_THREADS), 0, st, s, thr);
     else

@@ -25,6 +25,9 @@ struct Corr { float x1, y1, x2, y2; };
 #ifndef SFM_HYP_REFINE
 #define SFM_HYP_REFINE 3
 #endif
+#ifndef SFM_PROJ_ITERS
+#define SFM_PROJ_ITERS 3        // projector solver: projection + (SFM_PROJ_ITERS - 1) re-projections against the design rows
+#endif
 #ifndef SFM_HYP_FAST_ANGLE
 #define SFM_HYP_FAST_ANGLE 1     // device: approximate rotation angles in the 9x9 eigensolve
 #endif
@@ -324,7 +327,7 @@ SFM_HD void solve_hypothesis_projector(const Corr* pts, float* E) {
     for (int c = 0; c < 9; c++) e[c] = (c == best) ? 1.0f : 0.0f;
     // e <- e - A^T K^-1 (A e), three times (projection + two re-projections)
 #pragma unroll 1
-    for (int it = 0; it < 3; it++) {
+    for (int it = 0; it < SFM_PROJ_ITERS; it++) {
         float y[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {

@@ -26,6 +26,7 @@ constexpr int SCORE_MIN_TILE = 256;  // smallest hypothesis tile of any kernel v
 // [pair][...] with fixed strides so a batch is one launch (blockIdx.y / z = pair).
 struct DeviceState {
     int B;              // pairs in the batch
+    int pair0;          // index of this view's first pair in the handle's batch (sub-batch launches; seeds the per-pair sampler)
     int n_max;          // capacity: correspondences per pair
     int h_max;          // capacity: hypotheses per pair (local slice)
     int n;              // current correspondences per pair
@@ -58,6 +59,31 @@ struct DeviceState {
     const int* skip;    // adaptive termination: when non-null and *skip != 0 the hypgen / score kernels of
                         // the remaining rounds return at once (set by adaptive_decide_kernel); else nullptr
 };
+
+// A view of pairs [b0, b0 + nb) of the batch: every per-pair array advanced to pair b0, B = nb.  Kernels that derive
+// anything from the pair's absolute index (the sampler seed) use pair0 + blockIdx.y.
+inline DeviceState sub_batch(const DeviceState& s, int b0, int nb) {
+    DeviceState v = s;
+    const size_t b = (size_t)b0;
+    v.B = nb;
+    v.pair0 = s.pair0 + b0;
+    v.corr += b * s.n_stride;
+    v.corr_s += b * s.n_stride;
+    v.corr_dup += b * s.n_stride * 2;
+    v.Ecand += b * 9 * s.h_stride;
+    v.counts += b * s.h_stride;
+    v.tile_done += b * s.tiles_max;
+    v.best += b;
+    v.E += b * 9;
+    v.best_idx += b;
+    v.best_count += b;
+    v.P += b * 64;
+    v.P_ind += b;
+    v.points += b * 4 * s.n_stride;
+    v.tri_count += b;
+    v.vote += b * 8;
+    return v;
+}
 
 // Scratch of the local-optimisation (refit) stage, per pair.
 struct RefitState {
@@ -147,6 +173,7 @@ void launch_inlier_mask(const DeviceState& s, int pair, float thr, int model, un
 // Fused single-launch path for small problems (small.cu): one thread-block cluster per pair.
 enum { SMALL_INGEST = 1, SMALL_ESTIMATE = 2, SMALL_POSE = 4, SMALL_TRI = 8 };
 int small_path_max_hypotheses();
+void small_path_set_debug(long long* d_stamps);      // measurement hook: phase time stamps of the fused kernel
 cudaError_t launch_small_path(const DeviceState& s, const float* d_px, const int32_t* d_idx, long long idx_pair_stride, int H,
                               int h_offset, unsigned long long seed, float thr, int compat, int inliers_only, int mask,
                               cudaStream_t st);

@@ -30,6 +30,7 @@ namespace sfmb200 {
 constexpr int SMALL_THREADS = 512;
 constexpr int SMALL_HC_MAX = 128;        // hypotheses per CTA kept in shared memory
 constexpr int SMALL_G = 4;               // hypotheses per register group in the scoring loop
+constexpr int SMALL_PTS = 8;             // correspondences per thread held in registers while scoring
 
 struct SmallArgs {
     const float4* px;        // [B][n] pixel correspondences (SMALL_INGEST)
@@ -40,6 +41,7 @@ struct SmallArgs {
     int H, h_offset;
     float thr;
     int compat, inliers_only, mask;
+    long long* dbg;          // optional [8] clock64 stamps of CTA 0 thread 0 at the phase boundaries (tools/small_phases.py)
 };
 
 __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceState s, SmallArgs a) {
@@ -55,6 +57,12 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
     __shared__ unsigned long long sKey;
 
     if (rank == 0 && tid == 0 && (a.mask & SMALL_ESTIMATE)) s.best[b] = 0ull;
+    int stamp = 0;
+    auto mark = [&]() {
+        if (a.dbg != nullptr && rank == 0 && tid == 0 && b == 0) a.dbg[stamp] = clock64();
+        stamp++;
+    };
+    mark();
 
     // ---- ingest ----
     if (a.mask & SMALL_INGEST) {
@@ -64,6 +72,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         }
         cluster.sync();
     }
+    mark();
 
     if (a.mask & SMALL_ESTIMATE) {
         // ---- hypothesis generation: block k of 32 hypotheses -> cluster warp k ----
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             const bool live = j < H;
             Corr pts[8];
             float E[9];
-            const bool ok = load_sample<true>(corr, n, rows, a.seed + 0x632BE59BD9B4E019ull * (unsigned long long)b,
+            const bool ok = load_sample<true>(corr, n, rows, a.seed + 0x632BE59BD9B4E019ull * (unsigned long long)(s.pair0 + b),
                                         (long long)a.h_offset + (live ? j : 0), pts, s.sampler);
             solve_hypothesis_projector(pts, E);
             if (live) {
@@ -85,6 +94,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             }
         }
         cluster.sync();
+        mark();
 
         // ---- scoring: CTA `rank` owns hypotheses [h0, h1) ----
         const int Hc = (H + C - 1) / C;
@@ -101,7 +111,14 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         for (int t = tid; t < SMALL_HC_MAX; t += SMALL_THREADS) sCnt[t] = 0;
         if (tid == 0) sKey = 0ull;
         __syncthreads();
+        // this thread's correspondences (tid, tid + T, ...) are loaded ONCE into registers - the first version re-read them
+        // from L2 for every hypothesis group and spent 2/3 of the phase waiting for those loads; points beyond
+        // SMALL_PTS per thread (n > 4096) are streamed
         const float4* cs = s.corr_s + (size_t)b * s.n_stride;
+        float4 pr[SMALL_PTS];
+        const int my_pts = tid < n ? (n - tid + SMALL_THREADS - 1) / SMALL_THREADS : 0;
+#pragma unroll
+        for (int k = 0; k < SMALL_PTS; k++) pr[k] = k < my_pts ? __ldcg(cs + tid + k * SMALL_THREADS) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         for (int g0 = 0; g0 < mine; g0 += SMALL_G) {
             float e[SMALL_G][9];
             unsigned int cnt[SMALL_G];
@@ -112,7 +129,16 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
                 for (int q = 0; q < 9; q++) e[g][q] = sE[hh][q];
                 cnt[g] = 0u;
             }
-            for (int i = tid; i < n; i += SMALL_THREADS) {
+#pragma unroll
+            for (int k = 0; k < SMALL_PTS; k++) {
+                const unsigned int valid = k < my_pts ? 1u : 0u;
+#pragma unroll
+                for (int g = 0; g < SMALL_G; g++) {
+                    const float d = sampson_unit_d(e[g], pr[k].x, pr[k].y, pr[k].z, pr[k].w);
+                    cnt[g] += (__float_as_uint(d) >> 31) & valid;
+                }
+            }
+            for (int i = tid + SMALL_PTS * SMALL_THREADS; i < n; i += SMALL_THREADS) {
                 const float4 p = __ldcg(cs + i);
 #pragma unroll
                 for (int g = 0; g < SMALL_G; g++) {
@@ -142,6 +168,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             if (tid == 0 && sKey != 0ull) atomicMax(&s.best[b], sKey);
         }
         cluster.sync();
+        mark();
     }
 
     // ---- select (+ pose candidates + cheirality) : CTA 0, 4 lanes ----
@@ -185,6 +212,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
     }
     if (!(a.mask & SMALL_TRI)) return;
     cluster.sync();
+    mark();
 
     // ---- triangulation: same solve as triangulate_kernel ----
     {
@@ -209,7 +237,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
                 aa[0][c] = fmaf(pt.z, M[8 + c], -M[c]);
                 bb[0][c] = fmaf(pt.w, M[8 + c], -M[4 + c]);
             }
-            dlt_null_power4<1>(x1, y1, aa, bb, v);
+            dlt_null_power4_lanes<LaneF1>(x1[0], y1[0], aa[0], bb[0], v[0]);
             if (!inside) continue;
             float X = 0.0f, Y = 0.0f, Z = 0.0f;
             if (keep[0]) dehomogenise(v[0], X, Y, Z);
@@ -219,7 +247,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             out[(size_t)3 * s.n_stride + i] = 1.0f;
         }
     }
+    mark();
 }
+
+static long long* g_small_dbg = nullptr;
+void small_path_set_debug(long long* d_stamps) { g_small_dbg = d_stamps; }
 
 // Largest cluster the device can co-schedule for this kernel: 16 (non-portable) or 8.
 static int small_cluster_size() {
@@ -251,6 +283,7 @@ cudaError_t launch_small_path(const DeviceState& s, const float* d_px, const int
                               int h_offset, unsigned long long seed, float thr, int compat, int inliers_only, int mask,
                               cudaStream_t st) {
     SmallArgs a;
+    a.dbg = g_small_dbg;
     a.px = (const float4*)d_px;
     for (int i = 0; i < 9; i++) a.kinv.v[i] = s.Kinv[i];
     a.d_idx = d_idx;

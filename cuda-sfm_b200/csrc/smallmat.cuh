@@ -289,6 +289,9 @@ SFM_HD void svd3_reference_orientation(const float* a, float* u, float* s, float
     }
 }
 
+#ifndef SFM_PROJECT_SWEEPS
+#define SFM_PROJECT_SWEEPS 4    // one-sided Jacobi sweeps of the rank-2 projection's 3x3 SVD (3 already reach fp32 accuracy: tools record in DESIGN.md)
+#endif
 // Closest essential matrix in the reference's sense (SfM/kernels.h:281-295):
 // E <- U diag(1,1,0) V^T.  The reference leaves the QR residue of S
 // off-diagonals in (<= 1e-6 typical); we use the exact diag.
@@ -301,7 +304,7 @@ SFM_HD void project_essential(float* E) {
 #pragma unroll
     for (int i = 0; i < 9; i++) En[i] = E[i] * inv;
     float u[9], s[9], v[9];
-    svd3<5>(En, u, s, v);
+    svd3<SFM_PROJECT_SWEEPS>(En, u, s, v);
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -596,6 +599,8 @@ struct LaneF1 {
     static SFM_HD T add(T a, T b) { return a + b; }
     static SFM_HD T neg(T a) { return -a; }
     static SFM_HD T rsqrt_scale(T tr) { return (tr > 0.0f && tr < 3.0e38f) ? sfm_rsqrt(tr) : 0.0f; }
+    static SFM_HD T splat(float c) { return c; }
+    static SFM_HD bool all_below(T num, T lim) { return num <= lim; }      // also true for 0 <= 0 (degenerate: nothing to refine)
 };
 #if defined(__CUDACC__)
 struct LaneF2 {
@@ -605,10 +610,24 @@ struct LaneF2 {
     static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
     static __device__ __forceinline__ T neg(T a) { return make_float2(-a.x, -a.y); }
     static __device__ __forceinline__ T rsqrt_scale(T tr) { return make_float2(LaneF1::rsqrt_scale(tr.x), LaneF1::rsqrt_scale(tr.y)); }
+    static __device__ __forceinline__ T splat(float c) { return make_float2(c, c); }
+    static __device__ __forceinline__ bool all_below(T num, T lim) { return num.x <= lim.x && num.y <= lim.y; }
 };
 #endif
+// Convergence: sin^2 of the angle between the last two iterates, from (w.w)(u.u) - (w.u)^2 - resolvable in fp32 down to
+// ~2e-7.  Every point of a sane two-view geometry passes after the four steps.  Points with sigma_4 / sigma_3 close to 1
+// (gross outliers, a grossly wrong pose) do not: for them S is squared and re-normalised, S <- S S / trace, which doubles
+// the number of power steps per product, and two more products are taken - up to DLT_MAX_SQUARINGS rounds, i.e.
+// 2^6 = 64 steps per product in the last one; whatever has not converged by then has no well-defined null vector in the
+// reference's SVD either.  ~105 instructions per round, in registers, no call; a converged lane that shares a packed
+// pair with an unconverged one just gets more accurate.
+#ifndef DLT_MAX_SQUARINGS
+#define DLT_MAX_SQUARINGS 6
+#endif
+constexpr float DLT_SIN2_CONVERGED = 5e-7f;      // angle between the last two iterates below 7e-4
 template <class L>
-SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const typename L::T* a, const typename L::T* b, typename L::T* v) {
+SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const typename L::T* a, const typename L::T* b, typename L::T* v,
+                                  bool refine = true) {
     typedef typename L::T T;
     T k[4][4];
     const T na3 = L::neg(a[3]), nb3 = L::neg(b[3]);
@@ -626,8 +645,8 @@ SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const type
 #pragma unroll
         for (int j = i; j < 4; j++)
             S[i][j] = L::fma(k[3][i], k[3][j], L::fma(k[2][i], k[2][j], L::fma(k[1][i], k[1][j], L::mul(k[0][i], k[0][j]))));
-    const T r = L::rsqrt_scale(L::add(L::add(S[0][0], S[1][1]), L::add(S[2][2], S[3][3])));
-    const T it = L::mul(r, r);
+    T r = L::rsqrt_scale(L::add(L::add(S[0][0], S[1][1]), L::add(S[2][2], S[3][3])));
+    T it = L::mul(r, r);
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -644,6 +663,39 @@ SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const type
         for (int i = 0; i < 4; i++) w[i] = L::fma(S[i][3], u[3], L::fma(S[i][2], u[2], L::fma(S[i][1], u[1], L::mul(S[i][0], u[0]))));
 #pragma unroll
         for (int i = 0; i < 4; i++) u[i] = L::fma(S[i][3], w[3], L::fma(S[i][2], w[2], L::fma(S[i][1], w[1], L::mul(S[i][0], w[0]))));
+    }
+    if (refine) {
+#pragma unroll 1
+        for (int round = 0; round < DLT_MAX_SQUARINGS; round++) {
+            const T ww = L::fma(w[3], w[3], L::fma(w[2], w[2], L::fma(w[1], w[1], L::mul(w[0], w[0]))));
+            const T uu = L::fma(u[3], u[3], L::fma(u[2], u[2], L::fma(u[1], u[1], L::mul(u[0], u[0]))));
+            const T wu = L::fma(w[3], u[3], L::fma(w[2], u[2], L::fma(w[1], u[1], L::mul(w[0], u[0]))));
+            const T den = L::mul(ww, uu);
+            if (L::all_below(L::fma(L::neg(wu), wu, den), L::mul(den, L::splat(DLT_SIN2_CONVERGED)))) break;
+            T Q[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = i; j < 4; j++)
+                    Q[i][j] = L::fma(S[i][3], S[3][j], L::fma(S[i][2], S[2][j], L::fma(S[i][1], S[1][j], L::mul(S[i][0], S[0][j]))));
+            r = L::rsqrt_scale(L::add(L::add(Q[0][0], Q[1][1]), L::add(Q[2][2], Q[3][3])));
+            it = L::mul(r, r);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = i; j < 4; j++) {
+                    S[i][j] = L::mul(Q[i][j], it);
+                    S[j][i] = S[i][j];
+                }
+            // keep |u| near 1 (two products shrink it by up to 16x per round)
+            const T ru = L::rsqrt_scale(uu);
+#pragma unroll
+            for (int i = 0; i < 4; i++) u[i] = L::mul(u[i], ru);
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[i] = L::fma(S[i][3], u[3], L::fma(S[i][2], u[2], L::fma(S[i][1], u[1], L::mul(S[i][0], u[0]))));
+#pragma unroll
+            for (int i = 0; i < 4; i++) u[i] = L::fma(S[i][3], w[3], L::fma(S[i][2], w[2], L::fma(S[i][1], w[1], L::mul(S[i][0], w[0]))));
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) v[i] = u[i];

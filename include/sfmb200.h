@@ -62,6 +62,10 @@ typedef enum {
                                       SFMB200_OPT_SMALL_PATH_EVALS, 0 never, 1 whenever eligible (projector solver,
                                       H <= 128 * cluster size, reference pose semantics, no per-stage profiling) */
     SFMB200_OPT_SMALL_PATH_EVALS = 8, /* the n * H limit of the automatic choice (default 6,000,000) */
+    SFMB200_OPT_BATCH_PIPELINE = 11, /* whole-path calls on a batch: cut the pairs into this many chunks and generate the hypotheses
+                                      of later chunks on a side stream while earlier chunks are scored (same bits): 2..16 chunks;
+                                      -1 (default), 0, 1: off - measured on B200 the co-resident generation only time-shares the
+                                      FMA pipe with scoring (config 4: 42.41 vs 42.47 ms), see DESIGN.md */
     SFMB200_OPT_SAMPLER = 10,      /* sample rows drawn on the device (d_idx == NULL): 0 (default) 8 distinct indices per hypothesis,
                                       independent between hypotheses; 1 the reference's scheme (sfm.cu:95-104): ONE
                                       permutation of the point indices cut into disjoint groups of 8, which needs
@@ -75,6 +79,8 @@ typedef enum {
 
 const char* sfmb200_last_error(void);
 int sfmb200_version(void);
+/* "src=<hash> nvcc_flags=<...>": hash of the sources this library was compiled from (cuda-sfm_b200/build.py: source_hash) */
+const char* sfmb200_build_info(void);
 
 /* ---- lifetime: SfM::Image_pair::Image_pair / ~Image_pair (SfM/sfm.cu:28-78, 346-359) ---- */
 /* K, Kinv: host 3x3 row-major, as src/main.cpp:292-297 builds them. */
@@ -260,6 +266,10 @@ int sfmb200_stage_times(sfmb200_t* h, int max_sets, float* h_ms, int* sets);
 /* FP32-pipe probe: runs `iters` iterations of an FFMA (mode 0) or FFMA2 (mode 1)
  * stream on all SMs; returns lane-FMAs executed in *fmas and device time in *ms. */
 int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms);
+
+/* measurement hook for the fused small-problem kernel: device int64 [8] receiving clock64() of pair 0 / CTA 0 at its phase
+ * boundaries (start, ingest, hypgen, scoring, pose, triangulation); NULL switches it off */
+int sfmb200_small_path_debug(int64_t* d_stamps);
 
 /* ---- host-side small-matrix entry points (no GPU): svd.h facade + CPU tests ---- */
 void sfmb200_host_svd3(const float a[9], float u[9], float s[9], float v[9]);
