@@ -118,6 +118,9 @@ def dist_setup(gpus: int):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
@@ -472,7 +475,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     # ---- the other BASELINE configs (all ranks take part; rank 0 reports) ----
-    extra = run_configs(pkg, torch, dist, rank, world, K, Kinv, args)
+    extra = {} if args.no_extras else run_configs(pkg, torch, dist, rank, world, K, Kinv, args)
 
     if rank != 0:
         if world > 1:
@@ -649,6 +652,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline config-2 regions only (for profiler captures: skips the sustained run's companions c1, c3, c4, c5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

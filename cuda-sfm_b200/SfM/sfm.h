@@ -142,7 +142,7 @@ public:
     }
     // ---- beyond the reference (its README.md:52,65-69 future work) ----
     // RANSAC that stops once log(1-confidence)/log(1-w^8) hypotheses were tried; returns the number tried
-    int estimateEAdaptive(int maxH, uint64_t seed, float threshold, float confidence = 0.99f, int firstRound = 1024, int growth = 4) {
+    int estimateEAdaptive(int maxH, uint64_t seed, float threshold, float confidence = 0.99f, int firstRound = 4096, int growth = 4) {
         int32_t used = 0;
         check(sfmb200_estimate_e_adaptive(h_, nullptr, maxH, firstRound, growth, seed, threshold, confidence, &used), "estimateEAdaptive");
         return used;

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(TRI_THREADS, SFMB200_TRI_MINB) triangulate_ker
     }
 }
 #ifndef SFMB200_TRI_CTAS_PER_SM
-#define SFMB200_TRI_CTAS_PER_SM 8
+#define SFMB200_TRI_CTAS_PER_SM 16     // measured: 16 -> 15.3 us, 8 -> 16.4 us, one CTA per chunk -> 16.4 us at 1M points (profiles/r02_triangulation.md)
 #endif
 void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st) {
     constexpr int CHUNK = TRI_THREADS * SFMB200_TRI_PTS;

@@ -472,6 +472,7 @@ static const ScoreVariant kVariants[] = {
     {2, 0, 256, 1}, {4, 1, 256, 1}, {4, 0, 256, 1}, {8, 0, 256, 2}, {8, 1, 256, 1},
     {4, 0, 128, 1}, {4, 1, 128, 1}, {8, 0, 128, 4}, {8, 1, 128, 2}, {2, 0, 128, 1},
     {CONST_HPT, 0, CONST_THREADS, CONST_MINB},      // 10: constant-bank path (score_const_kernel)
+    {8, 1, 128, 3},                                 // 11: packed, three 128-thread CTAs per SM = 3 warps per scheduler (<= 168 registers)
 };
 constexpr int kConstVariant = 10;
 // Also measured on B200 and dropped (profiles/r01_variant_sweep.md): 12 / 16 hypotheses per
@@ -503,6 +504,7 @@ static int occupancy_one() {
         case 6: CALL(4, true, 128, 1); break;        \
         case 7: CALL(8, false, 128, 4); break;       \
         case 8: CALL(8, true, 128, 2); break;        \
+        case 11: CALL(8, true, 128, 3); break;       \
         default: CALL(2, false, 128, 1); break;      \
     }
 

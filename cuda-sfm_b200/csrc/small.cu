@@ -29,8 +29,8 @@ namespace sfmb200 {
 
 constexpr int SMALL_THREADS = 512;
 constexpr int SMALL_HC_MAX = 128;        // hypotheses per CTA kept in shared memory
-constexpr int SMALL_G = 4;               // hypotheses per register group in the scoring loop
-constexpr int SMALL_PTS = 8;             // correspondences per thread held in registers while scoring
+constexpr int SMALL_G = 2;               // hypothesis PAIRS per register group in the scoring loop
+constexpr int SMALL_PTS = 5;             // correspondences per thread held in registers while scoring (n <= 2560 without streaming)
 
 struct SmallArgs {
     const float4* px;        // [B][n] pixel correspondences (SMALL_INGEST)
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = s.n, H = a.H;
     const int stride = C * SMALL_THREADS;
-    __shared__ float sE[SMALL_HC_MAX][9];
+    __shared__ float2 sE2[SMALL_HC_MAX / 2][9];      // scaled E of the CTA's hypotheses, two per float2
     __shared__ int sCnt[SMALL_HC_MAX];
     __shared__ unsigned long long sKey;
 
@@ -96,60 +96,71 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         cluster.sync();
         mark();
 
-        // ---- scoring: CTA `rank` owns hypotheses [h0, h1) ----
+        // ---- scoring: CTA `rank` owns hypotheses [h0, h1), scored two at a time in packed FFMA2 (same fma tree per lane
+        //      as the scalar form: sampson.cuh) ----
         const int Hc = (H + C - 1) / C;
         const int h0 = rank * Hc, h1 = min(H, h0 + Hc);
-        const int mine = max(h1 - h0, 0);
+        const int mine = max(h1 - h0, 0), mine_pairs = (mine + 1) >> 1;
         const ThrScale ts = make_thr_scale(a.thr);
         const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
-        for (int t = tid; t < mine * 9; t += SMALL_THREADS) {
-            const int hh = t / 9, q = t - 9 * hh;
-            float v = __ldcg(Eb + (size_t)q * s.h_stride + h0 + hh);      // written by another SM before the barrier
+        for (int t = tid; t < mine_pairs * 18; t += SMALL_THREADS) {
+            const int hh = t / 9, q = t - 9 * hh;                         // hh < 2 * mine_pairs; the odd tail is a zero E
+            float v = hh < mine ? __ldcg(Eb + (size_t)q * s.h_stride + h0 + hh) : 0.0f;   // written by another SM before the barrier
             if (q != 8) v *= thr_scale_factor(ts, q);                      // E~ = D E D (sampson.cuh), as score_kernel does
-            sE[hh][q] = v;
+            reinterpret_cast<float*>(&sE2[hh >> 1][q])[hh & 1] = v;
         }
         for (int t = tid; t < SMALL_HC_MAX; t += SMALL_THREADS) sCnt[t] = 0;
         if (tid == 0) sKey = 0ull;
         __syncthreads();
-        // this thread's correspondences (tid, tid + T, ...) are loaded ONCE into registers - the first version re-read them
-        // from L2 for every hypothesis group and spent 2/3 of the phase waiting for those loads; points beyond
-        // SMALL_PTS per thread (n > 4096) are streamed
+        // this thread's correspondences (tid, tid + T, ...) are loaded ONCE, pre-duplicated for the packed operands;
+        // correspondences beyond SMALL_PTS per thread (n > 2560) are streamed from L2
         const float4* cs = s.corr_s + (size_t)b * s.n_stride;
-        float4 pr[SMALL_PTS];
         const int my_pts = tid < n ? (n - tid + SMALL_THREADS - 1) / SMALL_THREADS : 0;
+        const int warp_pts = (tid & ~31) < n ? (n - (tid & ~31) + SMALL_THREADS - 1) / SMALL_THREADS : 0;      // lane 0's count: the warp's maximum
+        float2 px1[SMALL_PTS], py1[SMALL_PTS], px2[SMALL_PTS], py2[SMALL_PTS];
 #pragma unroll
-        for (int k = 0; k < SMALL_PTS; k++) pr[k] = k < my_pts ? __ldcg(cs + tid + k * SMALL_THREADS) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        for (int g0 = 0; g0 < mine; g0 += SMALL_G) {
-            float e[SMALL_G][9];
-            unsigned int cnt[SMALL_G];
+        for (int k = 0; k < SMALL_PTS; k++) {
+            const float4 p = k < my_pts ? __ldcg(cs + tid + k * SMALL_THREADS) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            px1[k] = make_float2(p.x, p.x); py1[k] = make_float2(p.y, p.y);
+            px2[k] = make_float2(p.z, p.z); py2[k] = make_float2(p.w, p.w);
+        }
+        for (int g0 = 0; g0 < mine_pairs; g0 += SMALL_G) {
+            float2 e2[SMALL_G][9];
+            unsigned int cnt[2 * SMALL_G];
 #pragma unroll
             for (int g = 0; g < SMALL_G; g++) {
-                const int hh = min(g0 + g, mine - 1);
+                const int pp = min(g0 + g, mine_pairs - 1);
 #pragma unroll
-                for (int q = 0; q < 9; q++) e[g][q] = sE[hh][q];
-                cnt[g] = 0u;
+                for (int q = 0; q < 9; q++) e2[g][q] = sE2[pp][q];
+                cnt[2 * g] = cnt[2 * g + 1] = 0u;
             }
 #pragma unroll
             for (int k = 0; k < SMALL_PTS; k++) {
-                const unsigned int valid = k < my_pts ? 1u : 0u;
+                if (k < warp_pts) {                                        // warp-uniform: no work for slots nobody in the warp fills
+                    const unsigned int valid = k < my_pts ? 1u : 0u;
 #pragma unroll
-                for (int g = 0; g < SMALL_G; g++) {
-                    const float d = sampson_unit_d(e[g], pr[k].x, pr[k].y, pr[k].z, pr[k].w);
-                    cnt[g] += (__float_as_uint(d) >> 31) & valid;
+                    for (int g = 0; g < SMALL_G; g++) {
+                        const float2 d = sampson_unit_d2(e2[g], px1[k], py1[k], px2[k], py2[k]);
+                        cnt[2 * g] += (__float_as_uint(d.x) >> 31) & valid;
+                        cnt[2 * g + 1] += (__float_as_uint(d.y) >> 31) & valid;
+                    }
                 }
             }
             for (int i = tid + SMALL_PTS * SMALL_THREADS; i < n; i += SMALL_THREADS) {
                 const float4 p = __ldcg(cs + i);
+                const float2 x1 = make_float2(p.x, p.x), y1 = make_float2(p.y, p.y), x2 = make_float2(p.z, p.z), y2 = make_float2(p.w, p.w);
 #pragma unroll
                 for (int g = 0; g < SMALL_G; g++) {
-                    const float d = sampson_unit_d(e[g], p.x, p.y, p.z, p.w);
-                    cnt[g] += __float_as_uint(d) >> 31;
+                    const float2 d = sampson_unit_d2(e2[g], x1, y1, x2, y2);
+                    cnt[2 * g] += __float_as_uint(d.x) >> 31;
+                    cnt[2 * g + 1] += __float_as_uint(d.y) >> 31;
                 }
             }
 #pragma unroll
-            for (int g = 0; g < SMALL_G; g++) {
+            for (int g = 0; g < 2 * SMALL_G; g++) {
                 const unsigned int w = __reduce_add_sync(0xFFFFFFFFu, cnt[g]);
-                if (lane == 0 && g0 + g < mine && w) atomicAdd(&sCnt[g0 + g], (int)w);
+                const int hh = 2 * g0 + g;
+                if (lane == 0 && (g0 + (g >> 1)) < mine_pairs && hh < mine && w) atomicAdd(&sCnt[hh], (int)w);
             }
         }
         __syncthreads();

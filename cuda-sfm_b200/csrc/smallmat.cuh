@@ -599,8 +599,13 @@ struct LaneF1 {
     static SFM_HD T add(T a, T b) { return a + b; }
     static SFM_HD T neg(T a) { return -a; }
     static SFM_HD T rsqrt_scale(T tr) { return (tr > 0.0f && tr < 3.0e38f) ? sfm_rsqrt(tr) : 0.0f; }
+    typedef bool M;                                                          // per-lane flags
     static SFM_HD T splat(float c) { return c; }
-    static SFM_HD bool all_below(T num, T lim) { return num <= lim; }      // also true for 0 <= 0 (degenerate: nothing to refine)
+    static SFM_HD M none() { return false; }
+    static SFM_HD M below(T num, T lim) { return num <= lim; }              // also true for 0 <= 0 (degenerate: nothing to refine)
+    static SFM_HD M join(M a, M b) { return a || b; }
+    static SFM_HD bool all(M m) { return m; }
+    static SFM_HD T keep(M m, T old_v, T new_v) { return m ? old_v : new_v; }
 };
 #if defined(__CUDACC__)
 struct LaneF2 {
@@ -610,8 +615,13 @@ struct LaneF2 {
     static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
     static __device__ __forceinline__ T neg(T a) { return make_float2(-a.x, -a.y); }
     static __device__ __forceinline__ T rsqrt_scale(T tr) { return make_float2(LaneF1::rsqrt_scale(tr.x), LaneF1::rsqrt_scale(tr.y)); }
+    struct M { bool x, y; };
     static __device__ __forceinline__ T splat(float c) { return make_float2(c, c); }
-    static __device__ __forceinline__ bool all_below(T num, T lim) { return num.x <= lim.x && num.y <= lim.y; }
+    static __device__ __forceinline__ M none() { return M{false, false}; }
+    static __device__ __forceinline__ M below(T num, T lim) { return M{num.x <= lim.x, num.y <= lim.y}; }
+    static __device__ __forceinline__ M join(M a, M b) { return M{a.x || b.x, a.y || b.y}; }
+    static __device__ __forceinline__ bool all(M m) { return m.x && m.y; }
+    static __device__ __forceinline__ T keep(M m, T old_v, T new_v) { return make_float2(m.x ? old_v.x : new_v.x, m.y ? old_v.y : new_v.y); }
 };
 #endif
 // Convergence: sin^2 of the angle between the last two iterates, from (w.w)(u.u) - (w.u)^2 - resolvable in fp32 down to
@@ -665,13 +675,17 @@ SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const type
         for (int i = 0; i < 4; i++) u[i] = L::fma(S[i][3], w[3], L::fma(S[i][2], w[2], L::fma(S[i][1], w[1], L::mul(S[i][0], w[0]))));
     }
     if (refine) {
+        typename L::M done = L::none();
 #pragma unroll 1
         for (int round = 0; round < DLT_MAX_SQUARINGS; round++) {
             const T ww = L::fma(w[3], w[3], L::fma(w[2], w[2], L::fma(w[1], w[1], L::mul(w[0], w[0]))));
             const T uu = L::fma(u[3], u[3], L::fma(u[2], u[2], L::fma(u[1], u[1], L::mul(u[0], u[0]))));
             const T wu = L::fma(w[3], u[3], L::fma(w[2], u[2], L::fma(w[1], u[1], L::mul(w[0], u[0]))));
             const T den = L::mul(ww, uu);
-            if (L::all_below(L::fma(L::neg(wu), wu, den), L::mul(den, L::splat(DLT_SIN2_CONVERGED)))) break;
+            // a lane that has converged is frozen for good: the result of a point never depends on the point it shares
+            // a packed pair with
+            done = L::join(done, L::below(L::fma(L::neg(wu), wu, den), L::mul(den, L::splat(DLT_SIN2_CONVERGED))));
+            if (L::all(done)) break;
             T Q[4][4];
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -689,12 +703,18 @@ SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const type
                 }
             // keep |u| near 1 (two products shrink it by up to 16x per round)
             const T ru = L::rsqrt_scale(uu);
+            T un[4], wn[4], u2[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) u[i] = L::mul(u[i], ru);
+            for (int i = 0; i < 4; i++) un[i] = L::mul(u[i], ru);
 #pragma unroll
-            for (int i = 0; i < 4; i++) w[i] = L::fma(S[i][3], u[3], L::fma(S[i][2], u[2], L::fma(S[i][1], u[1], L::mul(S[i][0], u[0]))));
+            for (int i = 0; i < 4; i++) wn[i] = L::fma(S[i][3], un[3], L::fma(S[i][2], un[2], L::fma(S[i][1], un[1], L::mul(S[i][0], un[0]))));
 #pragma unroll
-            for (int i = 0; i < 4; i++) u[i] = L::fma(S[i][3], w[3], L::fma(S[i][2], w[2], L::fma(S[i][1], w[1], L::mul(S[i][0], w[0]))));
+            for (int i = 0; i < 4; i++) u2[i] = L::fma(S[i][3], wn[3], L::fma(S[i][2], wn[2], L::fma(S[i][1], wn[1], L::mul(S[i][0], wn[0]))));
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                w[i] = L::keep(done, w[i], wn[i]);
+                u[i] = L::keep(done, u[i], u2[i]);
+            }
         }
     }
 #pragma unroll

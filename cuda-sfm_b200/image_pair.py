@@ -131,8 +131,10 @@ class BatchedPairs:
         self.H = H
 
     def estimate_e_adaptive(self, H_max: int, seed: int = 0, thr: float = 1e-6, confidence: float = 0.99,
-                            first_round: int = 1024, growth: int = 4, d_idx=None) -> int:
-        """RANSAC with adaptive termination, rounds skipped on the device; returns the hypotheses tried."""
+                            first_round: int = 4096, growth: int = 4, d_idx=None) -> int:
+        """RANSAC with adaptive termination, rounds skipped on the device; returns the hypotheses tried.  Defaults: rounds
+        [0, 4096), [4096, 16384), [16384, 65536), ... - every round costs three dependent launches and a small round fills
+        the GPU badly, so few and large ones (profiles/r02_adaptive.md)."""
         used = C.c_int32(0)
         self.lib.call("sfmb200_estimate_e_adaptive", self._h, _dptr(d_idx), H_max, first_round, growth, C.c_uint64(seed),
                       C.c_float(thr), C.c_float(confidence), C.byref(used))

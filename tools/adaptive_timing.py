@@ -34,10 +34,11 @@ for outl in (0.3, 0.5, 0.6, 0.7):
     t_fixed = timed(lambda: h.estimate_e(H, 1237, 1e-6))
     cnt_fixed = int(h.get_best()[1][0])
     # time without the D2H of `used` (h_used = NULL): pure enqueue
-    call = lambda: h.lib.call("sfmb200_estimate_e_adaptive", h._h, None, H, 1024, 4, C.c_uint64(1237), C.c_float(1e-6), C.c_float(0.99), None)
-    t_adapt = timed(call)
-    used = h.estimate_e_adaptive(H, 1237, 1e-6, 0.99, 1024, 4)
-    cnt = int(h.get_best()[1][0])
-    print(json.dumps(dict(outlier_frac=outl, n=n, H_max=H, fixed_ms=t_fixed, fixed_inliers=cnt_fixed, adaptive_ms=t_adapt,
-                          adaptive_used=used, adaptive_inliers=cnt)), flush=True)
+    for first, growth in ((1024, 4), (4096, 4), (4096, 16), (8192, 8)):
+        call = lambda: h.lib.call("sfmb200_estimate_e_adaptive", h._h, None, H, first, growth, C.c_uint64(1237), C.c_float(1e-6), C.c_float(0.99), None)
+        t_adapt = timed(call)
+        used = h.estimate_e_adaptive(H, 1237, 1e-6, 0.99, first, growth)
+        cnt = int(h.get_best()[1][0])
+        print(json.dumps(dict(outlier_frac=outl, n=n, H_max=H, first_round=first, growth=growth, fixed_ms=t_fixed, fixed_inliers=cnt_fixed,
+                              adaptive_ms=t_adapt, adaptive_used=used, adaptive_inliers=cnt)), flush=True)
     h.close()
