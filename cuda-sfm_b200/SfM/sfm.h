@@ -170,6 +170,12 @@ public:
         check(sfmb200_chain_views(h_, d_cloud_4xN, d_seen, cameras_3x4, scales, links), "chainViews");
         check(sfmb200_synchronize(h_), "chainViews");
     }
+    // global bundle adjustment of all cameras and points of the chained reconstruction (after chainViews with a cloud;
+    // at most 17 images); cameras_3x4 / stats[8] may be null (see sfmb200_bundle_adjust_global)
+    void bundleAdjustGlobal(float* d_cloud_4xN, const int32_t* d_seen, int iterations = 30, float* cameras_3x4 = nullptr, float* stats = nullptr) {
+        check(sfmb200_bundle_adjust_global(h_, d_cloud_4xN, d_seen, iterations, cameras_3x4, stats), "bundleAdjustGlobal");
+        check(sfmb200_synchronize(h_), "bundleAdjustGlobal");
+    }
     int pairs() const { return image_count - 1; }
     void setCompat(bool reference_semantics) { check(sfmb200_set_option(h_, SFMB200_OPT_COMPAT, reference_semantics), "setCompat"); }
     // host getters; with image_count > 2 the arrays hold one entry per pair: E [pairs()][9], P [pairs()][64]

@@ -52,6 +52,7 @@ SIGNATURES = {
     "sfmb200_mg_set_timeout_ms": (C.c_int, [_vp, C.c_int]),
     "sfmb200_mg_close": (C.c_int, [_vp]),
     "sfmb200_chain_views": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "sfmb200_bundle_adjust_global": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp]),
     "sfmb200_bundle_adjust": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sfmb200_estimate_e_adaptive": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float, C.c_float, _vp]),
     "sfmb200_best_buffer": (C.c_int, [_vp, C.POINTER(_vp)]),

@@ -38,6 +38,10 @@ struct sfmb200_handle {
     BAState ba;
     ChainState chain;
     void* chain_arena;     // lazily allocated by sfmb200_chain_views
+    GbaState gba;
+    void* gba_arena;       // lazily allocated by sfmb200_bundle_adjust_global
+    float* gba_stats;      // device [8] statistics of the last global adjustment
+    bool have_chain;       // chain_views ran on the current reconstruction
     void* staging_in;      // lazily allocated: device copy of pageable host input
     void* staging_out;     // lazily allocated: compact device copy of the points for host output
     void* ba_arena;        // lazily allocated by sfmb200_bundle_adjust (6 floats + 1 byte per correspondence)
@@ -254,6 +258,7 @@ int sfmb200_destroy(sfmb200_t* h) {
     }
     cudaFree(h->arena);
     if (h->chain_arena) cudaFree(h->chain_arena);
+    if (h->gba_arena) cudaFree(h->gba_arena);
     if (h->ba_arena) cudaFree(h->ba_arena);
     if (h->staging_in) cudaFree(h->staging_in);
     if (h->staging_out) cudaFree(h->staging_out);
@@ -498,6 +503,7 @@ int sfmb200_estimate_e_slice(sfmb200_t* h, const int32_t* d_idx, int H_total, in
     h->have_candidates = true;
     h->have_E = true;
     h->have_pose = false;
+    h->have_chain = false;
     h->model = 0;
     return SFMB200_OK;
 }
@@ -535,6 +541,7 @@ int sfmb200_find_homography(sfmb200_t* h, int loops, uint64_t seed, float thresh
     h->have_candidates = true;
     h->have_E = false;        // s.E holds a homography now: the pose stages must not consume it
     h->have_pose = false;
+    h->have_chain = false;
     h->model = 1;
     if (h_H) CK(cudaMemcpyAsync(h_H, h->s.E, (size_t)h->s.B * 9 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (h_matches) CK(cudaMemcpyAsync(h_matches, h->s.best_count, (size_t)h->s.B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -620,6 +627,7 @@ int sfmb200_estimate_e_adaptive(sfmb200_t* h, const int32_t* d_idx, int H_max, i
     h->have_candidates = false;   // the candidate arena holds whichever round ran last, not [0, used)
     h->have_E = true;
     h->have_pose = false;
+    h->have_chain = false;
     h->model = 0;
     if (h_used) {
         CK(cudaMemcpyAsync(h_used, h->adapt + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -782,6 +790,7 @@ int sfmb200_adopt_best(sfmb200_t* h, const int32_t* d_idx, int H_total, uint64_t
     h->launches++;
     h->have_E = true;
     h->have_pose = false;
+    h->have_chain = false;
     h->model = 0;          // s.E is an essential matrix scored at h->thr (set by the slice estimate that preceded)
     return SFMB200_OK;
 }
@@ -795,6 +804,7 @@ int sfmb200_refine_e(sfmb200_t* h, int iterations) {
     h->launches += launch_refit(h->s, h->refit, h->thr > 0 ? h->thr : 1e-6f, iterations, h->stream);
     CKL();
     h->have_pose = false;
+    h->have_chain = false;
     return SFMB200_OK;
 }
 // Scratch of the bundle adjustment: allocated on first use so that handles that never adjust (the batched
@@ -893,6 +903,51 @@ int sfmb200_chain_views(sfmb200_t* h, float* d_cloud, int32_t* d_count, float* h
     if (h_scales) CK(cudaMemcpyAsync(h_scales, h->chain.scales, B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (h_used) CK(cudaMemcpyAsync(h_used, h->chain.used, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (h_cameras || h_scales || h_used) CK(cudaStreamSynchronize(h->stream));
+    h->have_chain = true;
+    return SFMB200_OK;
+}
+
+// Global bundle adjustment of all cameras and all points of the chained reconstruction (chain.cu).
+int sfmb200_bundle_adjust_global(sfmb200_t* h, float* d_cloud, const int32_t* d_count, int iterations, float* h_cameras,
+                                 float* h_stats) {
+    ENTER(h);
+    if (!h || !d_cloud || !d_count) return fail(SFMB200_ERR_ARG, "null argument%s");
+    if (iterations < 1 || iterations > 1000) return fail(SFMB200_ERR_ARG, "iterations must be in [1, 1000]%s");
+    if (h->s.B > GBA_MAX_PAIRS) return fail(SFMB200_ERR_ARG, "bundle_adjust_global handles at most 16 pairs (17 views)%s");
+    if (!h->have_chain || !h->chain_arena || !h->have_points || !h->have_E || !h->have_pose || h->model != 0)
+        return fail(SFMB200_ERR_STATE, "bundle_adjust_global follows chain_views (cloud and count from that call)%s");
+    const DeviceState& s = h->s;
+    if (!h->gba_arena) {
+        const size_t V = s.B + 1, n = s.n_max;
+        const int nb = 148;
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+        size_t o_cam = carve(2 * V * 12 * sizeof(float)), o_pts = carve(2 * 3 * n * sizeof(float)), o_obs = carve(n * sizeof(unsigned int));
+        size_t o_lin = carve(n * 9 * sizeof(float)), o_part = carve(gba_part_doubles(s.B, nb) * sizeof(double));
+        size_t o_p2 = carve((size_t)nb * 2 * sizeof(double)), o_dc = carve(6 * (size_t)s.B * sizeof(double));
+        size_t o_ci = carve(8 * sizeof(int)), o_cf = carve(8 * sizeof(float)), o_st = carve(8 * sizeof(float));
+        CK(cudaMalloc(&h->gba_arena, off));
+        CK(cudaMemsetAsync(h->gba_arena, 0, off, h->stream));
+        char* base = (char*)h->gba_arena;
+        h->gba.cam = (float*)(base + o_cam);
+        h->gba.pts = (float*)(base + o_pts);
+        h->gba.obs = (unsigned int*)(base + o_obs);
+        h->gba.lin = (float*)(base + o_lin);
+        h->gba.part = (double*)(base + o_part);
+        h->gba.part2 = (double*)(base + o_p2);
+        h->gba.dc = (double*)(base + o_dc);
+        h->gba.ctl_i = (int*)(base + o_ci);
+        h->gba.ctl_f = (float*)(base + o_cf);
+        h->gba.nb = nb;
+        h->gba_stats = (float*)(base + o_st);
+    }
+    float* d_stats = h->gba_stats;
+    h->launches += launch_global_ba(h->s, h->chain, h->gba, h->thr > 0 ? h->thr : 1e-6f, iterations, d_cloud, d_count, d_stats, h->stream);
+    CKL();
+    const size_t B = h->s.B;
+    if (h_cameras) CK(cudaMemcpyAsync(h_cameras, h->chain.cameras, (B + 1) * 12 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_stats) CK(cudaMemcpyAsync(h_stats, d_stats, 8 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_cameras || h_stats) CK(cudaStreamSynchronize(h->stream));
     return SFMB200_OK;
 }
 
@@ -1170,6 +1225,7 @@ int sfmb200_set_E(sfmb200_t* h, const float* h_E) {
     CK(cudaStreamSynchronize(h->stream));
     h->have_E = true;
     h->have_pose = false;
+    h->have_chain = false;
     h->model = 0;
     if (!(h->thr > 0)) h->thr = 1e-6f;
     return SFMB200_OK;

@@ -137,6 +137,24 @@ struct ChainState {
 };
 int launch_chain(const DeviceState& s, const ChainState& c, float thr, float* d_cloud, int* d_count, cudaStream_t st);
 
+// Scratch of the global bundle adjustment over the chained reconstruction (chain.cu); allocated on first use.
+struct GbaState {
+    float* cam;             // [2][pairs + 1][12] double-buffered cameras: R row-major (9), t (3)
+    float* pts;             // [2][3][n] double-buffered points (SoA)
+    unsigned int* obs;      // [n] bit k: view k observes the track; 0 = the track takes no part
+    float* lin;             // [n][9] per track: inverse of the damped point block (6, packed) and its gradient (3)
+    double* part;           // [nb][blocks + 1][42] per-CTA partial sums of the reduced camera system (+ the cost)
+    double* part2;          // [nb][2] candidate cost / observations behind their camera
+    double* dc;             // [6 pairs] camera step
+    int* ctl_i;             // [8]
+    float* ctl_f;           // [8]
+    int nb;                 // CTAs of the accumulate / update kernels
+};
+constexpr int GBA_MAX_PAIRS = 16;
+size_t gba_part_doubles(int pairs, int nb);
+int launch_global_ba(const DeviceState& s, const ChainState& c, const GbaState& g, float thr, int iterations, float* d_cloud,
+                     const int* d_count, float* d_stats, cudaStream_t st);
+
 int launch_bundle_adjust(const DeviceState& s, const BAState& ba, float thr, int iterations, float lambda0,
                          int tri_inliers_only, int first_round, float* d_stats, cudaStream_t st);
 

@@ -187,6 +187,20 @@ class BatchedPairs:
         self.lib.call("sfmb200_chain_views", self._h, _dptr(cloud), _dptr(count), _hptr(cams), _hptr(scales), _hptr(used))
         return dict(cameras=cams, scales=scales, used=used, cloud=cloud, count=count)
 
+    GBA_STATS = ("cost_entry", "cost", "accepted", "lambda", "gauge_scale", "iterations", "spare0", "spare1")
+
+    def bundle_adjust_global(self, chain: dict, iterations: int = 30):
+        """Global bundle adjustment of all cameras and points of the chained reconstruction (after chain_views(want_cloud=True),
+        whose dict is passed in and updated: cloud in place, cameras replaced).  Returns the [8] statistics (GBA_STATS)."""
+        if chain.get("cloud") is None or chain.get("count") is None:
+            raise ValueError("bundle_adjust_global needs the cloud and count of chain_views(want_cloud=True)")
+        cams = np.empty((self.pairs + 1, 3, 4), np.float32)
+        st = np.empty(8, np.float32)
+        self.lib.call("sfmb200_bundle_adjust_global", self._h, _dptr(chain["cloud"], "float32", 4 * self.n), _dptr(chain["count"], "int32", self.n),
+                      iterations, _hptr(cams), _hptr(st))
+        chain["cameras"] = cams
+        return st
+
     def pose_candidates(self):
         self.lib.call("sfmb200_pose_candidates", self._h)
 

@@ -209,6 +209,18 @@ int sfmb200_bundle_adjust(sfmb200_t* h, int outer_rounds, int iterations, float*
  * [pairs+1][12] row-major 3x4; h_scales: NULL or host float [pairs]; h_used: NULL or host int32
  * [pairs] tracks that linked pair b-1 and b.  Host outputs force a synchronise. */
 int sfmb200_chain_views(sfmb200_t* h, float* d_cloud, int32_t* d_count, float* h_cameras, float* h_scales, int32_t* h_used);
+/* Global bundle adjustment over the chained reconstruction (README.md:65-69 lists bundle adjustment and more
+ * views as future work): Levenberg-Marquardt on the reprojection error of EVERY observation - track i in view k, for the views
+ * of the pairs in which the track is valid - over all cameras but the first (rotation + translation; camera 0 stays [I|0]) and
+ * one 3-D point per track seen by at least two views.  Point blocks are eliminated; the reduced camera system (6 x pairs
+ * unknowns) is assembled per camera pair and solved on the device by a Cholesky factorisation; a step is accepted on strict
+ * decrease with every observation still in front of its camera (lambda / 3, else 4 lambda); the gauge (|t_1|) is restored at
+ * the end.  Call after sfmb200_chain_views with the d_cloud / d_count of that call: d_cloud (device [4][n]) is updated in place
+ * for the adjusted tracks, the chain's cameras are replaced.  At most 16 pairs.  h_cameras: NULL or host float [pairs+1][12]
+ * row-major 3x4; h_stats: NULL or host float [8]: cost at entry, cost at exit (sum of squared residuals, normalised
+ * coordinates), accepted steps, lambda, gauge scale, iterations run.  Host outputs force a synchronise. */
+int sfmb200_bundle_adjust_global(sfmb200_t* h, float* d_cloud, const int32_t* d_count, int iterations, float* h_cameras,
+                                 float* h_stats);
 int sfmb200_get_refit_iterations(sfmb200_t* h, int32_t* h_accepted /* [pairs] */);
 
 /* ---- poses: computePosecandidates (sfm.cu:238-252), choosePose (254-307) ---- */

@@ -771,6 +771,109 @@ def chain_merge(Xs, valids, G, S):
     return out, cnt
 
 
+GBA_GATE = 25.0
+
+
+def gba_observations(xs, valids, G=None, X=None, thr: float = 1e-6):
+    """Observation set of the global adjustment (chain.cu: gba_prepare_kernel): view k sees track i when the track is valid in
+    a pair that contains view k and - when the chained start (G, X) is given - its reprojection error there is at most
+    GBA_GATE x thr squared (a match can pass a pair's epipolar test and still be wrong along the epipolar line).
+    xs: per pair (n,4) normalised correspondences; valids: per pair (n,) bool.
+    Returns uv (V, n, 2) and obs (V, n) bool; tracks seen by fewer than two views are dropped."""
+    B, n = len(xs), len(xs[0])
+    V = B + 1
+    uv = np.zeros((V, n, 2))
+    obs = np.zeros((V, n), bool)
+    uv[0] = xs[0][:, :2]
+    for b in range(B):
+        uv[b + 1] = xs[b][:, 2:]
+        obs[b] |= valids[b]
+        obs[b + 1] |= valids[b]
+    if G is not None:
+        Xc = np.asarray(X, float)[:3]
+        for k in range(V):
+            Y = Xc.T @ G[k][:3, :3].T + G[k][:3, 3]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                d2 = ((Y[:, :2] / Y[:, 2:3] - uv[k]) ** 2).sum(1)
+            obs[k] &= (Y[:, 2] > 0) & (d2 <= GBA_GATE * thr)
+    obs[:, obs.sum(0) < 2] = False
+    return uv, obs
+
+
+def gba_cost(uv, obs, G, X):
+    c = 0.0
+    for k in range(len(G)):
+        Y = X[:, obs[k]].T @ G[k][:3, :3].T + G[k][:3, 3]
+        if np.any(Y[:, 2] <= 0):
+            return np.inf
+        c += (((Y[:, :2] / Y[:, 2:3]) - uv[k][obs[k]]) ** 2).sum()
+    return float(c)
+
+
+def bundle_adjust_global(uv, obs, G, X, iterations: int = 30, lam0: float = 1e-3):
+    """Global bundle adjustment over the chained reconstruction (chain.cu, sfmb200_bundle_adjust_global) in fp64 with the same
+    parameterisation (cameras 1..V-1: left-multiplicative so(3) update + translation; camera 0 fixed; one point per active
+    track), the same multiplicative LM damping, accept rule (strict decrease, every observation in front of its camera:
+    lambda / 3, else 4 lambda) and final gauge (|t_1| restored).  The step is taken from the explicit damped normal
+    equations - identical to the Schur-complement step of the CUDA code.  G: (V,4,4); X: (3,n) or (4,n).
+    Returns G, X, stats dict."""
+    V, n = obs.shape
+    G = np.array(G, float).copy()
+    X = np.array(X, float)[:3].copy()
+    act = np.flatnonzero(obs.any(0))
+    pid = -np.ones(n, int)
+    pid[act] = np.arange(len(act))
+    ncam = 6 * (V - 1)
+    t1 = np.linalg.norm(G[1][:3, 3]) if V > 1 else 1.0
+    lam = lam0
+    cost = gba_cost(uv, obs, G, X)
+    cost0, accepted = cost, 0
+    for _ in range(iterations):
+        rows = int(obs.sum()) * 2
+        J = np.zeros((rows, ncam + 3 * len(act)))
+        r = np.zeros(rows)
+        q = 0
+        for k in range(V):
+            R, t = G[k][:3, :3], G[k][:3, 3]
+            for i in np.flatnonzero(obs[k]):
+                Q = R @ X[:, i]
+                Y = Q + t
+                iz = 1.0 / Y[2]
+                u, v = Y[0] * iz, Y[1] * iz
+                bp = np.array([[iz, 0, -u * iz], [0, iz, -v * iz]])
+                r[q:q + 2] = [u - uv[k][i, 0], v - uv[k][i, 1]]
+                J[q:q + 2, ncam + 3 * pid[i]: ncam + 3 * pid[i] + 3] = bp @ R
+                if k > 0:
+                    N = np.array([[0, Q[2], -Q[1]], [-Q[2], 0, Q[0]], [Q[1], -Q[0], 0]])
+                    J[q:q + 2, 6 * (k - 1): 6 * (k - 1) + 3] = bp @ N
+                    J[q:q + 2, 6 * (k - 1) + 3: 6 * (k - 1) + 6] = bp
+                q += 2
+        H = J.T @ J
+        H[np.diag_indices_from(H)] *= 1.0 + lam
+        try:
+            d = np.linalg.solve(H, -J.T @ r)
+        except np.linalg.LinAlgError:
+            lam = min(4 * lam, 1e6)
+            continue
+        Gn = G.copy()
+        for k in range(1, V):
+            w, dt = d[6 * (k - 1): 6 * (k - 1) + 3], d[6 * (k - 1) + 3: 6 * (k - 1) + 6]
+            Gn[k][:3, :3] = _rodrigues(w) @ G[k][:3, :3]
+            Gn[k][:3, 3] = G[k][:3, 3] + dt
+        Xn = X.copy()
+        Xn[:, act] += d[ncam:].reshape(-1, 3).T
+        cn = gba_cost(uv, obs, Gn, Xn)
+        if np.isfinite(cn) and cn < cost:
+            G, X, cost, accepted = Gn, Xn, cn, accepted + 1
+            lam = max(lam / 3, 1e-9)
+        else:
+            lam = min(4 * lam, 1e6)
+    sc = t1 / np.linalg.norm(G[1][:3, 3]) if V > 1 else 1.0
+    G[:, :3, 3] *= sc
+    X[:, act] *= sc
+    return G, X, {"cost_entry": cost0, "cost": cost, "accepted": accepted, "lambda": lam, "gauge_scale": sc}
+
+
 def to_vbo(points_soa: np.ndarray) -> np.ndarray:
     """kernCopyPositionsToVBO (kernels.h:471-483): 4xN SoA -> Nx4 AoS (x,y,z,1)."""
     out = points_soa.T.copy()
