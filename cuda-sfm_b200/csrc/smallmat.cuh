@@ -611,8 +611,13 @@ struct LaneF1 {
 struct LaneF2 {
     typedef float2 T;
     static __device__ __forceinline__ T fma(T a, T b, T c) { return __ffma2_rn(a, b, c); }
+#ifdef SFM_LANEF2_MUL_AS_FMA      // experiment: FMUL2 / FADD2 through FFMA2 (a * b + 0, a * 1 + b)
+    static __device__ __forceinline__ T mul(T a, T b) { return __ffma2_rn(a, b, make_float2(0.0f, 0.0f)); }
+    static __device__ __forceinline__ T add(T a, T b) { return __ffma2_rn(a, make_float2(1.0f, 1.0f), b); }
+#else
     static __device__ __forceinline__ T mul(T a, T b) { return __fmul2_rn(a, b); }
     static __device__ __forceinline__ T add(T a, T b) { return __fadd2_rn(a, b); }
+#endif
     static __device__ __forceinline__ T neg(T a) { return make_float2(-a.x, -a.y); }
     static __device__ __forceinline__ T rsqrt_scale(T tr) { return make_float2(LaneF1::rsqrt_scale(tr.x), LaneF1::rsqrt_scale(tr.y)); }
     struct M { bool x, y; };

@@ -44,8 +44,33 @@ acc = h.refine_e(3)
 h.pose_candidates(); h.choose_pose(); h.triangulate()
 st = h.bundle_adjust(2, 4)
 ch = h.chain_views()
+gst = h.bundle_adjust_global(ch, iterations=3)
 Hm, cnt = h.find_homography(1500, 3, 5.0)
 h.synchronize()
-print("8f stages: used", used, "refits", acc.tolist(), "ba inliers", st[:, 6].tolist(), "scales", ch["scales"].tolist(), "h matches", cnt.tolist())
+print("8f stages: used", used, "refits", acc.tolist(), "ba inliers", st[:, 6].tolist(), "scales", ch["scales"].tolist(), "global ba", gst[:3].tolist(),
+      "h matches", cnt.tolist())
 h.close()
+# round 2: fused small-problem path (forced on and off), symmetric-epipolar metric, disjoint sampler, batched pipeline, peer exchange
+for n, H, pairs in ((2153, 269, 1), (900, 100, 3), (4100, 600, 1)):
+    px = np.stack([O.synthetic_pair(n, seed=20 + b)["px"] for b in range(pairs)])
+    h = pkg.BatchedPairs(K, Kinv, pairs, n, H)
+    for small in (1, 0):
+        h.set_option(7, small)
+        out = h.run_host(px, H, 5, 1e-6)
+        h.set_points_xy(torch.from_numpy(px).cuda())
+        h.estimate_e(H, 5, 1e-6)
+    h.set_option(9, 1)
+    h.run_device(torch.from_numpy(px).cuda(), H, 5, 1e-6)
+    h.set_option(9, 0)
+    h.set_option(10, 1)
+    h.estimate_e(min(H, n // 8), 5, 1e-6)
+    h.set_option(10, 0)
+    h.set_option(11, 2)
+    h.run_device(torch.from_numpy(px).cuda(), H, 5, 1e-6)
+    pkg.sharding.connect_peers(h, 0, 1)
+    pkg.sharding.estimate_e_p2p(h, H, 5, 1e-6)
+    pkg.sharding.estimate_e_p2p(h, H, 6, 1e-6)
+    h.synchronize()
+    print("round-2 paths", n, H, pairs, "inliers", out["inliers"].tolist(), "timeouts", pkg.sharding.p2p_timeouts(h))
+    h.close()
 print("sanitize run done")
