@@ -45,6 +45,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 N_CORR, N_HYP, THR, SEED = 10_000, 65_536, 1e-6, 1237
+WORKLOAD = ("BASELINE config 2: synthetic two-view scene, 10,000 correspondences, 30% outliers, 1 px noise, 65,536 hypotheses, "
+            "full hot path per pair (ingest, hypgen, scoring+arg-max, pose candidates, cheirality, triangulation)")
 FLOP_PER_EVAL = 34.0              # 15 FFMA x2 + 3 FMUL + 1 compare
 # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch at this config,
 # from the ncu --set full capture summarised in profiles/r01_ncu_summary.md
@@ -536,9 +538,7 @@ def run_ours(args):
         "metric": "RANSAC hyp*corr evals/s", "value": value, "unit": "hyp*corr evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2: synthetic two-view scene, 10,000 correspondences, 30% outliers, "
-                               "1 px noise, 65,536 hypotheses, full hot path per pair (ingest, hypgen, scoring+arg-max, "
-                               "pose candidates, cheirality, triangulation)", "pairs_per_step_per_gpu": 1,
+        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1,
                    "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective",
                    "l2": "flushed between timed iterations (256 MiB write)", "threshold": THR, "seed": SEED,
                    "score_plan": score_plan},
@@ -592,7 +592,8 @@ def run_reference(args):
         x = O.normalise_points(px, Kinv)
         cpu = cpu_baseline(O, x)
         line = dict(base, value=cpu["value"], steps=1, warmup=0, ms_per_step=1e3 * N_HYP * N_CORR / cpu["value"],
-                    config={"workload": "BASELINE config 2 estimateE on the host cores (oracle port; oracle/_ref/libsfm_ref.so or GPU missing)"},
+                    config={"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "threshold": THR, "seed": SEED,
+                            "note": "estimateE on the host cores (oracle port; oracle/_ref/libsfm_ref.so or GPU missing)"},
                     cpu_baseline=cpu, e2e={"value": cpu["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(line), flush=True)
         return
@@ -635,7 +636,7 @@ def run_reference(args):
               f"fillXU + estimateE body with {Hs} of {H} injected hypotheses x {N_CORR} correspondences + "
               f"computePosecandidates + choosePose + linear_triangulation; host wall clock incl. its cudaMalloc/syncs")
     line = dict(base, value=value, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms,
-                config={"workload": "BASELINE config 2: 10,000 correspondences, 30% outliers, 65,536 hypotheses, full hot path per pair",
+                config={"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "threshold": THR, "seed": SEED,
                         "hypotheses_per_step": Hs, "first_full_size_step_s": t_first},
                 stage_ms={"estimateE": float(st[0]), "computePosecandidates": float(st[1]), "choosePose": float(st[2]),
                           "linear_triangulation": float(st[3])},
