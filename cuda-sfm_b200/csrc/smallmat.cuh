@@ -17,6 +17,17 @@
 
 namespace sfmb200 {
 
+// Raw MUFU.RSQ (rsqrt.approx.ftz.f32): rsqrtf() without -use_fast_math wraps the same instruction in denormal handling
+// (two FSETP, an FSEL and two FMUL by 2^24 / 2^12 per call); every caller here feeds it a normal number (sums of squares
+// behind explicit floors), for which the two give the same bits.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float sfm_mufu_rsq(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#endif
+
 // Symmetric Jacobi rotation that annihilates a_pq.  Returns (c, s, t) of the
 // rotation J = [c s; -s c] applied as A <- J^T A J, i.e. the classic
 //   t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (a_qq - a_pp) / (2 a_pq).
@@ -47,10 +58,10 @@ SFM_HD void jacobi_angle_fast(float app, float aqq, float apq, float& c, float& 
     float alpha = 0.5f * (aqq - app);
     float rho2 = fmaf(alpha, alpha, apq * apq);
     bool skip = !(rho2 > 1e-36f) || apq == 0.0f;
-    float rho = rho2 * rsqrtf(rho2);
+    float rho = rho2 * sfm_mufu_rsq(rho2);
     float denom = alpha + copysignf(rho, alpha);
     float tt = skip ? 0.0f : __fdividef(apq, denom);
-    float cc = rsqrtf(fmaf(tt, tt, 1.0f));
+    float cc = sfm_mufu_rsq(fmaf(tt, tt, 1.0f));
     c = cc;
     s = tt * cc;
     t = tt;
@@ -63,7 +74,7 @@ SFM_HD void jacobi_angle_fast(float app, float aqq, float apq, float& c, float& 
 // where the result feeds a self-correcting iteration or a normalisation.
 SFM_HD float sfm_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    return sfm_mufu_rsq(x);
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -73,7 +84,7 @@ SFM_HD float sfm_rsqrt(float x) {
 // exact value does not matter (conditioning scales).
 SFM_HD float sfm_sqrt_approx(float x) {
 #if defined(__CUDA_ARCH__)
-    return x > 0.0f ? x * rsqrtf(x) : 0.0f;
+    return x > 1e-30f ? x * sfm_mufu_rsq(x) : 0.0f;
 #else
     return sqrtf(x);
 #endif
@@ -91,7 +102,7 @@ SFM_HD void givens(float a, float b, float& c, float& s) {
     float r2 = fmaf(a, a, b * b);
     if (r2 < 1e-37f) { c = 1.0f; s = 0.0f; return; }
 #if defined(__CUDA_ARCH__)
-    float ir = rsqrtf(r2);
+    float ir = sfm_mufu_rsq(r2);
 #else
     float ir = 1.0f / sqrtf(r2);
 #endif
