@@ -120,9 +120,9 @@ def dist_setup(gpus: int):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL's own log (the "NCCL version ..." banner at NCCL_DEBUG >= VERSION, warnings)
+        # goes to a file instead of stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sfmb200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 

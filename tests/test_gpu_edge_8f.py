@@ -139,3 +139,31 @@ def test_python_mirror_validates_buffers(pkg, O):
     with pytest.raises(TypeError):
         h.estimate_e(H, 1, 1e-6, d_idx=torch.zeros((H, 8), dtype=torch.int64, device="cuda"))
     h.close()
+
+
+def test_handle_keeps_its_device_when_another_is_current(pkg, O):
+    """a handle belongs to the device that was current at create; every entry point makes that device current for
+    the call and restores the caller's.  Needs two GPUs (skipped on a one-GPU box)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    K, Kinv = O.reference_K()
+    n, H = 3000, 4096
+    px = O.synthetic_pair(n, seed=31)["px"]
+    torch.cuda.set_device(0)
+    ref = pkg.BatchedPairs(K, Kinv, 1, n, H)
+    want = ref.run_host(px, H, 3, THR)
+    torch.cuda.set_device(1)
+    h1 = pkg.BatchedPairs(K, Kinv, 1, n, H)              # lives on device 1
+    torch.cuda.set_device(0)                               # ... and is driven while device 0 is current
+    got = h1.run_host(px, H, 3, THR)
+    assert torch.cuda.current_device() == 0
+    for k in ("E", "P", "pose_index", "inliers", "points"):
+        assert np.array_equal(got[k], want[k]), k
+    d_px1 = torch.from_numpy(px).to("cuda:1")
+    h1.set_points_xy(d_px1)
+    h1.estimate_e(H, 3, THR)
+    h1.pose_candidates(); h1.choose_pose(); h1.triangulate()
+    assert np.array_equal(h1.get_points_host(0), want["points"][0])
+    h1.close(); ref.close()

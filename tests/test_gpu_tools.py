@@ -102,3 +102,28 @@ def test_whole_path_is_cuda_graph_capturable(pkg, O):
         got = (h.get_best()[0], h.get_E(), h.get_points_host(0))
         assert all(np.array_equal(a, b) for a, b in zip(ref, got))
         h.close()
+
+
+def test_bench_json_contract_reduced_extras():
+    """bench.py prints ONE JSON line with the contract's keys; the extra configs run at a reduced scale here
+    (SFMB200_BENCH_SCALE shrinks configs 3-5 only: the headline config 2 is always full size)."""
+    env = dict(os.environ, SFMB200_BENCH_SCALE="0.01")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3"], capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = [l for l in r.stdout.strip().splitlines() if l.strip()]
+    assert len(out) == 1, out[:3]
+    d = json.loads(out[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "sustained", "c1", "c3", "c4", "c5", "library"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["dtype"] == "f32" and "workload" in d["config"] and d["vs_baseline"] is None
+    assert d["value"] > 1e12 and d["e2e"]["value"] > 1e12 and d["e2e"]["h2d_bytes_per_step"] == 160000 and d["gpu_launches"] == 25
+    rf = d["roofline"]
+    assert 0.5 < rf["frac"] < 1.0 and rf["traffic"] > 2e6 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    assert d["library"]["built_from_this_tree"] is True
+    assert d["c3"]["same_winner_both_exchanges"] is True and d["c3"]["p2p"]["timeouts"] == 0
+    assert d["c1"]["winner"] == d["c1"]["winner_fixture_fp64"] or abs(d["c1"]["winner"][1] - d["c1"]["winner_fixture_fp64"][1]) <= 3
+    assert d["roofline_triangulation"]["frac"] is not None and d["c4"]["pairs"] >= 1
+    assert d["sustained"]["wall_s"] >= 1.5 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
