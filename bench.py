@@ -120,9 +120,6 @@ def dist_setup(gpus: int):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own log (the "NCCL version ..." banner at NCCL_DEBUG >= VERSION, warnings)
-        # goes to a file instead of stdout
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sfmb200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
@@ -567,7 +564,7 @@ def run_ours(args):
         **extra,
     }
     line["e2e"]["ms_per_pair_pageable_buffers"] = h2d_pageable
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -595,7 +592,7 @@ def run_reference(args):
                     config={"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "threshold": THR, "seed": SEED,
                             "note": "estimateE on the host cores (oracle port; oracle/_ref/libsfm_ref.so or GPU missing)"},
                     cpu_baseline=cpu, e2e={"value": cpu["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     torch.cuda.set_device(0)
     L = C.CDLL(path)
@@ -643,11 +640,30 @@ def run_reference(args):
                 cpu_baseline={"value": value, "unit": base["unit"], "cores": 1, "kind": "reference", "sample": sample,
                               "note": "the reference has no CPU path (README.md:12); this is its CUDA path on the same B200"},
                 e2e={"value": value, "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    print(json.dumps(line), flush=True)
+    emit(line)
     L.ref_destroy(r)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, written to the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner to stdout at
+    # NCCL_DEBUG >= VERSION): from here on file descriptor 1 points at stderr and emit() writes to the saved real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
