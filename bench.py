@@ -322,6 +322,19 @@ def run_configs(pkg, torch, dist, rank, world, K, Kinv, args) -> dict:
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
             dev[name] = sorted(ts)[len(ts) // 2]
+        # the same single-launch call with the stream kept busy by a ~100 us spin kernel while the host submits: the event pair then
+        # holds device time only (above, an idle GPU waits for the host to get from record() to the launch: ~10 us of Python + driver)
+        ts = []
+        for i in range(40):
+            flush[: 1 << 20].fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(200000)
+            a.record()
+            h.run_device(d_px1, H1, SEED, THR)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        dev["run_device_stream_busy"] = sorted(ts)[len(ts) // 2]
         staged()
         bi, bc = h.get_best()
         hp1 = torch.from_numpy(px1).pin_memory().numpy()
@@ -594,6 +607,31 @@ def run_reference(args):
                     cpu_baseline=cpu, e2e={"value": cpu["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         emit(line)
         return
+    if not args.ref_child:
+        # The reference exit()s the process on any CUDA error (common.cu:14) and its as-built path reads uninitialised memory
+        # (SURVEY Q9-Q13), so a run of it can die: it runs in a child process, is retried, and only then replaced by the port.
+        import subprocess
+        last = ""
+        for attempt in range(3):
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-child", "--gpus", str(args.gpus),
+                                "--steps", str(args.steps), "--warmup", str(args.warmup)], capture_output=True, text=True,
+                               env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+            rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode == 0 and rows:
+                line = json.loads(rows[-1])
+                line["attempts"] = attempt + 1
+                emit(line)
+                return
+            last = (r.stderr.strip().splitlines() or ["no output"])[-1][:200]
+            sys.stderr.write(f"[bench] reference child attempt {attempt + 1} failed (rc {r.returncode}): {last}\n")
+        x = O.normalise_points(px, Kinv)
+        cpu = cpu_baseline(O, x)
+        line = dict(base, value=cpu["value"], steps=1, warmup=0, ms_per_step=1e3 * N_HYP * N_CORR / cpu["value"],
+                    config={"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "threshold": THR, "seed": SEED,
+                            "note": f"estimateE on the host cores (oracle port): the reference's CUDA path died three times on this box ({last})"},
+                    cpu_baseline=cpu, e2e={"value": cpu["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        emit(line)
+        return
     torch.cuda.set_device(0)
     L = C.CDLL(path)
     L.ref_create.restype = C.c_void_p
@@ -669,6 +707,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-extras", action="store_true",
                     help="headline config-2 regions only (for profiler captures: skips the sustained run's companions c1, c3, c4, c5)")
     args = ap.parse_args()

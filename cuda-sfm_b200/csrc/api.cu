@@ -1363,7 +1363,7 @@ int sfmb200_small_path_debug(int64_t* d_stamps) {
 }
 
 int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms) {
-    if (!fmas || !ms || iters < 1 || mode < 0 || mode > 1) return fail(SFMB200_ERR_ARG, "bad argument%s");
+    if (!fmas || !ms || iters < 1 || mode < 0 || mode > 4) return fail(SFMB200_ERR_ARG, "bad argument%s");
     float* sink = nullptr;
     cudaEvent_t e0, e1;
     CK(cudaMalloc(&sink, 256));

@@ -368,7 +368,12 @@ __global__ void __launch_bounds__(TRI_THREADS, SFMB200_TRI_MINB) triangulate_ker
                 a[c] = __ffma2_rn(x2, m2, make_float2(-M[c], -M[c]));
                 bb[c] = __ffma2_rn(y2, m2, make_float2(-M[4 + c], -M[4 + c]));
             }
+#ifdef SFMB200_TRI_COPY_ONLY     // measurement build: the launch shape and the memory traffic without the solve (tools/tri_ab.py)
+#pragma unroll
+            for (int c = 0; c < 4; c++) vv[c] = __ffma2_rn(a[c], x1, __fmul2_rn(bb[c], y1));
+#else
             dlt_null_power4_lanes<LaneF2>(x1, y1, a, bb, vv);
+#endif
 #pragma unroll
             for (int c = 0; c < 4; c++) { v[0][c] = vv[c].x; v[1][c] = vv[c].y; }
         } else {

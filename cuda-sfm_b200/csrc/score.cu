@@ -646,7 +646,12 @@ __global__ void __launch_bounds__(PROBE_THREADS) fma_probe_kernel(int iters, flo
 #pragma unroll
             for (int r = 0; r < PROBE_INNER; r++)
 #pragma unroll
-                for (int i = 0; i < PROBE_CHAINS; i++) acc[i] = __ffma2_rn(acc[i], a, b);
+                for (int i = 0; i < PROBE_CHAINS; i++) {
+                    if constexpr (MODE == 1) acc[i] = __ffma2_rn(acc[i], a, b);
+                    else if constexpr (MODE == 2) acc[i] = __fmul2_rn(acc[i], a);                                   // FMUL2
+                    else if constexpr (MODE == 3) acc[i] = __fadd2_rn(acc[i], b);                                   // FADD2
+                    else acc[i] = __ffma2_rn(acc[i], a, make_float2(-acc[(i + 1) % PROBE_CHAINS].x, -acc[(i + 1) % PROBE_CHAINS].y));   // negated register operand
+                }
         }
         float t = 0.0f;
 #pragma unroll
@@ -659,8 +664,14 @@ double launch_fma_probe(int mode, int iters, cudaStream_t st, float* d_sink) {
     const int ctas = 148 * 8;
     if (mode == 0)
         fma_probe_kernel<0><<<ctas, PROBE_THREADS, 0, st>>>(iters, d_sink, 0.999f, 0.001f);
-    else
+    else if (mode == 1)
         fma_probe_kernel<1><<<ctas, PROBE_THREADS, 0, st>>>(iters, d_sink, 0.999f, 0.001f);
+    else if (mode == 2)
+        fma_probe_kernel<2><<<ctas, PROBE_THREADS, 0, st>>>(iters, d_sink, 0.999f, 0.001f);
+    else if (mode == 3)
+        fma_probe_kernel<3><<<ctas, PROBE_THREADS, 0, st>>>(iters, d_sink, 0.999f, 0.001f);
+    else
+        fma_probe_kernel<4><<<ctas, PROBE_THREADS, 0, st>>>(iters, d_sink, 0.999f, 0.001f);
     double per_thread = (double)iters * PROBE_INNER * PROBE_CHAINS * (mode == 0 ? 1.0 : 2.0);
     return per_thread * PROBE_THREADS * ctas;
 }

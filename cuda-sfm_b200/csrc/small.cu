@@ -41,7 +41,7 @@ struct SmallArgs {
     int H, h_offset;
     float thr;
     int compat, inliers_only, mask;
-    long long* dbg;          // optional [8] clock64 stamps of CTA 0 thread 0 at the phase boundaries (tools/small_phases.py)
+    long long* dbg;          // optional [16] clock64 stamps (0..5 phase boundaries, 8..14 inside scoring / pose) of CTA 0 thread 0 at the phase boundaries (tools/small_phases.py)
 };
 
 __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceState s, SmallArgs a) {
@@ -61,6 +61,9 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
     auto mark = [&]() {
         if (a.dbg != nullptr && rank == 0 && tid == 0 && b == 0) a.dbg[stamp] = clock64();
         stamp++;
+    };
+    auto sub = [&](int id) {            // finer stamps inside a phase (slots 8..15), same thread
+        if (a.dbg != nullptr && rank == 0 && tid == 0 && b == 0) a.dbg[id] = clock64();
     };
     mark();
 
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         for (int t = tid; t < SMALL_HC_MAX; t += SMALL_THREADS) sCnt[t] = 0;
         if (tid == 0) sKey = 0ull;
         __syncthreads();
+        sub(8);
         // this thread's correspondences (tid, tid + T, ...) are loaded ONCE, pre-duplicated for the packed operands;
         // correspondences beyond SMALL_PTS per thread (n > 2560) are streamed from L2
         const float4* cs = s.corr_s + (size_t)b * s.n_stride;
@@ -163,7 +167,9 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
                 if (lane == 0 && (g0 + (g >> 1)) < mine_pairs && hh < mine && w) atomicAdd(&sCnt[hh], (int)w);
             }
         }
+        sub(9);
         __syncthreads();
+        sub(10);
         unsigned long long key = 0ull;
         int* counts = s.counts + (size_t)b * s.h_stride;
         for (int t = tid; t < mine; t += SMALL_THREADS) {
@@ -178,6 +184,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             __syncthreads();
             if (tid == 0 && sKey != 0ull) atomicMax(&s.best[b], sKey);
         }
+        sub(11);
         cluster.sync();
         mark();
     }
@@ -205,8 +212,10 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
 #pragma unroll
                 for (int k = 0; k < 9; k++) E[k] = s.E[(size_t)b * 9 + k];
             }
+            sub(12);
             if (a.mask & SMALL_POSE) {
                 pose_candidate(E, c, a.compat, P);
+                sub(13);
                 if (a.compat) {
                     const float4 c0 = __ldcg(s.corr + (size_t)b * s.n_stride);
                     float Minv[16];
@@ -222,6 +231,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         if (lane == 0 && (a.mask & SMALL_POSE) && a.compat) s.P_ind[b] = m ? 31 - __clz(m) : 0;      // last passing index (sfm.cu:284-297)
     }
     if (!(a.mask & SMALL_TRI)) return;
+    sub(14);
     cluster.sync();
     mark();
 

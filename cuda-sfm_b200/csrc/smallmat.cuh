@@ -647,6 +647,9 @@ struct LaneF2 {
 // 2^6 = 64 steps per product in the last one; whatever has not converged by then has no well-defined null vector in the
 // reference's SVD either.  ~105 instructions per round, in registers, no call; a converged lane that shares a packed
 // pair with an unconverged one just gets more accurate.
+#ifndef DLT_POWER_PAIRS
+#define DLT_POWER_PAIRS 2      // fixed products with S before the first convergence check, in pairs
+#endif
 #ifndef DLT_MAX_SQUARINGS
 #define DLT_MAX_SQUARINGS 6
 #endif
@@ -684,7 +687,7 @@ SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const type
 #pragma unroll
     for (int i = 0; i < 4; i++) u[i] = L::mul(k[3][i], r);
 #pragma unroll
-    for (int step = 0; step < 2; step++) {
+    for (int step = 0; step < DLT_POWER_PAIRS; step++) {
 #pragma unroll
         for (int i = 0; i < 4; i++) w[i] = L::fma(S[i][3], u[3], L::fma(S[i][2], u[2], L::fma(S[i][1], u[1], L::mul(S[i][0], u[0]))));
 #pragma unroll

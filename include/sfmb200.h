@@ -275,12 +275,13 @@ int64_t sfmb200_launch_count(sfmb200_t* h);
 int sfmb200_stage_times(sfmb200_t* h, int max_sets, float* h_ms, int* sets);
 
 /* ---- measurement helpers ---- */
-/* FP32-pipe probe: runs `iters` iterations of an FFMA (mode 0) or FFMA2 (mode 1)
- * stream on all SMs; returns lane-FMAs executed in *fmas and device time in *ms. */
+/* FP32-pipe probe: runs `iters` iterations of an FFMA (mode 0), FFMA2 (mode 1), FMUL2 (2), FADD2 (3) or FFMA2-with-a-negated-
+ * register-operand (4) stream on all SMs; returns lane operations executed in *fmas and device time in *ms. */
 int sfmb200_fma_probe(int mode, int iters, double* fmas, float* ms);
 
-/* measurement hook for the fused small-problem kernel: device int64 [8] receiving clock64() of pair 0 / CTA 0 at its phase
- * boundaries (start, ingest, hypgen, scoring, pose, triangulation); NULL switches it off */
+/* measurement hook for the fused small-problem kernel: device int64 [16] receiving clock64() of pair 0 / CTA 0 at its phase
+ * boundaries (slots 0..5: start, ingest, hypgen, scoring, pose, triangulation) and inside the scoring / pose phases (8..14);
+ * NULL switches it off */
 int sfmb200_small_path_debug(int64_t* d_stamps);
 
 /* ---- host-side small-matrix entry points (no GPU): svd.h facade + CPU tests ---- */

@@ -11,7 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     pkg = entry.load_package()
     lib = pkg.load_library(path)
     K, Kinv = pkg.synthetic.reference_K()
-    for n in (1 << 20, 10000):
+    for n in (1 << 20, 1 << 22, 1 << 24, 10000):
         H = 4096
         px = pkg.synthetic.synthetic_pair(n, 0.3, 1.0, seed=77)["px"]
         d_px = torch.from_numpy(px[None]).cuda()
@@ -25,6 +25,19 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
             a.record(); h.triangulate(); b.record(); torch.cuda.synchronize()
             ms.append(a.elapsed_time(b))
         ms = sorted(ms[5:])
+        # third method: flush by writing, then READ a buffer larger than L2 (no dirty lines left to evict under the kernel), then
+        # a ~50 us spin kernel so that the host has submitted everything before the first event fires
+        big = torch.empty(64 << 20, dtype=torch.float32, device="cuda").fill_(1.0)
+        clean = []
+        for i in range(45):
+            flush.fill_(i & 0xFF)
+            big.sum()
+            torch.cuda._sleep(100000)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); h.triangulate(); b.record(); torch.cuda.synchronize()
+            clean.append(a.elapsed_time(b))
+        clean = sorted(clean[5:])
+        del big
         # second method: no flush writes; 12 handles of the same size used round robin, so the 16 MB input of a launch was
         # evicted by the 11 x 32 MB the other launches moved since it was last touched (inputs larger than L2)
         rot_ms = None
@@ -46,7 +59,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
                 hk.close()
         pts = h.get_points_host()
         t = ms[len(ms) // 2]
-        print(json.dumps(dict(lib=os.path.basename(path), n=n, tri_ms_median=t, tri_ms_min=ms[0], rotating_inputs_ms=rot_ms, gbs=32 * n / (t * 1e-3) / 1e9,
+        print(json.dumps(dict(lib=os.path.basename(path), n=n, tri_ms_median=t, tri_ms_min=ms[0], rotating_inputs_ms=rot_ms, clean_l2_ms_median=clean[len(clean) // 2], clean_l2_ms_min=clean[0], clean_frac_hbm=32 * n / (clean[len(clean) // 2] * 1e-3) / 1e9 / 6543.7, gbs=32 * n / (t * 1e-3) / 1e9,
                               frac_hbm=32 * n / (t * 1e-3) / 1e9 / 6543.7, checksum=float(np.nansum(np.abs(pts[:3]).clip(0, 1e3))),
                               nonfinite=int((~np.isfinite(pts)).sum()))), flush=True)
         h.close()
