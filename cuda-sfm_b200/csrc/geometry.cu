@@ -320,7 +320,14 @@ __global__ void __launch_bounds__(TRI_THREADS, SFMB200_TRI_MINB) triangulate_ker
     static_assert(PTS == 1 || PTS == 2, "one point per thread, or two in packed f32x2 arithmetic");
     pdl_wait();
     const int b = blockIdx.y;
+    // (Tried on the cold start - the selected pose sits behind its index, two dependent misses: requesting the first points
+    //  before the pose: 135 vs 131 us at 16M points, no change at 1M; an L2 prefetch of the four candidates from every thread:
+    //  600k requests for the same two lines serialise on one L2 slice, 26.6 us instead of 14.3 us at 1M points.)
+#ifdef SFMB200_TRI_FIXED_POSE      // measurement build: candidate 0 without the dependent index load
+    const float* Mg = s.P + (size_t)b * 64;
+#else
     const float* Mg = s.P + (size_t)b * 64 + 16 * __ldg(s.P_ind + b);
+#endif
     float M[12], e[9];
 #pragma unroll
     for (int k = 0; k < 12; k++) M[k] = __ldg(Mg + k);
@@ -398,20 +405,105 @@ __global__ void __launch_bounds__(TRI_THREADS, SFMB200_TRI_MINB) triangulate_ker
         }
     }
 }
+// Two ADJACENT points per thread (2j, 2j + 1) in packed f32x2: one pointer walks the correspondences, each output row
+// takes one 8-byte store per thread, and the bounds live outside the loop (an odd last point goes to the scalar tail).
+// Issue cost of a packed instruction on this part is two slots (tools/pipe_probe.py), so what the loop saves is its
+// non-arithmetic half: addresses, predicates, operand moves.
+template <bool INLIERS_ONLY>
+__global__ void __launch_bounds__(TRI_THREADS, SFMB200_TRI_MINB) triangulate_pairs_kernel(DeviceState s, float thr) {
+    pdl_wait();
+    const int b = blockIdx.y;
+    const int n = s.n, pairs = (n + 1) >> 1;            // an odd last point rides alone in the last pair (its twin is a copy)
+    const float4* corr = s.corr + (size_t)b * s.n_stride;
+    float* out = s.points + (size_t)b * 4 * s.n_stride;
+    int j = blockIdx.x * TRI_THREADS + threadIdx.x;
+    const int jstep = gridDim.x * TRI_THREADS;
+    // the first correspondences are in flight before anything waits for the pose
+    const float4* src = corr + 2 * (size_t)j;
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 n0 = zero4, n1 = zero4;
+    if (j < pairs) { n0 = __ldg(src); n1 = 2 * j + 1 < n ? __ldg(src + 1) : n0; }
+    const float* Mg = s.P + (size_t)b * 64 + 16 * __ldg(s.P_ind + b);
+    float M[12], e[9];
+#pragma unroll
+    for (int k = 0; k < 12; k++) M[k] = __ldg(Mg + k);
+    if constexpr (INLIERS_ONLY) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) e[k] = __ldg(s.E + (size_t)b * 9 + k);
+    }
+    const size_t row = (size_t)s.n_stride;
+    float2* dst = reinterpret_cast<float2*>(out) + j;
+    const float2 one2 = make_float2(1.0f, 1.0f);
+    for (; j < pairs; j += jstep) {
+        const float4 p0 = n0, p1 = n1;
+        src += 2 * (size_t)jstep;
+        const int jn = j + jstep;
+        if (jn < pairs) { n0 = __ldg(src); n1 = 2 * jn + 1 < n ? __ldg(src + 1) : n0; }
+        const float2 x1 = make_float2(p0.x, p1.x), y1 = make_float2(p0.y, p1.y);
+        const float2 x2 = make_float2(p0.z, p1.z), y2 = make_float2(p0.w, p1.w);
+        // rows 2, 3 of the DLT matrix (compute_linear_triangulation_A, kernels.h:387-431), then the null vector
+        float2 a[4], bb[4], vv[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float2 m2 = make_float2(M[8 + c], M[8 + c]);
+            a[c] = __ffma2_rn(x2, m2, make_float2(-M[c], -M[c]));
+            bb[c] = __ffma2_rn(y2, m2, make_float2(-M[4 + c], -M[4 + c]));
+        }
+#ifdef SFMB200_TRI_COPY_ONLY     // measurement build: the launch shape and the memory traffic without the solve (tools/tri_ab.py)
+#pragma unroll
+        for (int c = 0; c < 4; c++) vv[c] = __ffma2_rn(a[c], x1, __fmul2_rn(bb[c], y1));
+#else
+        dlt_null_power4_lanes<LaneF2>(x1, y1, a, bb, vv);
+#endif
+        float2 X, Y, Z;
+        dehomogenise2(vv, X, Y, Z);
+        if constexpr (INLIERS_ONLY) {
+            if (!(epipolar_d(s.metric, e, p0.x, p0.y, p0.z, p0.w, -thr) < 0.0f)) { X.x = 0.0f; Y.x = 0.0f; Z.x = 0.0f; }
+            if (!(epipolar_d(s.metric, e, p1.x, p1.y, p1.z, p1.w, -thr) < 0.0f)) { X.y = 0.0f; Y.y = 0.0f; Z.y = 0.0f; }
+        }
+        float* d = reinterpret_cast<float*>(dst);
+        if (2 * j + 1 < n) {
+            *reinterpret_cast<float2*>(d) = X;
+            *reinterpret_cast<float2*>(d + row) = Y;
+            *reinterpret_cast<float2*>(d + 2 * row) = Z;
+            *reinterpret_cast<float2*>(d + 3 * row) = one2;
+        } else {
+            d[0] = X.x;
+            d[row] = Y.x;
+            d[2 * row] = Z.x;
+            d[3 * row] = 1.0f;
+        }
+        dst += jstep;
+    }
+}
 #ifndef SFMB200_TRI_CTAS_PER_SM
-#define SFMB200_TRI_CTAS_PER_SM 16     // measured: 16 -> 15.3 us, 8 -> 16.4 us, one CTA per chunk -> 16.4 us at 1M points (profiles/r02_triangulation.md)
+#define SFMB200_TRI_CTAS_PER_SM 16     // grid cap; 8 are resident at 64 registers x 128 threads, the rest start as CTAs retire (measured faster than 8)
+#endif
+#ifndef SFMB200_TRI_KERNEL
+#define SFMB200_TRI_KERNEL 1           // 1: triangulate_kernel<SFMB200_TRI_PTS> (shipped), 2: triangulate_pairs_kernel (measured slower: profiles/r02_triangulation.md)
 #endif
 void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaStream_t st) {
-    constexpr int CHUNK = TRI_THREADS * SFMB200_TRI_PTS;
-    int gx = (s.n + CHUNK - 1) / CHUNK;
     int cap = (148 * SFMB200_TRI_CTAS_PER_SM + s.B - 1) / s.B;          // resident CTAs over the whole batch
     if (cap < 1) cap = 1;
+#if SFMB200_TRI_KERNEL == 2
+    int gx = ((s.n >> 1) + TRI_THREADS - 1) / TRI_THREADS;
+    if (gx < 1) gx = 1;
+    if (gx > cap) gx = cap;
+    dim3 grid(gx, s.B);
+    if (inliers_only)
+        launch_dep(triangulate_pairs_kernel<true>, grid, dim3(TRI_THREADS), 0, st, s, thr);
+    else
+        launch_dep(triangulate_pairs_kernel<false>, grid, dim3(TRI_THREADS), 0, st, s, thr);
+#else
+    constexpr int CHUNK = TRI_THREADS * SFMB200_TRI_PTS;
+    int gx = (s.n + CHUNK - 1) / CHUNK;
     if (gx > cap) gx = cap;
     dim3 grid(gx, s.B);
     if (inliers_only)
         launch_dep(triangulate_kernel<SFMB200_TRI_PTS, true>, grid, dim3(TRI_THREADS), 0, st, s, thr);
     else
         launch_dep(triangulate_kernel<SFMB200_TRI_PTS, false>, grid, dim3(TRI_THREADS), 0, st, s, thr);
+#endif
 }
 
 // ---------------------------------------------------------------------------

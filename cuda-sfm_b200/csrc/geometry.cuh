@@ -23,8 +23,7 @@ __device__ __forceinline__ void store_scaled(const DeviceState& s, size_t o, flo
     s.corr_dup[2 * o] = make_float4(x1, x1, y1, y1);
     s.corr_dup[2 * o + 1] = make_float4(x2, x2, y2, y2);
 }
-__device__ __forceinline__ void normalise_store(const DeviceState& s, int b, int i, float u1, float v1, float u2, float v2,
-                                                const Mat9& k) {
+__device__ __forceinline__ float4 normalise_point(float u1, float v1, float u2, float v2, const Mat9& k) {
     float x1 = fmaf(k.v[1], v1, fmaf(k.v[0], u1, k.v[2]));
     float y1 = fmaf(k.v[4], v1, fmaf(k.v[3], u1, k.v[5]));
     float z1 = fmaf(k.v[7], v1, fmaf(k.v[6], u1, k.v[8]));
@@ -35,9 +34,14 @@ __device__ __forceinline__ void normalise_store(const DeviceState& s, int b, int
     // float4 layout fixes z = 1, which is the same projective point.
     if (z1 != 1.0f) { x1 /= z1; y1 /= z1; }
     if (z2 != 1.0f) { x2 /= z2; y2 /= z2; }
+    return make_float4(x1, y1, x2, y2);
+}
+__device__ __forceinline__ void normalise_store(const DeviceState& s, int b, int i, float u1, float v1, float u2, float v2,
+                                                const Mat9& k) {
+    const float4 c = normalise_point(u1, v1, u2, v2, k);
     size_t o = (size_t)b * s.n_stride + i;
-    s.corr[o] = make_float4(x1, y1, x2, y2);
-    store_scaled(s, o, x1, y1, x2, y2);
+    s.corr[o] = c;
+    store_scaled(s, o, c.x, c.y, c.z, c.w);
 }
 
 // ---------------------------------------------------------------------------
@@ -48,10 +52,15 @@ __device__ __forceinline__ void normalise_store(const DeviceState& s, int b, int
 // compat = 0: textbook pose for x1^T E x2 = 0: X2 = R X1 + t, R = V W(^T) U^T, t = +-v3.
 // ---------------------------------------------------------------------------
 // Candidate c (0..3) of E into P[16].
+// Candidate c from the (oriented) SVD factors of E; v is modified.
+__device__ __forceinline__ void pose_from_svd(const float* u, float* v, int c, int compat, float* P);
 __device__ __forceinline__ void pose_candidate(const float* E, int c, int compat, float* P) {
     float u[9], sg[9], v[9];
     if (compat) svd3_reference_orientation(E, u, sg, v);     // candidate ORDER as the reference's svd() yields it
     else svd3<5>(E, u, sg, v);
+    pose_from_svd(u, v, c, compat, P);
+}
+__device__ __forceinline__ void pose_from_svd(const float* u, float* v, int c, int compat, float* P) {
     const float W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
     const float Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
     if (compat) {
@@ -106,15 +115,21 @@ __device__ __forceinline__ void dlt_matrix(float x1, float y1, float x2, float y
         A[12 + i] = fmaf(y2, M[8 + i], -M[4 + i]);
     }
 }
-// De-homogenise like normalize_pt_kernal (kernels.h:433-450): w == 0 -> origin.
+// De-homogenise like normalize_pt_kernal (kernels.h:433-450): w == 0 -> origin (as v * 0: the packed form of
+// triangulate_pairs_kernel does the same arithmetic, so both give the same bits).
 __device__ __forceinline__ void dehomogenise(const float* v, float& X, float& Y, float& Z) {
-    if (v[3] == 0.0f) { X = 0.0f; Y = 0.0f; Z = 0.0f; return; }
 #if defined(__CUDA_ARCH__)
-    float iw = __fdividef(1.0f, v[3]);      // MUFU.RCP: 1 ulp, |v| = 1
+    const float iw = v[3] == 0.0f ? 0.0f : __fdividef(1.0f, v[3]);      // MUFU.RCP: 1 ulp, |v| = 1
 #else
-    float iw = 1.0f / v[3];
+    const float iw = v[3] == 0.0f ? 0.0f : 1.0f / v[3];
 #endif
     X = v[0] * iw; Y = v[1] * iw; Z = v[2] * iw;
+}
+__device__ __forceinline__ void dehomogenise2(const float2* v, float2& X, float2& Y, float2& Z) {
+#if defined(__CUDA_ARCH__)
+    const float2 iw = make_float2(v[3].x == 0.0f ? 0.0f : __fdividef(1.0f, v[3].x), v[3].y == 0.0f ? 0.0f : __fdividef(1.0f, v[3].y));
+    X = __fmul2_rn(v[0], iw); Y = __fmul2_rn(v[1], iw); Z = __fmul2_rn(v[2], iw);
+#endif
 }
 
 // Cheirality of candidate M on correspondence c0 (reference semantics): returns

@@ -554,14 +554,10 @@ SFM_HD void sample_indices_disjoint(unsigned long long seed, unsigned long long 
 }
 
 #if defined(__CUDACC__)
-// Loads the 8 sampled correspondences of hypothesis (pair b, global index hg).
-// A sample with an out-of-range or repeated index is degenerate: returns false.
-// COHERENT: the correspondences were written earlier in the SAME kernel (small.cu): read them through L2 (ld.global.cg)
-// instead of the non-coherent read-only path.
-template <bool COHERENT = false>
-__device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int n, const int32_t* __restrict__ idx_rows,
-                                            unsigned long long seed, long long hg, Corr* pts, int sampler = 0) {
-    int id[8];
+// The 8 correspondence indices of hypothesis hg (caller's rows, or one of the two samplers); false = not 8 distinct
+// indices inside [0, n) - the hypothesis is void (E = 0) and the indices are replaced by 0.
+__device__ __forceinline__ bool sample_ids(int n, const int32_t* __restrict__ idx_rows, unsigned long long seed, long long hg,
+                                           int sampler, int* id) {
     if (idx_rows != nullptr) {
         const int4* row = reinterpret_cast<const int4*>(idx_rows + 8 * hg);
         int4 a = __ldg(row), b = __ldg(row + 1);
@@ -580,9 +576,21 @@ __device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int
         for (int j = 0; j < i; j++) ok = ok && (id[i] != id[j]);
     }
 #pragma unroll
+    for (int i = 0; i < 8; i++) id[i] = ok ? id[i] : 0;
+    return ok;
+}
+// Loads the 8 sampled correspondences of hypothesis (pair b, global index hg).
+// A sample with an out-of-range or repeated index is degenerate: returns false.
+// COHERENT: the correspondences were written earlier in the SAME kernel (small.cu): read them through L2 (ld.global.cg)
+// instead of the non-coherent read-only path.
+template <bool COHERENT = false>
+__device__ __forceinline__ bool load_sample(const float4* __restrict__ corr, int n, const int32_t* __restrict__ idx_rows,
+                                            unsigned long long seed, long long hg, Corr* pts, int sampler = 0) {
+    int id[8];
+    const bool ok = sample_ids(n, idx_rows, seed, hg, sampler, id);
+#pragma unroll
     for (int i = 0; i < 8; i++) {
-        int k = ok ? id[i] : 0;
-        float4 c = COHERENT ? __ldcg(corr + k) : __ldg(corr + k);
+        float4 c = COHERENT ? __ldcg(corr + id[i]) : __ldg(corr + id[i]);
         pts[i] = Corr{c.x, c.y, c.z, c.w};
     }
     return ok;

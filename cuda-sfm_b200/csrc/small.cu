@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
     __shared__ int sCnt[SMALL_HC_MAX];
     __shared__ unsigned long long sKey;
 
-    if (rank == 0 && tid == 0 && (a.mask & SMALL_ESTIMATE)) s.best[b] = 0ull;
     int stamp = 0;
     auto mark = [&]() {
         if (a.dbg != nullptr && rank == 0 && tid == 0 && b == 0) a.dbg[stamp] = clock64();
@@ -67,7 +66,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
     };
     mark();
 
-    // ---- ingest ----
+    // ---- ingest ----  (letting the generating warps normalise their own samples from the pixels instead of waiting for this
+    //      phase was measured: the first miss on the pixels is the latency either way, 43.75k vs 43.80k cycles in total)
     if (a.mask & SMALL_INGEST) {
         for (int i = rank * SMALL_THREADS + tid; i < n; i += stride) {
             const float4 p = __ldg(a.px + (size_t)b * n + i);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             Corr pts[8];
             float E[9];
             const bool ok = load_sample<true>(corr, n, rows, a.seed + 0x632BE59BD9B4E019ull * (unsigned long long)(s.pair0 + b),
-                                        (long long)a.h_offset + (live ? j : 0), pts, s.sampler);
+                                              (long long)a.h_offset + (live ? j : 0), pts, s.sampler);
             solve_hypothesis_projector(pts, E);
             if (live) {
                 float* out = s.Ecand + (size_t)b * 9 * s.h_stride + j;
@@ -121,12 +121,15 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         const float4* cs = s.corr_s + (size_t)b * s.n_stride;
         const int my_pts = tid < n ? (n - tid + SMALL_THREADS - 1) / SMALL_THREADS : 0;
         const int warp_pts = (tid & ~31) < n ? (n - (tid & ~31) + SMALL_THREADS - 1) / SMALL_THREADS : 0;      // lane 0's count: the warp's maximum
-        float2 px1[SMALL_PTS], py1[SMALL_PTS], px2[SMALL_PTS], py2[SMALL_PTS];
+        // a slot this thread has no point for holds zeros and SAMPSON_PAD: it can never count (sampson_unit_d2_pad)
+        float2 px1[SMALL_PTS], py1[SMALL_PTS], px2[SMALL_PTS], py2[SMALL_PTS], pad[SMALL_PTS];
 #pragma unroll
         for (int k = 0; k < SMALL_PTS; k++) {
             const float4 p = k < my_pts ? __ldcg(cs + tid + k * SMALL_THREADS) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             px1[k] = make_float2(p.x, p.x); py1[k] = make_float2(p.y, p.y);
             px2[k] = make_float2(p.z, p.z); py2[k] = make_float2(p.w, p.w);
+            const float nb = k < my_pts ? 0.0f : SAMPSON_PAD;
+            pad[k] = make_float2(nb, nb);
         }
         for (int g0 = 0; g0 < mine_pairs; g0 += SMALL_G) {
             float2 e2[SMALL_G][9];
@@ -141,12 +144,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
 #pragma unroll
             for (int k = 0; k < SMALL_PTS; k++) {
                 if (k < warp_pts) {                                        // warp-uniform: no work for slots nobody in the warp fills
-                    const unsigned int valid = k < my_pts ? 1u : 0u;
 #pragma unroll
                     for (int g = 0; g < SMALL_G; g++) {
-                        const float2 d = sampson_unit_d2(e2[g], px1[k], py1[k], px2[k], py2[k]);
-                        cnt[2 * g] += (__float_as_uint(d.x) >> 31) & valid;
-                        cnt[2 * g + 1] += (__float_as_uint(d.y) >> 31) & valid;
+                        const float2 d = sampson_unit_d2_pad(e2[g], px1[k], py1[k], px2[k], py2[k], pad[k]);
+                        cnt[2 * g] += __float_as_uint(d.x) >> 31;
+                        cnt[2 * g + 1] += __float_as_uint(d.y) >> 31;
                     }
                 }
             }
@@ -179,30 +181,47 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
                                           (unsigned long long)(0xFFFFFFFFu - (unsigned)(a.h_offset + h0 + t));
             key = kk > key ? kk : key;
         }
-        if (mine > 0) {
-            if (key != 0ull) atomicMax(&sKey, key);
-            __syncthreads();
-            if (tid == 0 && sKey != 0ull) atomicMax(&s.best[b], sKey);
+        // the CTA's best key stays in ITS shared memory: CTA 0 reads the C of them over the cluster's distributed shared
+        // memory after the barrier (no atomic round trip through L2)
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+            key = other > key ? other : key;
         }
+        if (lane == 0 && key != 0ull) atomicMax(&sKey, key);
         sub(11);
         cluster.sync();
         mark();
     }
 
-    // ---- select (+ pose candidates + cheirality) : CTA 0, 4 lanes ----
-    if ((a.mask & (SMALL_ESTIMATE | SMALL_POSE)) && rank == 0 && warp == 0) {
+    // ---- select (+ pose candidates + cheirality) : CTA 0.  Lanes 0..3 of warp 0 take one candidate each; in compat mode
+    //      the replay of the reference's SVD orientation (reference_null_direction: as long a chain as the SVD itself, and
+    //      independent of it) runs on warp 1 at the same time and is handed over through shared memory ----
+    if ((a.mask & (SMALL_ESTIMATE | SMALL_POSE)) && rank == 0) {
+        __shared__ float sNull[3];
+        const bool split = (a.mask & SMALL_POSE) && a.compat;           // uniform over the CTA
         const int c = lane;
+        const bool worker = warp == 0 && c < 4, helper = split && warp == 1 && lane == 0;
         bool pass = false;
-        if (c < 4) {
-            float E[9], P[16];
+        float E[9], P[16], u[9], sg[9], v[9];
+        // the cluster's best key: lane r of warps 0 and 1 reads CTA r's, a shuffle tree takes the maximum
+        unsigned long long cluster_key = 0ull;
+        if (warp < 2 && (a.mask & SMALL_ESTIMATE)) {
+            if (lane < C) cluster_key = *cluster.map_shared_rank(&sKey, lane);
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, cluster_key, o);
+                cluster_key = other > cluster_key ? other : cluster_key;
+            }
+        }
+        if (worker || helper) {
             if (a.mask & SMALL_ESTIMATE) {
-                const unsigned long long packed = __ldcg(&s.best[b]);
+                const unsigned long long packed = cluster_key;
                 const unsigned int hg = 0xFFFFFFFFu - (unsigned int)(packed & 0xFFFFFFFFull);
                 const int local = (int)hg - a.h_offset;
                 const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
 #pragma unroll
                 for (int k = 0; k < 9; k++) E[k] = (local >= 0 && local < s.h_stride) ? __ldcg(Eb + (size_t)k * s.h_stride + local) : 0.0f;
-                if (c == 0) {
+                if (worker && c == 0) {
+                    s.best[b] = packed;
                     s.best_idx[b] = (int)hg;
                     s.best_count[b] = (int)(packed >> 32);
 #pragma unroll
@@ -214,25 +233,41 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
             }
             sub(12);
             if (a.mask & SMALL_POSE) {
-                pose_candidate(E, c, a.compat, P);
-                sub(13);
-                if (a.compat) {
-                    const float4 c0 = __ldcg(s.corr + (size_t)b * s.n_stride);
-                    float Minv[16];
-                    pass = cheirality_compat(c0, P, Minv);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) P[i] = Minv[i];
+                if (helper) {
+                    float r[3];
+                    reference_null_direction(E, r);
+                    sNull[0] = r[0]; sNull[1] = r[1]; sNull[2] = r[2];
+                } else {
+                    svd3<5>(E, u, sg, v);
                 }
-#pragma unroll
-                for (int i = 0; i < 16; i++) s.P[(size_t)b * 64 + 16 * c + i] = P[i];
             }
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass) & 0xFu;
-        if (lane == 0 && (a.mask & SMALL_POSE) && a.compat) s.P_ind[b] = m ? 31 - __clz(m) : 0;      // last passing index (sfm.cu:284-297)
+        if (split) __syncthreads();
+        if (worker && (a.mask & SMALL_POSE)) {
+            if (split) {
+                const float r[3] = {sNull[0], sNull[1], sNull[2]};
+                svd3_orient(r, u, sg, v);
+            }
+            pose_from_svd(u, v, c, a.compat, P);
+            sub(13);
+            if (a.compat) {
+                const float4 c0 = __ldcg(s.corr + (size_t)b * s.n_stride);
+                float Minv[16];
+                pass = cheirality_compat(c0, P, Minv);
+#pragma unroll
+                for (int i = 0; i < 16; i++) P[i] = Minv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) s.P[(size_t)b * 64 + 16 * c + i] = P[i];
+        }
+        if (warp == 0) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass) & 0xFu;
+            if (lane == 0 && (a.mask & SMALL_POSE) && a.compat) s.P_ind[b] = m ? 31 - __clz(m) : 0;      // last passing index (sfm.cu:284-297)
+        }
     }
-    if (!(a.mask & SMALL_TRI)) return;
     sub(14);
-    cluster.sync();
+    cluster.sync();                       // also: no CTA leaves while CTA 0 may still read its shared memory
+    if (!(a.mask & SMALL_TRI)) return;
     mark();
 
     // ---- triangulation: same solve as triangulate_kernel ----

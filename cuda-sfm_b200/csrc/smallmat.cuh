@@ -285,10 +285,8 @@ SFM_HD void reference_null_direction(const float* a, float* v3) {
     v3[0] = V[2]; v3[1] = V[5]; v3[2] = V[8];
 }
 // svd3() with the discrete freedom fixed the way the reference's svd() fixes it (see reference_null_direction).
-SFM_HD void svd3_reference_orientation(const float* a, float* u, float* s, float* v) {
-    svd3<5>(a, u, s, v);
-    float r[3];
-    reference_null_direction(a, r);
+// (the two halves are independent until the last step: small.cu runs them on two warps)
+SFM_HD void svd3_orient(const float* r, float* u, float* s, float* v) {
     if (r[0] * v[2] + r[1] * v[5] + r[2] * v[8] < 0.0f) {
 #pragma unroll
         for (int row = 0; row < 3; row++) {
@@ -298,6 +296,12 @@ SFM_HD void svd3_reference_orientation(const float* a, float* u, float* s, float
         // s = u^T a v: negating columns 0 and 2 of both sides leaves the diagonal and flips s01, s10, s12, s21 (all ~0)
         s[1] = -s[1]; s[3] = -s[3]; s[5] = -s[5]; s[7] = -s[7];
     }
+}
+SFM_HD void svd3_reference_orientation(const float* a, float* u, float* s, float* v) {
+    svd3<5>(a, u, s, v);
+    float r[3];
+    reference_null_direction(a, r);
+    svd3_orient(r, u, s, v);
 }
 
 #ifndef SFM_PROJECT_SWEEPS
@@ -647,8 +651,8 @@ struct LaneF2 {
 // 2^6 = 64 steps per product in the last one; whatever has not converged by then has no well-defined null vector in the
 // reference's SVD either.  ~105 instructions per round, in registers, no call; a converged lane that shares a packed
 // pair with an unconverged one just gets more accurate.
-#ifndef DLT_POWER_PAIRS
-#define DLT_POWER_PAIRS 2      // fixed products with S before the first convergence check, in pairs
+#ifndef DLT_POWER_STEPS
+#define DLT_POWER_STEPS 3      // fixed products with S before the first convergence check
 #endif
 #ifndef DLT_MAX_SQUARINGS
 #define DLT_MAX_SQUARINGS 6
@@ -683,13 +687,14 @@ SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const type
             S[i][j] = L::mul(S[i][j], it);
             S[j][i] = S[i][j];
         }
+    // DLT_POWER_STEPS products with S from the start vector k3 / |.|; (w, u) = the last two iterates
     T u[4], w[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) u[i] = L::mul(k[3][i], r);
 #pragma unroll
-    for (int step = 0; step < DLT_POWER_PAIRS; step++) {
+    for (int step = 0; step < DLT_POWER_STEPS; step++) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) w[i] = L::fma(S[i][3], u[3], L::fma(S[i][2], u[2], L::fma(S[i][1], u[1], L::mul(S[i][0], u[0]))));
+        for (int i = 0; i < 4; i++) w[i] = u[i];
 #pragma unroll
         for (int i = 0; i < 4; i++) u[i] = L::fma(S[i][3], w[3], L::fma(S[i][2], w[2], L::fma(S[i][1], w[1], L::mul(S[i][0], w[0]))));
     }

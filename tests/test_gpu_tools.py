@@ -127,3 +127,29 @@ def test_bench_json_contract_reduced_extras():
     assert d["c1"]["winner"] == d["c1"]["winner_fixture_fp64"] or abs(d["c1"]["winner"][1] - d["c1"]["winner_fixture_fp64"][1]) <= 3
     assert d["roofline_triangulation"]["frac"] is not None and d["c4"]["pairs"] >= 1
     assert d["sustained"]["wall_s"] >= 1.5 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_bench_reference_arm_survives_a_dying_reference():
+    """bench.py --impl reference: the reference's CUDA path exit()s its process on any CUDA error (common.cu:14), so it runs in a
+    child that is retried; when every attempt dies the arm still prints its ONE line, from the oracle port, and says why."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libsfm_ref.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/libsfm_ref.so not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, SFMB200_BENCH_REF_CRASH="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = [l for l in r.stdout.strip().splitlines() if l.strip()]
+    assert len(out) == 1, out[:3]
+    d = json.loads(out[0])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert "died three times" in d["config"]["note"] and r.stderr.count("reference child attempt") == 3
+    # and the healthy path: one line, the reference itself, first or second attempt
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = [l for l in r.stdout.strip().splitlines() if l.strip()]
+    assert len(out) == 1, out[:3]
+    d = json.loads(out[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert 1 <= d["attempts"] <= 3 and d["config"]["workload"].startswith("BASELINE config 2")
