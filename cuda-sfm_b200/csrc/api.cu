@@ -160,7 +160,6 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_corr = carve(B * s.n_stride * sizeof(float4));
     size_t o_cs = carve(B * s.n_stride * sizeof(float4));
-    size_t o_dup = carve(B * s.n_stride * 2 * sizeof(float4));
     size_t o_ec = carve(B * 9 * (size_t)s.h_stride * sizeof(float));
     size_t o_cnt = carve(B * (size_t)s.h_stride * sizeof(int));
     size_t o_td = carve(B * (size_t)s.tiles_max * sizeof(int));
@@ -191,7 +190,6 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     char* base = (char*)h->arena;
     s.corr = (float4*)(base + o_corr);
     s.corr_s = (float4*)(base + o_cs);
-    s.corr_dup = (float4*)(base + o_dup);
     s.pt_scale = make_thr_scale(1e-6f).ik;     // the reference's threshold literal (sfm.cu:220) until told otherwise
     s.px = nullptr;            // staging for pageable host input: allocated on first use (ensure_staging)
     s.Ecand = (float*)(base + o_ec);
@@ -378,7 +376,7 @@ int sfmb200_set_points_sift_filtered(sfmb200_t* h, const void* d_sift, int n, fl
 }
 // `scale` > 0: the ingest also commits a new threshold scale for the scaled copies (run_device / run_host pass the
 // scale of their threshold).  It is committed only once the arguments are validated, right before the launch that
-// writes corr_s / corr_dup with it - a failed call leaves pt_scale describing what the buffers really hold.
+// writes corr_s with it - a failed call leaves pt_scale describing what the buffers really hold.
 static int ingest_xy(sfmb200_t* h, const float* d_px, int n, float scale) {
     int rc = check_n(h, d_px, n);
     if (rc) return rc;

@@ -13,15 +13,13 @@ struct Mat9 { float v[9]; };
 // ---------------------------------------------------------------------------
 // Ingest.  X = K^-1 [u v 1]^T for both images (copy_point + 2 cublasSgemm in the
 // reference).  Writes the float4 correspondence array every later stage reads
-// and the duplicated layout the packed scoring path stages through TMA.
+// and the threshold-scaled copy the scoring kernels stage through TMA.
 // ---------------------------------------------------------------------------
-// Threshold-scaled copies for the scoring kernels (sampson.cuh): coordinates * pt_scale, plain and duplicated.
+// Threshold-scaled copy for the scoring kernels (sampson.cuh): coordinates * pt_scale.
 __device__ __forceinline__ void store_scaled(const DeviceState& s, size_t o, float x1, float y1, float x2, float y2) {
     const float k = s.pt_scale;
     x1 *= k; y1 *= k; x2 *= k; y2 *= k;
     s.corr_s[o] = make_float4(x1, y1, x2, y2);
-    s.corr_dup[2 * o] = make_float4(x1, x1, y1, y1);
-    s.corr_dup[2 * o + 1] = make_float4(x2, x2, y2, y2);
 }
 __device__ __forceinline__ float4 normalise_point(float u1, float v1, float u2, float v2, const Mat9& k) {
     float x1 = fmaf(k.v[1], v1, fmaf(k.v[0], u1, k.v[2]));

@@ -36,10 +36,9 @@ struct DeviceState {
     float Kinv[9];
     float K[9];
 
-    float pt_scale;     // 1/sqrt(thr) currently materialised in corr_s / corr_dup (sampson.cuh); 1 for the homography model
+    float pt_scale;     // 1/sqrt(thr) currently materialised in corr_s (sampson.cuh); 1 for the homography model
     float4* corr;       // [B][n_stride]   (x1,y1,x2,y2) normalised camera coords
     float4* corr_s;     // [B][n_stride]   corr * pt_scale: what the scalar scoring kernels stage
-    float4* corr_dup;   // [B][n_stride][2] (x1,x1,y1,y1),(x2,x2,y2,y2) * pt_scale for FFMA2 scoring
     float* px;          // [B][n_stride][4] staging for host pixel input (device)
     float* Ecand;       // [B][9][h_stride] SoA essential-matrix candidates
     int* counts;        // [B][h_stride] inlier count per hypothesis
@@ -69,7 +68,6 @@ inline DeviceState sub_batch(const DeviceState& s, int b0, int nb) {
     v.pair0 = s.pair0 + b0;
     v.corr += b * s.n_stride;
     v.corr_s += b * s.n_stride;
-    v.corr_dup += b * s.n_stride * 2;
     v.Ecand += b * 9 * s.h_stride;
     v.counts += b * s.h_stride;
     v.tile_done += b * s.tiles_max;
@@ -163,7 +161,7 @@ void launch_ingest_sift_filtered(const DeviceState& s, const void* d_sift, int n
                                  int* d_scratch, int* d_kept_index, cudaStream_t st);
 void launch_ingest_xy(const DeviceState& s, const float* d_px, int n, cudaStream_t st);
 void launch_ingest_normalised(const DeviceState& s, const float* d_x, int n, cudaStream_t st);
-void launch_rescale_points(const DeviceState& s, cudaStream_t st);   // corr -> corr_s, corr_dup with s.pt_scale
+void launch_rescale_points(const DeviceState& s, cudaStream_t st);   // corr -> corr_s with s.pt_scale
 void launch_hypgen(const DeviceState& s, const int32_t* d_idx, long long idx_pair_stride, int H, int h_offset,
                    unsigned long long seed, int solver, cudaStream_t st, int keep_best = 0);
 void launch_adaptive_decide(const DeviceState& s, int* d_adapt, int round_begin, int done_after, double log1mp, int last,

@@ -12,7 +12,7 @@ namespace sfmb200 {
 // E~ = D E D, D = diag(k, k, 1), the Sampson error in the scaled coordinates is error / thr, so
 //   inlier  <=>  num~^2 - den~ < 0,   num~ = x1~^T E~ x2~,  den~ = (E~ x2~)_0^2 + (E~ x2~)_1^2 + (E~^T x1~)_0^2 + (E~^T x1~)_1^2:
 // 17 FP32-pipe instructions per evaluation instead of 18 (no thr * den product).  The scoring kernels read
-// pre-scaled correspondences (DeviceState::corr_s / corr_dup) and scale each hypothesis once when it is
+// pre-scaled correspondences (DeviceState::corr_s) and scale each hypothesis once when it is
 // loaded; every other classifier calls sampson_d, which applies the same scaling per call - same operations in
 // the same order, so all of them agree bit for bit.
 struct ThrScale { float k, ik, k2; };
