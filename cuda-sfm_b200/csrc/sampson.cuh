@@ -50,20 +50,6 @@ __device__ __forceinline__ float2 sampson_unit_d2(const float2* e, float2 x1, fl
     float2 den = __ffma2_rn(l0, l0, __ffma2_rn(l1, l1, __ffma2_rn(m0, m0, __fmul2_rn(m1, m1))));
     return __ffma2_rn(num, num, make_float2(-den.x, -den.y));
 }
-// The same with a per-point term folded into the innermost product of the denominator.  nb = 0 leaves every bit as it is
-// (fma(m1, m1, +0) rounds the same product fmul does); nb = SAMPSON_PAD makes the result positive - no inlier - whatever E
-// is: how a padding slot is kept out of a count without masking it (small.cu).
-constexpr float SAMPSON_PAD = -3.0e38f;
-__device__ __forceinline__ float2 sampson_unit_d2_pad(const float2* e, float2 x1, float2 y1, float2 x2, float2 y2, float2 nb) {
-    float2 l0 = __ffma2_rn(e[0], x2, __ffma2_rn(e[1], y2, e[2]));
-    float2 l1 = __ffma2_rn(e[3], x2, __ffma2_rn(e[4], y2, e[5]));
-    float2 l2 = __ffma2_rn(e[6], x2, __ffma2_rn(e[7], y2, e[8]));
-    float2 num = __ffma2_rn(x1, l0, __ffma2_rn(y1, l1, l2));
-    float2 m0 = __ffma2_rn(e[0], x1, __ffma2_rn(e[3], y1, e[6]));
-    float2 m1 = __ffma2_rn(e[1], x1, __ffma2_rn(e[4], y1, e[7]));
-    float2 den = __ffma2_rn(l0, l0, __ffma2_rn(l1, l1, __ffma2_rn(m0, m0, __ffma2_rn(m1, m1, nb))));
-    return __ffma2_rn(num, num, make_float2(-den.x, -den.y));
-}
 // unscaled E, unscaled coordinates, nthr = -thr: the form every classifier outside the scoring kernels uses
 __device__ __forceinline__ float sampson_d(const float* e, float x1, float y1, float x2, float y2, float nthr) {
     const ThrScale t = make_thr_scale(-nthr);

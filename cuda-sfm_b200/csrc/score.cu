@@ -37,7 +37,8 @@
 #include "sampson.cuh"
 
 #ifndef SFMB200_SCORE_UNROLL
-#define SFMB200_SCORE_UNROLL 4      // points per unrolled step of the packed inner loop (swept: profiles/r01_variant_sweep.md)
+#define SFMB200_SCORE_UNROLL 2      // points per unrolled step of the packed inner loop.  With the pre-duplicated tile: 4 (profiles/
+                                    // r01_variant_sweep.md); with the broadcast-operand tile 1 / 2 / 3 / 4 / 8 -> 0.408 / 0.381 / 0.382 / 0.385 / 0.387 ms at config 2
 #endif
 
 namespace sfmb200 {

@@ -29,8 +29,7 @@ namespace sfmb200 {
 
 constexpr int SMALL_THREADS = 512;
 constexpr int SMALL_HC_MAX = 128;        // hypotheses per CTA kept in shared memory
-constexpr int SMALL_G = 2;               // hypothesis PAIRS per register group in the scoring loop
-constexpr int SMALL_PTS = 5;             // correspondences per thread held in registers while scoring (n <= 2560 without streaming)
+constexpr int SMALL_SMEM_PTS = 2560;     // correspondences per shared-memory tile while scoring (40 KB; larger n: several tiles)
 
 struct SmallArgs {
     const float4* px;        // [B][n] pixel correspondences (SMALL_INGEST)
@@ -55,6 +54,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
     __shared__ float2 sE2[SMALL_HC_MAX / 2][9];      // scaled E of the CTA's hypotheses, two per float2
     __shared__ int sCnt[SMALL_HC_MAX];
     __shared__ unsigned long long sKey;
+    __shared__ __align__(16) float4 sPts[SMALL_SMEM_PTS];   // scaled correspondences of the current tile
 
     int stamp = 0;
     auto mark = [&]() {
@@ -82,6 +82,17 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         const float4* corr = s.corr + (size_t)b * s.n_stride;
         const int32_t* rows = a.d_idx ? a.d_idx + (size_t)b * a.idx_pair_stride : nullptr;
         const int cluster_warps = C * (SMALL_THREADS / 32);
+        // warps of this CTA that generate: 0 .. gen_warps-1.  The others would idle until the barrier: they bring the first
+        // tile of scaled correspondences (written before the ingest barrier) into shared memory for the scoring phase.
+        const int blocks32 = (H + 31) >> 5;
+        const int gen_warps = min(SMALL_THREADS / 32, max(0, (blocks32 - rank + C - 1) / C));
+        const float4* cs = s.corr_s + (size_t)b * s.n_stride;
+        const int tile0 = min(n, SMALL_SMEM_PTS);
+        const bool preload = gen_warps < SMALL_THREADS / 32;
+        if (preload && warp >= gen_warps) {
+            const int loaders = SMALL_THREADS - 32 * gen_warps;
+            for (int i = tid - 32 * gen_warps; i < tile0; i += loaders) sPts[i] = __ldcg(cs + i);
+        }
         for (int k = warp * C + rank; k * 32 < H; k += cluster_warps) {
             const int j = k * 32 + lane;
             const bool live = j < H;
@@ -116,57 +127,51 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) small_path_kernel(DeviceStat
         if (tid == 0) sKey = 0ull;
         __syncthreads();
         sub(8);
-        // this thread's correspondences (tid, tid + T, ...) are loaded ONCE, pre-duplicated for the packed operands;
-        // correspondences beyond SMALL_PTS per thread (n > 2560) are streamed from L2
-        const float4* cs = s.corr_s + (size_t)b * s.n_stride;
-        const int my_pts = tid < n ? (n - tid + SMALL_THREADS - 1) / SMALL_THREADS : 0;
-        const int warp_pts = (tid & ~31) < n ? (n - (tid & ~31) + SMALL_THREADS - 1) / SMALL_THREADS : 0;      // lane 0's count: the warp's maximum
-        // a slot this thread has no point for holds zeros and SAMPSON_PAD: it can never count (sampson_unit_d2_pad)
-        float2 px1[SMALL_PTS], py1[SMALL_PTS], px2[SMALL_PTS], py2[SMALL_PTS], pad[SMALL_PTS];
+        // Thread layout: hypothesis pair p = tid / T, T = 512 / pairs threads per pair, each striding over the tile's points with
+        // the pair's E in registers for the whole phase and the point as the broadcast operand of the FFMA2s - the loop of the
+        // large-problem kernel (score.cu) at 2 hypotheses per thread: no per-group reload of E, no partial register slots.
+        const int T = mine_pairs > 0 ? SMALL_THREADS / mine_pairs : SMALL_THREADS;
+        const int my_pair = tid / T;
+        const bool active = my_pair < mine_pairs;
+        const int first = tid - my_pair * T;
+        float2 e2[9];
 #pragma unroll
-        for (int k = 0; k < SMALL_PTS; k++) {
-            const float4 p = k < my_pts ? __ldcg(cs + tid + k * SMALL_THREADS) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            px1[k] = make_float2(p.x, p.x); py1[k] = make_float2(p.y, p.y);
-            px2[k] = make_float2(p.z, p.z); py2[k] = make_float2(p.w, p.w);
-            const float nb = k < my_pts ? 0.0f : SAMPSON_PAD;
-            pad[k] = make_float2(nb, nb);
-        }
-        for (int g0 = 0; g0 < mine_pairs; g0 += SMALL_G) {
-            float2 e2[SMALL_G][9];
-            unsigned int cnt[2 * SMALL_G];
-#pragma unroll
-            for (int g = 0; g < SMALL_G; g++) {
-                const int pp = min(g0 + g, mine_pairs - 1);
-#pragma unroll
-                for (int q = 0; q < 9; q++) e2[g][q] = sE2[pp][q];
-                cnt[2 * g] = cnt[2 * g + 1] = 0u;
+        for (int q = 0; q < 9; q++) e2[q] = active ? sE2[my_pair][q] : make_float2(0.0f, 0.0f);
+        unsigned int cnt0 = 0u, cnt1 = 0u;
+        for (int c0 = 0; c0 < n; c0 += SMALL_SMEM_PTS) {
+            const int nc = min(SMALL_SMEM_PTS, n - c0);
+            if (c0 > 0 || !preload) {
+                if (c0 > 0) __syncthreads();                               // the previous tile has been consumed
+                for (int i = tid; i < nc; i += SMALL_THREADS) sPts[i] = __ldcg(cs + c0 + i);
+                __syncthreads();
             }
+            if (active) {
+                int i = first;
+                for (; i + 3 * T < nc; i += 4 * T) {
 #pragma unroll
-            for (int k = 0; k < SMALL_PTS; k++) {
-                if (k < warp_pts) {                                        // warp-uniform: no work for slots nobody in the warp fills
-#pragma unroll
-                    for (int g = 0; g < SMALL_G; g++) {
-                        const float2 d = sampson_unit_d2_pad(e2[g], px1[k], py1[k], px2[k], py2[k], pad[k]);
-                        cnt[2 * g] += __float_as_uint(d.x) >> 31;
-                        cnt[2 * g + 1] += __float_as_uint(d.y) >> 31;
+                    for (int u = 0; u < 4; u++) {
+                        const float4 p = sPts[i + u * T];
+                        const float2 d = sampson_unit_d2(e2, make_float2(p.x, p.x), make_float2(p.y, p.y), make_float2(p.z, p.z),
+                                                         make_float2(p.w, p.w));
+                        cnt0 += __float_as_uint(d.x) >> 31;
+                        cnt1 += __float_as_uint(d.y) >> 31;
                     }
                 }
-            }
-            for (int i = tid + SMALL_PTS * SMALL_THREADS; i < n; i += SMALL_THREADS) {
-                const float4 p = __ldcg(cs + i);
-                const float2 x1 = make_float2(p.x, p.x), y1 = make_float2(p.y, p.y), x2 = make_float2(p.z, p.z), y2 = make_float2(p.w, p.w);
-#pragma unroll
-                for (int g = 0; g < SMALL_G; g++) {
-                    const float2 d = sampson_unit_d2(e2[g], x1, y1, x2, y2);
-                    cnt[2 * g] += __float_as_uint(d.x) >> 31;
-                    cnt[2 * g + 1] += __float_as_uint(d.y) >> 31;
+                for (; i < nc; i += T) {
+                    const float4 p = sPts[i];
+                    const float2 d = sampson_unit_d2(e2, make_float2(p.x, p.x), make_float2(p.y, p.y), make_float2(p.z, p.z),
+                                                     make_float2(p.w, p.w));
+                    cnt0 += __float_as_uint(d.x) >> 31;
+                    cnt1 += __float_as_uint(d.y) >> 31;
                 }
             }
-#pragma unroll
-            for (int g = 0; g < 2 * SMALL_G; g++) {
-                const unsigned int w = __reduce_add_sync(0xFFFFFFFFu, cnt[g]);
-                const int hh = 2 * g0 + g;
-                if (lane == 0 && (g0 + (g >> 1)) < mine_pairs && hh < mine && w) atomicAdd(&sCnt[hh], (int)w);
+        }
+        {   // the T threads of a pair: lanes of a warp that share the pair add up by REDUX, one shared atomic per warp and pair
+            const unsigned int grp = __match_any_sync(0xFFFFFFFFu, active ? my_pair : -1);
+            const unsigned int w0 = __reduce_add_sync(grp, cnt0), w1 = __reduce_add_sync(grp, cnt1);
+            if (active && lane == __ffs(grp) - 1) {
+                if (w0) atomicAdd(&sCnt[2 * my_pair], (int)w0);
+                if (w1 && 2 * my_pair + 1 < mine) atomicAdd(&sCnt[2 * my_pair + 1], (int)w1);
             }
         }
         sub(9);
