@@ -469,10 +469,16 @@ static void launch_score_const(const DeviceState& s, const ScorePlan& plan, int 
 // more reuse, at the price of registers (occupancy) and coarser tiles.
 // Measured on B200 (profiles/): scalar FFMA with 8 hypotheses per thread is the
 // fastest at scale; the small-tile kernels serve small hypothesis counts.
+#ifndef SFMB200_V4_MINB
+#define SFMB200_V4_MINB 1      // resident CTAs per SM the default packed variant is compiled for (2 = 128-register cap: measured slower)
+#endif
+#ifndef SFMB200_V8_MINB
+#define SFMB200_V8_MINB 2
+#endif
 struct ScoreVariant { int hpt; int packed; int threads; int minb; };
 static const ScoreVariant kVariants[] = {
-    {2, 0, 256, 1}, {4, 1, 256, 1}, {4, 0, 256, 1}, {8, 0, 256, 2}, {8, 1, 256, 1},
-    {4, 0, 128, 1}, {4, 1, 128, 1}, {8, 0, 128, 4}, {8, 1, 128, 2}, {2, 0, 128, 1},
+    {2, 0, 256, 1}, {4, 1, 256, 1}, {4, 0, 256, 1}, {8, 0, 256, 2}, {8, 1, 256, SFMB200_V4_MINB},
+    {4, 0, 128, 1}, {4, 1, 128, 1}, {8, 0, 128, 4}, {8, 1, 128, SFMB200_V8_MINB}, {2, 0, 128, 1},
     {CONST_HPT, 0, CONST_THREADS, CONST_MINB},      // 10: constant-bank path (score_const_kernel)
     {8, 1, 128, 3},                                 // 11: packed, three 128-thread CTAs per SM = 3 warps per scheduler (<= 168 registers)
 };
@@ -501,11 +507,11 @@ static int occupancy_one() {
         case 1: CALL(4, true, 256, 1); break;        \
         case 2: CALL(4, false, 256, 1); break;       \
         case 3: CALL(8, false, 256, 2); break;       \
-        case 4: CALL(8, true, 256, 1); break;        \
+        case 4: CALL(8, true, 256, SFMB200_V4_MINB); break;        \
         case 5: CALL(4, false, 128, 1); break;       \
         case 6: CALL(4, true, 128, 1); break;        \
         case 7: CALL(8, false, 128, 4); break;       \
-        case 8: CALL(8, true, 128, 2); break;        \
+        case 8: CALL(8, true, 128, SFMB200_V8_MINB); break;        \
         case 11: CALL(8, true, 128, 3); break;       \
         default: CALL(2, false, 128, 1); break;      \
     }
