@@ -659,14 +659,17 @@ def run_reference(args):
         # (SURVEY Q9-Q13), so a run of it can die: it runs in a child process, is retried, and only then replaced by the port.
         import subprocess
         last = ""
-        for attempt in range(3):
+        ATTEMPTS = 6
+        for attempt in range(ATTEMPTS):
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-child", "--gpus", str(args.gpus),
                                 "--steps", str(args.steps), "--warmup", str(args.warmup)], capture_output=True, text=True,
                                env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
             rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
             if r.returncode == 0 and rows:
                 line = json.loads(rows[-1])
-                line["attempts"] = attempt + 1
+                line["attempts"] = attempt + 1          # attempts - 1 children died in the reference's own code (see stderr)
+                if attempt:
+                    line["died_before"] = last
                 emit(line)
                 return
             last = (r.stderr.strip().splitlines() or ["no output"])[-1][:200]
@@ -675,7 +678,7 @@ def run_reference(args):
         cpu = cpu_baseline(O, x)
         line = dict(base, value=cpu["value"], steps=1, warmup=0, ms_per_step=1e3 * N_HYP * N_CORR / cpu["value"],
                     config={"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "threshold": THR, "seed": SEED,
-                            "note": f"estimateE on the host cores (oracle port): the reference's CUDA path died three times on this box ({last})"},
+                            "note": f"estimateE on the host cores (oracle port): the reference's CUDA path died {ATTEMPTS} times in a row on this box ({last})"},
                     cpu_baseline=cpu, e2e={"value": cpu["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         emit(line)
         return

@@ -142,7 +142,7 @@ def test_bench_reference_arm_survives_a_dying_reference():
     assert len(out) == 1, out[:3]
     d = json.loads(out[0])
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
-    assert "died three times" in d["config"]["note"] and r.stderr.count("reference child attempt") == 3
+    assert "times in a row" in d["config"]["note"] and r.stderr.count("reference child attempt") == 6
     # and the healthy path: one line, the reference itself, first or second attempt
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=900)
@@ -152,4 +152,4 @@ def test_bench_reference_arm_survives_a_dying_reference():
     d = json.loads(out[0])
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"]
     if d["cpu_baseline"]["kind"] == "reference":
-        assert 1 <= d["attempts"] <= 3 and d["config"]["workload"].startswith("BASELINE config 2")
+        assert 1 <= d["attempts"] <= 6 and d["config"]["workload"].startswith("BASELINE config 2")
