@@ -10,7 +10,8 @@ K, Kinv = pkg.synthetic.reference_K()
 n, H = 1 << 20, 4096
 px = pkg.synthetic.synthetic_pair(n, 0.3, 1.0, seed=77)["px"]
 d_px = torch.from_numpy(px[None]).cuda()
-h = pkg.BatchedPairs(K, Kinv, 1, n, H)
+lib = pkg.load_library(os.environ["SFMB200_LIB"]) if os.environ.get("SFMB200_LIB") else None      # an experimental build (tools/proto/explibs)
+h = pkg.BatchedPairs(K, Kinv, 1, n, H, lib=lib) if lib else pkg.BatchedPairs(K, Kinv, 1, n, H)
 h.run_device(d_px, H, 1237, 1e-6)
 for _ in range(3):
     h.triangulate()
