@@ -2,14 +2,16 @@
 // See hyp_solver.cuh for the per-hypothesis math and the reference kernels it
 // replaces (SfM/kernels.h:196-295, SfM/sfm.cu:107-129).
 //
-// Roofline: FP32 pipe.  ~5 sweeps x 36 rotations x ~80 FP32 instructions plus
-// Gram build / refinement / 3x3 SVD ~= 17 k FP32 instructions per hypothesis;
-// memory traffic is 8 gathered 16-byte correspondences (L2 hits) in and 36 B out.
+// Roofline: FP32 pipe / issue.  Default solver (8x8 Cholesky projector): ~3.6 k instructions per hypothesis (ncu: 7.42e6
+// warp instructions for 65,536 hypotheses); the 9x9 Jacobi eigensolve: ~5 sweeps x 36 rotations x ~80 FP32 instructions
+// plus Gram build / refinement / 3x3 SVD ~= 17 k.  Memory traffic is 8 gathered 16-byte correspondences (L2 hits) in and
+// 36 B out.
 #include "hyp_solver.cuh"
 #include "internal.cuh"
 
 #ifndef SFMB200_HYPGEN_MINB
-#define SFMB200_HYPGEN_MINB 4       // resident CTAs per SM the projector kernel is compiled for (A/B: profiles/r01_variant_sweep.md)
+#define SFMB200_HYPGEN_MINB 4       // resident CTAs per SM the projector kernel is compiled for (A/B: profiles/r01_variant_sweep.md;
+                                    // round 2, 96 registers without spills at 5: 18.4 vs 17.8 us at config 2, 0.140 vs 0.145 ms on a config-4 slice)
 #endif
 
 namespace sfmb200 {
