@@ -231,7 +231,7 @@ int sfmb200_create(const float K[9], const float Kinv[9], int pairs, int max_poi
     h->tri_inliers_only = 0;
     h->pipeline_chunks = -1;
     h->small_path = -1;
-    h->small_evals = 6000000;      // crossover with the five-launch path on B200 (profiles/r02_small_path.md)
+    h->small_evals = 2500000;      // crossover with the five-launch path on B200: device time ~1.5e6, call latency ~2.5e6 (profiles/r02_small_path.md)
     *out = h;
     return SFMB200_OK;
 }
@@ -456,12 +456,16 @@ static ScorePlan plan_essential(const sfmb200_handle* h, int n, int H) {
 // The fused single-launch path (small.cu) serves essential-matrix estimates with the projector solver whose
 // hypotheses fit one cluster's shared memory; `pose`: the call also runs the pose stage, which the fused kernel
 // implements in reference (compat) semantics only.  Not used while per-stage events are being recorded.
+constexpr int SMALL_PATH_MAX_PAIRS = 4;
 static bool small_path_ok(const sfmb200_handle* h, int H, bool pose) {
     if (h->small_path == 0 || h->profile || h->hyp_solver != 1 || h->s.skip != nullptr || h->s.metric != 0) return false;
     if (h->score_variant >= 0 && h->small_path != 1) return false;      // the caller asked for a specific scoring kernel
     if (pose && !h->compat) return false;
     if (H > small_path_max_hypotheses()) return false;
     if (h->small_path == 1) return true;
+    // automatic: one 16-CTA cluster per pair fills a GPC, so beyond a handful of pairs the clusters queue up behind each other
+    // while the general path's kernels spread every pair over the whole GPU (measured: 4 pairs 28.7 vs 30.7 us, 8 pairs 50 vs 35 us)
+    if (h->s.B > SMALL_PATH_MAX_PAIRS) return false;
     return (long long)h->s.n * (long long)H <= h->small_evals;
 }
 

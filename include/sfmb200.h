@@ -61,7 +61,7 @@ typedef enum {
                                       triangulation; same bits as the five-launch path): -1 (default) when n * H is at most
                                       SFMB200_OPT_SMALL_PATH_EVALS, 0 never, 1 whenever eligible (projector solver,
                                       H <= 128 * cluster size, reference pose semantics, no per-stage profiling) */
-    SFMB200_OPT_SMALL_PATH_EVALS = 8, /* the n * H limit of the automatic choice (default 6,000,000) */
+    SFMB200_OPT_SMALL_PATH_EVALS = 8, /* the n * H limit of the automatic choice (default 2,500,000; the automatic choice also needs <= 4 pairs per handle) */
     SFMB200_OPT_BATCH_PIPELINE = 11, /* whole-path calls on a batch: cut the pairs into this many chunks and generate the hypotheses
                                       of later chunks on a side stream while earlier chunks are scored (same bits): 2..16 chunks;
                                       -1 (default), 0, 1: off - measured on B200 the co-resident generation only time-shares the

@@ -85,7 +85,13 @@ def test_fused_path_host_entry_and_dispatch(pkg, O):
     h.set_option(8, 1000)
     h.run_host(px, H, 3, THR)
     assert h.score_plan()["variant"] >= 0
-    h.set_option(8, 6000000)
+    h.set_option(8, 2500000)
+    # the automatic choice is for a handful of pairs: a 16-CTA cluster per pair fills a GPC, many pairs queue up behind each other
+    for pairs, fused in ((4, True), (8, False)):
+        hb = pkg.BatchedPairs(K, Kinv, pairs, n, H)
+        hb.run_host(np.stack([px] * pairs), H, 3, THR)
+        assert (hb.score_plan()["variant"] == -2) == fused, pairs
+        hb.close()
     # not eligible: Jacobi solver, explicit scoring variant, textbook pose mode, more hypotheses than a cluster holds
     for opt, val in ((5, 0), (2, 0), (1, 0)):
         h.set_option(opt, val)
