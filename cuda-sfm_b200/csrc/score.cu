@@ -538,11 +538,15 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override, int sms) {
     if (variant_override >= 0 && variant_override < kNumVariants) {
         p.variant = variant_override;
     } else {
-        // Measured on B200 (profiles/): packed FFMA2 with 8 hypotheses per thread and one
-        // 256-thread CTA per SM is the fastest at every large shape; smaller tiles only
-        // when H cannot fill a 2048 tile.  The constant-bank kernel (variant 10) is never
-        // chosen automatically: see the note above score_const_kernel.
-        p.variant = H >= 1536 ? 4 : (H >= 768 ? 1 : (H >= 384 ? 6 : 9));
+        // Measured on B200 (profiles/r02_score_variants.md, tools/score_plan_sweep.py): packed FFMA2 with 8 hypotheses per
+        // thread and one 256-thread CTA per SM (4) is the fastest at every large shape; below ~1e8 evaluations per launch the
+        // kernel is latency- rather than throughput-bound and the 512-hypothesis tile (6), below ~3e7 the 256-hypothesis
+        // scalar tile (9) win by up to 24 %.  The constant-bank kernel (variant 10) is never chosen automatically: see the
+        // note above score_const_kernel.
+        const double W = (double)B * (double)n * (double)H;       // evaluations per launch
+        if (H >= 1536) p.variant = W >= 1.2e8 ? 4 : 6;
+        else if (H >= 768) p.variant = W >= 2e8 ? 1 : (W >= 3e7 ? 6 : 9);
+        else p.variant = W >= 3e7 ? 6 : 9;
     }
     const ScoreVariant& v = kVariants[p.variant];
     p.hyp_per_cta = v.hpt * v.threads;
