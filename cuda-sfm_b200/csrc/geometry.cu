@@ -189,29 +189,51 @@ __global__ void choose_pose_compat_kernel(DeviceState s) {
 
 // Whole-path fusion of select + pose candidates + (compat) cheirality: the three
 // are each a few microseconds of latency-bound work, so as separate launches the
-// gaps cost more than the math.  4 lanes per pair.
-__global__ void select_pose_choose_kernel(DeviceState s, int h_offset, int compat) {
+// gaps cost more than the math.  A CTA of two warps serves SPC_PAIRS pairs: warp 0 holds 4 lanes per pair (one pose
+// candidate each: 3x3 SVD of E, candidate, cheirality), warp 1 one lane per pair for the replay of the reference's SVD
+// orientation (reference_null_direction: as long a dependent chain as the SVD and independent of it), handed over through
+// shared memory - the two chains run side by side instead of one after the other (small.cu does the same).
+constexpr int SPC_PAIRS = 8;
+__global__ void __launch_bounds__(64) select_pose_choose_kernel(DeviceState s, int h_offset, int compat) {
     pdl_wait();
     pdl_trigger();
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    int b = g >> 2, c = g & 3;
-    bool active = b < s.B;
+    __shared__ float sNull[SPC_PAIRS][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp == 0 ? lane >> 2 : lane;           // pair slot inside the CTA
+    const int c = lane & 3;                                   // candidate (warp 0)
+    const int b = blockIdx.x * SPC_PAIRS + slot;
+    const bool worker = warp == 0 && b < s.B;
+    const bool helper = warp == 1 && compat && lane < SPC_PAIRS && b < s.B;
     bool pass = false;
-    if (active) {
+    float E[9], P[16], u[9], sg[9], v[9];
+    if (worker || helper) {
         unsigned long long packed = s.best[b];
         unsigned int hg = 0xFFFFFFFFu - (unsigned int)(packed & 0xFFFFFFFFull);
         int local = (int)hg - h_offset;
         const float* Eb = s.Ecand + (size_t)b * 9 * s.h_stride;
-        float E[9], P[16];
 #pragma unroll
         for (int k = 0; k < 9; k++) E[k] = (local >= 0 && local < s.h_stride) ? Eb[(size_t)k * s.h_stride + local] : 0.0f;
-        if (c == 0) {
+        if (worker && c == 0) {
             s.best_idx[b] = (int)hg;
             s.best_count[b] = (int)(packed >> 32);
 #pragma unroll
             for (int k = 0; k < 9; k++) s.E[(size_t)b * 9 + k] = E[k];
         }
-        pose_candidate(E, c, compat, P);
+        if (helper) {
+            float r[3];
+            reference_null_direction(E, r);
+            sNull[slot][0] = r[0]; sNull[slot][1] = r[1]; sNull[slot][2] = r[2];
+        } else {
+            svd3<5>(E, u, sg, v);
+        }
+    }
+    __syncthreads();
+    if (worker) {
+        if (compat) {
+            const float r[3] = {sNull[slot][0], sNull[slot][1], sNull[slot][2]};
+            svd3_orient(r, u, sg, v);
+        }
+        pose_from_svd(u, v, c, compat, P);
         if (compat) {
             float4 c0 = s.corr[(size_t)b * s.n_stride];
             float Minv[16];
@@ -222,15 +244,16 @@ __global__ void select_pose_choose_kernel(DeviceState s, int h_offset, int compa
 #pragma unroll
         for (int i = 0; i < 16; i++) s.P[(size_t)b * 64 + 16 * c + i] = P[i];
     }
-    unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-    if (active && c == 0 && compat) {
-        unsigned mine = (m >> ((threadIdx.x & 31) & ~3)) & 0xFu;
-        s.P_ind[b] = mine ? 31 - __clz(mine) : 0;
+    if (warp == 0) {
+        unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+        if (worker && c == 0 && compat) {
+            unsigned mine = (m >> (lane & ~3)) & 0xFu;
+            s.P_ind[b] = mine ? 31 - __clz(mine) : 0;
+        }
     }
 }
 void launch_select_pose_choose(const DeviceState& s, int h_offset, int compat, cudaStream_t st) {
-    int threads = 4 * s.B;
-    launch_dep(select_pose_choose_kernel, dim3((threads + 63) / 64), dim3(64), 0, st, s, h_offset, compat);
+    launch_dep(select_pose_choose_kernel, dim3((s.B + SPC_PAIRS - 1) / SPC_PAIRS), dim3(64), 0, st, s, h_offset, compat);
 }
 
 // compat = 0: every inlier of the selected E votes for the candidates that put it in front of both cameras.
