@@ -565,7 +565,12 @@ ScorePlan make_score_plan(int B, int n, int H, int variant_override, int sms) {
 // Homography model: the same kernel with the transfer-error test; three tile sizes are enough
 // (thr here is the SQUARED pixel / coordinate threshold).
 ScorePlan make_score_plan_homography(int B, int n, int H, int sms) {
+#ifdef SFMB200_HOMOG_PLAN_BY_H      // the rule before the sweep (A/B)
     return make_score_plan(B, n, H, H >= 1536 ? 4 : (H >= 384 ? 6 : 9), sms);     // tiles of 2048 / 512 / 256 hypotheses
+#else
+    const double W = (double)B * (double)n * (double)H;      // same reading as make_score_plan: small launches are latency-bound
+    return make_score_plan(B, n, H, H >= 1536 ? (W >= 1.2e8 ? 4 : 6) : (W >= 3e7 ? 6 : 9), sms);
+#endif
 }
 // The other two models (homography transfer error; symmetric epipolar distance) in the three tile sizes of
 // make_score_plan_homography.
