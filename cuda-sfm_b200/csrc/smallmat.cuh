@@ -658,6 +658,62 @@ struct LaneF2 {
 #define DLT_MAX_SQUARINGS 6
 #endif
 constexpr float DLT_SIN2_CONVERGED = 5e-7f;      // angle between the last two iterates below 7e-4
+// The refinement rounds, out of line: the common path (every point converged after the fixed steps) keeps nothing alive
+// for them - no spills at 64 registers in triangulate_kernel, 5 % off its time per point at large n - and only a thread
+// whose pair needs them pays the call and the copies to the stack.
+#if defined(__CUDACC__)
+#define SFM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define SFM_HD_NOINLINE
+#endif
+template <class L>
+SFM_HD_NOINLINE void dlt_refine_rounds(typename L::T (&S)[4][4], typename L::T* u, typename L::T* w) {
+    typedef typename L::T T;
+    T r, it;
+    {
+        typename L::M done = L::none();
+#pragma unroll 1
+        for (int round = 0; round < DLT_MAX_SQUARINGS; round++) {
+            const T ww = L::fma(w[3], w[3], L::fma(w[2], w[2], L::fma(w[1], w[1], L::mul(w[0], w[0]))));
+            const T uu = L::fma(u[3], u[3], L::fma(u[2], u[2], L::fma(u[1], u[1], L::mul(u[0], u[0]))));
+            const T wu = L::fma(w[3], u[3], L::fma(w[2], u[2], L::fma(w[1], u[1], L::mul(w[0], u[0]))));
+            const T den = L::mul(ww, uu);
+            // a lane that has converged is frozen for good: the result of a point never depends on the point it shares
+            // a packed pair with
+            done = L::join(done, L::below(L::fma(L::neg(wu), wu, den), L::mul(den, L::splat(DLT_SIN2_CONVERGED))));
+            if (L::all(done)) break;
+            T Q[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = i; j < 4; j++)
+                    Q[i][j] = L::fma(S[i][3], S[3][j], L::fma(S[i][2], S[2][j], L::fma(S[i][1], S[1][j], L::mul(S[i][0], S[0][j]))));
+            r = L::rsqrt_scale(L::add(L::add(Q[0][0], Q[1][1]), L::add(Q[2][2], Q[3][3])));
+            it = L::mul(r, r);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = i; j < 4; j++) {
+                    S[i][j] = L::mul(Q[i][j], it);
+                    S[j][i] = S[i][j];
+                }
+            // keep |u| near 1 (two products shrink it by up to 16x per round)
+            const T ru = L::rsqrt_scale(uu);
+            T un[4], wn[4], u2[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) un[i] = L::mul(u[i], ru);
+#pragma unroll
+            for (int i = 0; i < 4; i++) wn[i] = L::fma(S[i][3], un[3], L::fma(S[i][2], un[2], L::fma(S[i][1], un[1], L::mul(S[i][0], un[0]))));
+#pragma unroll
+            for (int i = 0; i < 4; i++) u2[i] = L::fma(S[i][3], wn[3], L::fma(S[i][2], wn[2], L::fma(S[i][1], wn[1], L::mul(S[i][0], wn[0]))));
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                w[i] = L::keep(done, w[i], wn[i]);
+                u[i] = L::keep(done, u[i], u2[i]);
+            }
+        }
+    }
+}
 template <class L>
 SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const typename L::T* a, const typename L::T* b, typename L::T* v,
                                   bool refine = true) {
@@ -699,46 +755,23 @@ SFM_HD void dlt_null_power4_lanes(typename L::T x1, typename L::T y1, const type
         for (int i = 0; i < 4; i++) u[i] = L::fma(S[i][3], w[3], L::fma(S[i][2], w[2], L::fma(S[i][1], w[1], L::mul(S[i][0], w[0]))));
     }
     if (refine) {
-        typename L::M done = L::none();
-#pragma unroll 1
-        for (int round = 0; round < DLT_MAX_SQUARINGS; round++) {
-            const T ww = L::fma(w[3], w[3], L::fma(w[2], w[2], L::fma(w[1], w[1], L::mul(w[0], w[0]))));
-            const T uu = L::fma(u[3], u[3], L::fma(u[2], u[2], L::fma(u[1], u[1], L::mul(u[0], u[0]))));
-            const T wu = L::fma(w[3], u[3], L::fma(w[2], u[2], L::fma(w[1], u[1], L::mul(w[0], u[0]))));
-            const T den = L::mul(ww, uu);
-            // a lane that has converged is frozen for good: the result of a point never depends on the point it shares
-            // a packed pair with
-            done = L::join(done, L::below(L::fma(L::neg(wu), wu, den), L::mul(den, L::splat(DLT_SIN2_CONVERGED))));
-            if (L::all(done)) break;
-            T Q[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = i; j < 4; j++)
-                    Q[i][j] = L::fma(S[i][3], S[3][j], L::fma(S[i][2], S[2][j], L::fma(S[i][1], S[1][j], L::mul(S[i][0], S[0][j]))));
-            r = L::rsqrt_scale(L::add(L::add(Q[0][0], Q[1][1]), L::add(Q[2][2], Q[3][3])));
-            it = L::mul(r, r);
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = i; j < 4; j++) {
-                    S[i][j] = L::mul(Q[i][j], it);
-                    S[j][i] = S[i][j];
-                }
-            // keep |u| near 1 (two products shrink it by up to 16x per round)
-            const T ru = L::rsqrt_scale(uu);
-            T un[4], wn[4], u2[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) un[i] = L::mul(u[i], ru);
-#pragma unroll
-            for (int i = 0; i < 4; i++) wn[i] = L::fma(S[i][3], un[3], L::fma(S[i][2], un[2], L::fma(S[i][1], un[1], L::mul(S[i][0], un[0]))));
-#pragma unroll
-            for (int i = 0; i < 4; i++) u2[i] = L::fma(S[i][3], wn[3], L::fma(S[i][2], wn[2], L::fma(S[i][1], wn[1], L::mul(S[i][0], wn[0]))));
+        // the first convergence check inline; the rounds themselves out of line and only for a pair that needs them
+        const T ww = L::fma(w[3], w[3], L::fma(w[2], w[2], L::fma(w[1], w[1], L::mul(w[0], w[0]))));
+        const T uu = L::fma(u[3], u[3], L::fma(u[2], u[2], L::fma(u[1], u[1], L::mul(u[0], u[0]))));
+        const T wu = L::fma(w[3], u[3], L::fma(w[2], u[2], L::fma(w[1], u[1], L::mul(w[0], u[0]))));
+        const T den = L::mul(ww, uu);
+        if (!L::all(L::below(L::fma(L::neg(wu), wu, den), L::mul(den, L::splat(DLT_SIN2_CONVERGED))))) {
+            // copies whose address escapes: S, u, w themselves stay in registers on the common path
+            T Sc[4][4], uc[4], wc[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                w[i] = L::keep(done, w[i], wn[i]);
-                u[i] = L::keep(done, u[i], u2[i]);
+                uc[i] = u[i]; wc[i] = w[i];
+#pragma unroll
+                for (int j = 0; j < 4; j++) Sc[i][j] = S[i][j];
             }
+            dlt_refine_rounds<L>(Sc, uc, wc);
+#pragma unroll
+            for (int i = 0; i < 4; i++) u[i] = uc[i];
         }
     }
 #pragma unroll

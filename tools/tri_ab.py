@@ -20,7 +20,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         a.record(); tiny.fill_(1.0); b.record(); torch.cuda.synchronize()
         fl.append(a.elapsed_time(b))
     print(json.dumps(dict(lib=os.path.basename(path), empty_launch_ms_median=sorted(fl)[15], empty_launch_ms_min=min(fl))), flush=True)
-    for n in (1 << 20, 1 << 22, 1 << 24, 10001):
+    for n in (1 << 20, 1 << 24):
         H = 4096
         px = pkg.synthetic.synthetic_pair(n, 0.3, 1.0, seed=77)["px"]
         d_px = torch.from_numpy(px[None]).cuda()
