@@ -520,7 +520,7 @@ void launch_triangulate(const DeviceState& s, int inliers_only, float thr, cudaS
 #else
     constexpr int CHUNK = TRI_THREADS * SFMB200_TRI_PTS;
     int gx = (s.n + CHUNK - 1) / CHUNK;
-    if (gx > cap) gx = cap;
+    if (gx > cap) gx = cap;      // (a grid of only-resident CTAs with equal shares was measured: 10.5 vs 9.8 us at 1M, 127 vs 121 us at 16M points)
     dim3 grid(gx, s.B);
     if (inliers_only)
         launch_dep(triangulate_kernel<SFMB200_TRI_PTS, true>, grid, dim3(TRI_THREADS), 0, st, s, thr);
