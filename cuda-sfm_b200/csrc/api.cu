@@ -351,6 +351,7 @@ int sfmb200_set_points_sift(sfmb200_t* h, const void* d_sift, int n) {
     CKL();
     h->launches++;
     h->have_points = true;
+    h->have_chain = false;       // the chained reconstruction belonged to the previous correspondences
     return SFMB200_OK;
 }
 int sfmb200_set_points_sift_filtered(sfmb200_t* h, const void* d_sift, int n, float min_score, float max_ambiguity,
@@ -372,6 +373,7 @@ int sfmb200_set_points_sift_filtered(sfmb200_t* h, const void* d_sift, int n, fl
     if (kept < 8) return fail(SFMB200_ERR_STATE, "fewer than 8 correspondences survive the match filter%s");
     h->s.n = kept;
     h->have_points = true;
+    h->have_chain = false;       // the chained reconstruction belonged to the previous correspondences
     return SFMB200_OK;
 }
 // `scale` > 0: the ingest also commits a new threshold scale for the scaled copies (run_device / run_host pass the
@@ -388,6 +390,7 @@ static int ingest_xy(sfmb200_t* h, const float* d_px, int n, float scale) {
     CKL();
     h->launches++;
     h->have_points = true;
+    h->have_chain = false;       // the chained reconstruction belonged to the previous correspondences
     return SFMB200_OK;
 }
 int sfmb200_set_points_xy(sfmb200_t* h, const float* d_px, int n) {
@@ -428,6 +431,7 @@ int sfmb200_set_points_normalised(sfmb200_t* h, const float* d_x, int n) {
     CKL();
     h->launches++;
     h->have_points = true;
+    h->have_chain = false;       // the chained reconstruction belonged to the previous correspondences
     return SFMB200_OK;
 }
 
@@ -1059,6 +1063,8 @@ static int run_stages(sfmb200_t* h, int H, uint64_t seed, float thr) {
     }
     prof_mark(h, 6);
     h->have_candidates = h->have_E = h->have_pose = true;
+    h->have_chain = false;        // a new reconstruction: what chain_views left is stale
+    h->model = 0;                 // s.E is an essential matrix again (find_homography may have run on this handle before)
     return sfmb200_triangulate(h);
 }
 
@@ -1084,6 +1090,7 @@ static int run_small(sfmb200_t* h, const float* d_px, int n, int H, uint64_t see
     h->plan.variant = -2;
     h->launches += 1;
     h->have_points = h->have_candidates = h->have_E = h->have_pose = true;
+    h->have_chain = false;
     return 1;
 }
 

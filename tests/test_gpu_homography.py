@@ -126,3 +126,32 @@ def test_homography_pixel_semantics_with_real_intrinsics(pkg, O):
         hb.find_homography(loops, seed, thresh)
     for h in (hp, hk, hb):
         h.close()
+
+
+@pytest.mark.parametrize("n,H", [(1500, 300), (6000, 2048)])        # fused small-problem path / general five-launch path
+def test_whole_path_after_homography_is_an_essential_estimate_again(pkg, O, n, H):
+    """find_homography leaves a homography in the handle (the pose stages refuse it); a whole-path run afterwards must put the
+    handle back into the essential-matrix state - inlier colouring, refit and the pose getters work, and the result equals a
+    fresh handle's bit for bit.  (The general path once kept the stale model flag.)"""
+    import torch
+
+    K, Kinv = O.reference_K()
+    px = O.synthetic_pair(n, seed=31)["px"]
+    d_px = torch.from_numpy(px[None]).cuda()
+    fresh = pkg.BatchedPairs(K, Kinv, 1, n, max(H, 1024))
+    fresh.run_device(d_px, H, 9, 1e-6)
+    h = pkg.BatchedPairs(K, Kinv, 1, n, max(H, 1024))
+    h.set_points_xy(d_px)
+    h.find_homography(1024, 3, 5.0)
+    with pytest.raises(pkg.SfmError):
+        h.pose_candidates()
+    h.run_device(d_px, H, 9, 1e-6)
+    assert np.array_equal(h.get_E(), fresh.get_E()) and np.array_equal(h.get_points_host(0), fresh.get_points_host(0))
+    assert np.array_equal(h.get_best()[1], fresh.get_best()[1]) and np.array_equal(h.get_pose_index(), fresh.get_pose_index())
+    pos = torch.empty((n, 4), device="cuda")
+    col = torch.empty((n, 4), device="cuda")
+    h.copy_to_vbo_coloured(pos, col, 0, 1.0, 1)            # needs an essential matrix: raised SFMB200_ERR_STATE before the fix
+    green = int((col[:, 1] == 1.0).sum().item())
+    assert green == int(h.get_best()[1][0])
+    h.refine_e(2)
+    h.close(); fresh.close()
