@@ -167,3 +167,50 @@ def test_handle_keeps_its_device_when_another_is_current(pkg, O):
     h1.pose_candidates(); h1.choose_pose(); h1.triangulate()
     assert np.array_equal(h1.get_points_host(0), want["points"][0])
     h1.close(); ref.close()
+
+
+@pytest.mark.parametrize("n,H", [(1200, 150), (5000, 1024)])        # fused small-problem path / general five-launch path
+def test_dirty_handle_equals_fresh_handle(pkg, O, n, H):
+    """Whatever ran on a handle before - homography, adaptive estimate, refit, bundle adjustment, chaining, another threshold,
+    another metric or sampler (reset afterwards), a slice estimate - a whole-path run gives the bits a fresh handle gives, and
+    the stages that follow it are accepted."""
+    import torch
+
+    K, Kinv = O.reference_K()
+    px = np.ascontiguousarray(pkg.synthetic.synthetic_sequence(3, n, seed=51)["px_pairs"])       # 3 views = 2 consecutive pairs
+    d_px = torch.from_numpy(px).cuda()
+    cap = max(H, 4096)
+    fresh = pkg.BatchedPairs(K, Kinv, 2, n, cap)
+    fresh.run_device(d_px, H, 21, 1e-6)
+    want = (fresh.get_E(), fresh.get_best()[0], fresh.get_best()[1], fresh.get_poses(), fresh.get_pose_index(),
+            fresh.get_points_host(0), fresh.get_points_host(1))
+
+    def check(h, what):
+        h.run_device(d_px, H, 21, 1e-6)
+        got = (h.get_E(), h.get_best()[0], h.get_best()[1], h.get_poses(), h.get_pose_index(), h.get_points_host(0), h.get_points_host(1))
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b), what
+        h.get_inlier_mask(); h.refine_e(1)                       # accepted: the handle holds an essential-matrix estimate again
+
+    h = pkg.BatchedPairs(K, Kinv, 2, n, cap)
+    h.set_points_xy(d_px)
+    h.find_homography(1024, 3, 5.0)
+    check(h, "after find_homography")
+    h.estimate_e_adaptive(4096, 5, 4e-6, 0.99)                   # another threshold: the scaled copies are re-materialised
+    h.refine_e(2)
+    h.pose_candidates(); h.choose_pose(); h.triangulate()
+    h.bundle_adjust(1, 3)
+    check(h, "after adaptive + refit + bundle adjustment at another threshold")
+    h.run_device(d_px, H, 21, 1e-6)                              # (the refit inside check() invalidated the poses)
+    ch = h.chain_views()
+    h.bundle_adjust_global(ch, iterations=2)
+    check(h, "after chaining + global bundle adjustment")
+    for opt, val, back in ((9, 1, 0), (10, 1, 0), (5, 0, 1), (1, 0, 1), (3, 1, 0)):     # metric, sampler, solver, pose mode, inliers-only
+        h.set_option(opt, val)
+        h.run_device(d_px, H, 21, 1e-6)
+        h.set_option(opt, back)
+        check(h, f"after option {opt} = {val} and back")
+    lo, hi = pkg.sharding.shard_range(H, 1, 2)
+    h.estimate_e(hi - lo, 21, 1e-6, H_total=H, h_begin=lo)
+    check(h, "after a slice estimate")
+    h.close(); fresh.close()
