@@ -82,6 +82,17 @@ int sfmb200_version(void);
 /* "src=<hash> nvcc_flags=<...>": hash of the sources this library was compiled from (cuda-sfm_b200/build.py: source_hash) */
 const char* sfmb200_build_info(void);
 
+/* ---- handle state ----
+ * A handle remembers which stages have run: a stage called before its prerequisite returns SFMB200_ERR_STATE (triangulate
+ * before the poses, poses before an estimate, chain / global bundle adjustment before chain_views ...).  What a call leaves:
+ *   set_points_*            new correspondences; a previous E / pose stays usable (e.g. triangulate other matches with a known
+ *                           pose), the chained reconstruction does not
+ *   estimate_e* / run_*     an essential-matrix estimate (run_*: also poses, pose index, points); chained reconstruction dropped
+ *   refine_e                a new E: pose_candidates / choose_pose / triangulate must run again before the stages that need a pose
+ *   bundle_adjust           refined E, selected pose and points, consistent with each other (chain_views may follow directly)
+ *   find_homography         a HOMOGRAPHY in place of E: the pose stages refuse it until the next estimate_e* / run_*
+ * Whatever ran before, estimate_e* / run_* give the bits a fresh handle gives (tests/test_gpu_edge_8f.py). */
+
 /* ---- lifetime: SfM::Image_pair::Image_pair / ~Image_pair (SfM/sfm.cu:28-78, 346-359) ---- */
 /* K, Kinv: host 3x3 row-major, as src/main.cpp:292-297 builds them. */
 int sfmb200_create(const float h_K[9], const float h_Kinv[9], int pairs, int max_points, int max_hypotheses,
